@@ -1,0 +1,83 @@
+"""Load ``tests/golden/*.npz`` (made by ``oracle/make_golden.py`` from the unmodified
+reference) and turn the stored reference kwargs into oracle specs."""
+import json
+import os
+
+import numpy as np
+import torch
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+_ENC = {
+    "PositionalEncodingNeRF": "nerf",
+    "PositionalEncodingFourier": "fourier",
+    "TriplaneEncoding": "triplane",
+    "PermutohedralEncoding": "permuto",
+}
+
+
+def load(name):
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    meta = json.loads(bytes(z["meta_json"]).decode())
+    arrays = {k: torch.from_numpy(z[k]) for k in z.files if k != "meta_json"}
+    return meta, arrays
+
+
+def encoding_kind(field_kwargs):
+    return _ENC[field_kwargs["encoding_type"].split(".")[-1]]
+
+
+def field_spec(field_kwargs):
+    from oracle import restatement as R
+
+    return R.FieldSpec(
+        encoding=encoding_kind(field_kwargs),
+        encoding_kwargs=dict(field_kwargs["encoding_kwargs"]),
+        num_layers=field_kwargs["num_layers"],
+        dim_out=field_kwargs["dim_out"],
+        dim_mlp_out=field_kwargs.get("dim_mlp_out"),
+        skip_mode=field_kwargs.get("skip_mode", "no"),
+    )
+
+
+def render_spec(meta):
+    from oracle import restatement as R
+
+    cfg = meta["config"]
+    mk = cfg["model_kwargs"]
+    rdg = cfg.get("range_depth_guided")
+    return R.RenderSpec(
+        num_samples=meta["num_samples"],
+        num_samples_depth_guided=meta.get("num_samples_depth_guided", 0),
+        range_depth_guided=cfg["truncation_distance"] if rdg is None else rdg,
+        near_distance=meta.get("near_distance", cfg["near_distance"]),
+        far_distance=meta.get("far_distance", cfg["far_distance"]),
+        truncation_distance=cfg["truncation_distance"],
+        freespace_weight=cfg["freespace_weight"],
+        tsdf_weight=cfg["tsdf_weight"],
+        geometry_mode=cfg["geometry_mode"],
+        geometry_factor=cfg["geometry_factor"],
+        color_factor=cfg["color_factor"],
+        field_radius=mk["field_radius"],
+        scale_mode=mk["scale_mode"],
+        num_knn=mk["num_knn"],
+        distance_factor=mk["distance_factor"],
+        outside_value=mk["outside_value"],
+        block_size=cfg["block_size"],
+        pixel_block_size=cfg["pixel_block_size"],
+    )
+
+
+def camera_spec(cam):
+    from oracle import restatement as R
+
+    return R.CameraSpec(**cam)
+
+
+def params(arrays, prefix="param:"):
+    return {k[len(prefix):]: v for k, v in arrays.items() if k.startswith(prefix)}
+
+
+VMAP_CASES = ["c1_vmap_256x32", "vmap_guided_nrgbd", "vmap_behind_camera", "vmap_neus",
+              "vmap_density", "vmap_occupancy", "c2_vmap_w128_s64"]
+KNN_CASES = ["knn_render", "knn_render_w128"]

@@ -1,0 +1,107 @@
+"""Pin ``oracle.restatement`` against the golden vectors produced by the UNMODIFIED
+reference (``oracle/make_golden.py``).  CPU only."""
+import pytest
+import torch
+
+import golden_util as G
+from oracle import restatement as R
+
+TOL = dict(rtol=2e-5, atol=2e-6)
+
+
+def _close(a, b, **kw):
+    kw = {**TOL, **kw}
+    assert a.shape == b.shape, (a.shape, b.shape)
+    assert torch.allclose(a, b, **kw), f"max abs diff {(a - b).abs().max().item():.3e}"
+
+
+@pytest.mark.parametrize("name", G.VMAP_CASES)
+def test_render_vmap_matches_reference(name):
+    meta, a = G.load(name)
+    fs, rs, cam = G.field_spec(meta["field_kwargs"]), G.render_spec(meta), G.camera_spec(meta["camera"])
+    p = R.render_rays(
+        a["ijs"], a["c2ws"], cam, rs, fs, G.params(a), a["positions"], a["orientations"],
+        field_ids=a["field_ids"], use_vmap=True, near_distances=a["near"].clone(),
+        far_distances=a["far"].clone(), gt_distances=a["gt"].clone() if "gt" in a else None,
+        jitter=a["jitter"], jitter_guided=a.get("jitter_guided"))
+    _close(p.rgbds, a["out_rgbds"], atol=1e-5)
+    _close(p.color_vars, a["out_color_vars"], atol=1e-5)
+    _close(p.depth_vars, a["out_depth_vars"], atol=1e-5)
+    _close(p.term_probs, a["out_term_probs"], atol=1e-5)
+    if "out_freespace" in a:
+        _close(p.freespace_geometry, a["out_freespace"], atol=1e-5)
+        _close(p.tsdf_residuals, a["out_tsdf"], atol=1e-5)
+    # fixtures must be non-degenerate to mean anything
+    tp = a["out_term_probs"]
+    assert 0.02 < tp.mean() < 0.999 and tp.std() > 1e-3
+
+
+@pytest.mark.parametrize("name", G.KNN_CASES)
+def test_render_knn_matches_reference(name):
+    meta, a = G.load(name)
+    fs, rs, cam = G.field_spec(meta["field_kwargs"]), G.render_spec(meta), G.camera_spec(meta["camera"])
+    p = R.render_rays(a["ijs"], a["c2ws"], cam, rs, fs, G.params(a), a["positions"],
+                      a["orientations"], jitter=a["jitter"])
+    _close(p.rgbds, a["out_rgbds"], atol=1e-5)
+    _close(p.color_vars, a["out_color_vars"], atol=1e-5)
+    _close(p.depth_vars, a["out_depth_vars"], atol=1e-5)
+    _close(p.term_probs, a["out_term_probs"], atol=1e-5)
+    out = R.fieldset_forward_knn(a["knn_query"], a["positions"], a["orientations"], None, fs,
+                                 G.params(a), rs)
+    _close(out, a["knn_out"], atol=1e-5)
+    inside = (a["knn_out"] != rs.outside_value).any(-1).float().mean()
+    assert 0.05 < inside < 0.999
+
+
+def test_quadrature_modes():
+    meta, a = G.load("quadrature_modes")
+    for mode, info in meta["modes"].items():
+        out = R.quadrature(a["colors"], a["geom"] * info["geom_scale"], a["dist"], a["depth"],
+                           a["isd"] if mode == "neus" else None, mode, info["geometry_factor"])
+        for nm, o in zip(["colors", "depths", "color_vars", "depth_vars", "term", "weights"], out):
+            _close(o, a[f"out_{mode}_{nm}"])
+
+
+def test_fields_forward():
+    meta, a = G.load("fields_forward")
+    for name, info in meta["variants"].items():
+        fs = G.field_spec(info["field_kwargs"])
+        params = G.params(a, prefix=f"{name}:param:")
+        enc = R.encode(a[f"{name}:x"], fs, params)
+        _close(enc, a[f"{name}:enc"], atol=1e-6)
+        y = R.field_forward(a[f"{name}:x"], fs, params)
+        _close(y, a[f"{name}:y"], atol=1e-5)
+        assert y.shape[-1] == 4 and fs.dim_encoding() == enc.shape[-1]
+
+
+def test_sampler():
+    meta, a = G.load("sampler")
+    cam = G.camera_spec(meta["camera"])
+    pts, dist = R.sample_ijs_uniform(a["ijs"], cam, 12, a["near"], a["far"], a["jitter"])
+    _close(pts, a["out_points"])
+    _close(dist, a["out_dist"])
+    pts2, dist2 = R.sample_ijs_uniform(a["ijs"], cam, 7, 0.25, 5.0, a["jitter2"])
+    _close(pts2, a["out_points2"])
+    _close(dist2, a["out_dist2"])
+    _close(R.ijs_to_directions(a["ijs"] // 2, G.camera_spec(meta["camera2"])), a["out_dirs_cam2"])
+    _close(R.transform_points(a["out_points"], a["c2ws"].unsqueeze(-3)), a["out_world"])
+
+
+def test_live_reference_if_present():
+    """Where /root/reference exists, also compare against the live reference (not just fixtures)."""
+    from oracle import ref_loader
+
+    if not ref_loader.available():
+        pytest.skip("reference tree not present (GPU box)")
+    ref = ref_loader.load()
+    meta, a = G.load("vmap_guided_nrgbd")
+    cam = ref.camera.Camera(**meta["camera"])
+    g = torch.Generator().manual_seed(7)
+    ijs = torch.stack([torch.randint(0, 480, (5, 9), generator=g),
+                       torch.randint(0, 640, (5, 9), generator=g)], -1)
+    jit = torch.rand(5, 9, 6, generator=g)
+    with ref_loader.injected_jitter(jit):
+        pts, dist = cam.sample_ijs_uniform(ijs, 6, 0.3, 2.0)
+    pts2, dist2 = R.sample_ijs_uniform(ijs, G.camera_spec(meta["camera"]), 6, 0.3, 2.0, jit)
+    _close(pts2, pts)
+    _close(dist2, dist)
