@@ -1,0 +1,239 @@
+/*
+ * ngm_b200.h -- C ABI of libngm_b200.so: the B200 (sm_100a) ray-render hot path of
+ * KTH-RPL/neural_graph_mapping.
+ *
+ * The reference has no FFI: its boundary for this path is Python duck-typing selected by
+ * YAML type strings (utils.str_to_object, ngm/utils.py:114-138).  This header is the C
+ * boundary that sits directly under that Python surface; every entry point names the
+ * reference function it replaces ("ngm/" = /root/reference/src/neural_graph_mapping/).
+ * The Python mirror (neural_graph_mapping_b200/{camera,models,renderer}.py) binds these
+ * with ctypes; INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions (all entry points):
+ *   - plain C: pointers, sizes, scalars.  No torch / C++ types cross the boundary.
+ *   - every pointer is a DEVICE pointer to caller-owned memory (fp32 unless stated,
+ *     densely packed row-major); the library never allocates or frees device memory.
+ *   - asynchronous on the CUDA stream passed as `void* stream` (a cudaStream_t); no host
+ *     synchronisation inside; thread-safe per (device, stream).
+ *   - return 0 on success, a negative NgmStatus on failure; ngm_last_error() returns a
+ *     thread-local message.  No exceptions cross the ABI.  There is NO CPU fallback.
+ */
+#ifndef NGM_B200_H_
+#define NGM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NGM_ABI_VERSION 1
+#define NGM_MAX_LINEARS 9 /* num_layers + 1 <= 9 */
+
+typedef enum NgmStatus {
+  NGM_OK = 0,
+  NGM_ERR_INVALID_ARG = -1,  /* ValueError in the reference (run_mapping.py:498, models.py:110,219,285) */
+  NGM_ERR_UNSUPPORTED = -2,  /* configuration outside what this build implements */
+  NGM_ERR_CUDA = -3,         /* a CUDA runtime call failed; message has cudaGetErrorString */
+  NGM_ERR_WORKSPACE = -4     /* workspace missing or too small (see ngm_*_workspace_bytes) */
+} NgmStatus;
+
+/* ngm/positional_encodings.py: PositionalEncodingNeRF :219, PositionalEncodingFourier :164,
+ * TriplaneEncoding :69, PermutohedralEncoding :19 (third-party kernel; parity unpinned) */
+typedef enum NgmEncoding { NGM_ENC_NERF = 0, NGM_ENC_FOURIER = 1, NGM_ENC_TRIPLANE = 2, NGM_ENC_PERMUTO = 3 } NgmEncoding;
+/* ngm/models.py:104-113 skip_mode */
+typedef enum NgmSkipMode { NGM_SKIP_NO = 0, NGM_SKIP_ADD = 1, NGM_SKIP_CONCAT = 2, NGM_SKIP_REZERO = 3 } NgmSkipMode;
+/* ngm/models.py:278-285 scale_mode */
+typedef enum NgmScaleMode { NGM_SCALE_NO = 0, NGM_SCALE_UNIT_BALL = 1, NGM_SCALE_UNIT_CUBE = 2 } NgmScaleMode;
+/* ngm/run_mapping.py:746-762 geometry_mode */
+typedef enum NgmGeometryMode { NGM_GEOM_DENSITY = 0, NGM_GEOM_OCCUPANCY = 1, NGM_GEOM_NEUS = 2, NGM_GEOM_NRGBD = 3 } NgmGeometryMode;
+/* arithmetic of the MLP operands: fp32 FFMA path (reference arithmetic) or fp16 operands with
+ * fp32 accumulation on tcgen05 tensor cores.  Geometry, sigmoid, transmittance and every
+ * accumulator of the compositor are fp32 in both. */
+typedef enum NgmPrecision { NGM_PREC_FP32 = 0, NGM_PREC_FP16 = 1 } NgmPrecision;
+typedef enum NgmTriplaneMode { NGM_TRIPLANE_SUM = 0, NGM_TRIPLANE_PRODUCT = 1, NGM_TRIPLANE_CONCAT = 2 } NgmTriplaneMode;
+
+/* Pinhole camera as used by Camera.ijs_to_directions (ngm/camera.py:186-203):
+ * cx0/cy0 are the principal point for pixel_center 0, i.e. get_pinhole_camera_parameters(0.0)
+ * (ngm/camera.py:98-116) = cx_in - pixel_center. */
+typedef struct NgmCamera {
+  float fx, fy, cx0, cy0;
+  int32_t width, height;
+} NgmCamera;
+
+/* One NeuralField architecture (ngm/models.py:66-182) plus the stacked per-field parameter
+ * tables in the reference's own layout: all_fields_params[name] = (num_fields, *shape), fp32
+ * (ngm/models.py:254-264).  `*_stride` = elements between consecutive fields (normally the
+ * per-field numel; 0 broadcasts one field, e.g. a single NeuralField).  Field f of a call reads
+ * row field_slots[f] (see the Args structs) -- so neither set_vmap_fields' gather copy
+ * (ngm/models.py:274-276) nor a weight repack is needed by the caller. */
+typedef struct NgmFieldDesc {
+  int32_t encoding;      /* NgmEncoding */
+  int32_t dim_encoding;  /* E = encoding.get_out_dim() */
+  int32_t num_layers;    /* hidden layers L; linears = L + 1 */
+  int32_t dim_mlp_out;   /* W */
+  int32_t dim_out;       /* 4 for the renderer (rgb + geometry) */
+  int32_t skip_mode;     /* NgmSkipMode */
+  /* encoding kwargs */
+  int32_t nerf_num_octaves, nerf_start_octave;               /* positional_encodings.py:229 */
+  int32_t fourier_num_features, fourier_raw_coords;          /* rows of _encoding._linear.weight; :187-195 */
+  int32_t triplane_resolution, triplane_components, triplane_mode; /* :96-121 */
+  int32_t permuto_levels, permuto_feats, permuto_log2_capacity, permuto_concat_points; /* :22-62 */
+  float permuto_concat_scaling;
+  int32_t _pad0;
+  /* _linears.{i}.weight (out,in) and .bias (out,), i = 0..num_layers */
+  const float* weights[NGM_MAX_LINEARS];
+  int64_t weight_stride[NGM_MAX_LINEARS];
+  const float* biases[NGM_MAX_LINEARS];
+  int64_t bias_stride[NGM_MAX_LINEARS];
+  const float* rezero; /* _rezero (num_layers,), skip_mode rezero only */
+  int64_t rezero_stride;
+  /* encoding parameters: fourier `_encoding._linear.weight` (n,3) | triplane
+   * `_encoding.plane_coef` (3,C,res,res) | permuto lattice table (levels,capacity,feats) */
+  const float* enc_param0;
+  int64_t enc_param0_stride;
+  /* permuto: per-level random shift (levels,3) */
+  const float* enc_param1;
+  int64_t enc_param1_stride;
+  /* permuto: per-level, per-axis scale factors (levels,3), shared by all fields */
+  const float* permuto_scale;
+} NgmFieldDesc;
+
+/* ---- stage: ray sampler --------------------------------------------------------------
+ * Replaces Camera.sample_ijs_uniform (ngm/camera.py:215-292, uniform branch), the
+ * depth-guided second sample set + sort/gather merge (ngm/run_mapping.py:521-545) and
+ * utils.transform_points (ngm/utils.py:276-286 at run_mapping.py:547).
+ * Rays are the flattened leading dims of `ijs`.  St = num_samples + num_samples_guided. */
+typedef struct NgmSampleArgs {
+  NgmCamera cam;
+  int64_t num_rays;
+  const int64_t* ijs;   /* (num_rays, 2) int64 [row, col] */
+  const float* c2ws;    /* (4,4) row-major, or (num_rays,4,4) when c2w_per_ray != 0; OpenGL */
+  const float* near;    /* (num_rays) or NULL -> near_scalar */
+  const float* far;     /* (num_rays) or NULL -> far_scalar */
+  const float* gt;      /* (num_rays) or NULL; 0.0 = unavailable (run_mapping.py:522-526) */
+  const float* jitter;        /* (num_rays, num_samples) U[0,1) or NULL -> Philox(seed, offset) */
+  const float* jitter_guided; /* (num_rays, num_samples_guided) or NULL -> Philox */
+  uint64_t seed, offset;
+  float near_scalar, far_scalar, range_guided;
+  int32_t c2w_per_ray;
+  int32_t num_samples, num_samples_guided; /* guided set is used only when gt != NULL */
+  /* outputs, any may be NULL: */
+  float* points_cam;   /* (num_rays, St, 3) */
+  float* points_world; /* (num_rays, St, 3) */
+  float* distances;    /* (num_rays, St) sorted ascending */
+  float* depths;       /* (num_rays, St) = -points_cam.z (run_mapping.py:612) */
+} NgmSampleArgs;
+
+/* ---- stage: field evaluation ---------------------------------------------------------
+ * Replaces NeuralFieldSet.forward, vmap branch (ngm/models.py:329-345): world->local
+ * (quaternion_invert/apply, :331-335), _scale_local_points (:278-285) and NeuralField.forward
+ * (:143-182) for `num_fields` fields x `points_per_field` points.  With positions == NULL the
+ * points are already local (NeuralField.forward / the :336-337 branch). */
+typedef struct NgmFieldFwdArgs {
+  NgmFieldDesc field;
+  int64_t points_per_field;
+  const float* points;        /* (num_fields, points_per_field, 3) */
+  const float* positions;     /* (num_slots, 3) or NULL */
+  const float* orientations;  /* (num_slots, 4) real-first quaternions, or NULL */
+  const int64_t* field_slots; /* (num_fields) row of each field in positions/orientations/param tables; NULL = identity */
+  float* out;                 /* (num_fields, points_per_field, dim_out) */
+  void* workspace;
+  size_t workspace_bytes;
+  float field_radius;
+  int32_t num_fields;
+  int32_t scale_mode; /* NgmScaleMode */
+  int32_t precision;  /* NgmPrecision */
+} NgmFieldFwdArgs;
+
+/* ---- stage: compositor ---------------------------------------------------------------
+ * Replaces the post-MLP split + masks (ngm/run_mapping.py:610-639) and
+ * NeuralGraphMap._quadrature (ngm/run_mapping.py:709-799). */
+typedef struct NgmCompositeArgs {
+  int64_t num_rays;
+  const float* colors;      /* sample colours, element (r,s,c) at colors[(r*S+s)*color_stride + c] */
+  const float* geometries;  /* sample geometry, element (r,s) at geometries[(r*S+s)*geometry_stride] */
+  const float* distances;   /* (num_rays, S) */
+  const float* depths;      /* (num_rays, S) */
+  const float* neus_isd;    /* neus: inverse sd per group of rays_per_isd rays (F,), else NULL */
+  const float* gt;          /* (num_rays) or NULL */
+  int64_t color_stride, geometry_stride; /* (3,1) for separate tensors, (4,4) for packed MLP output */
+  int64_t rays_per_isd;
+  int32_t num_samples;      /* S */
+  int32_t geometry_mode;    /* NgmGeometryMode */
+  float geometry_factor, color_factor, truncation;
+  int32_t overwrite_behind_camera; /* geometry := fill where depth < 0 (run_mapping.py:614-622) */
+  /* outputs; rgbd is required, the others may be NULL */
+  float* rgbd;       /* (num_rays, 4): colour(3), depth */
+  float* color_var;  /* (num_rays, 3) */
+  float* depth_var;  /* (num_rays) */
+  float* term_prob;  /* (num_rays) */
+  float* weights;    /* (num_rays, S) sample weights (zero-filled for the dropped last sample) */
+  /* dense aux outputs + masks; the host compacts them to the reference's 1-D tensors */
+  float* freespace;        /* (num_rays, S): geometry * truncation      (run_mapping.py:625-628) */
+  uint8_t* freespace_mask; /* (num_rays, S) */
+  float* tsdf;             /* (num_rays, S): geometry*truncation - (gt - dist) (:633-637) */
+  uint8_t* tsdf_mask;      /* (num_rays, S) */
+} NgmCompositeArgs;
+
+/* ---- fused render --------------------------------------------------------------------
+ * Replaces NeuralGraphMap._render_ijs with use_vmap=True (ngm/run_mapping.py:440-666):
+ * sampler -> world->local -> encoding -> per-field MLP -> compositor for
+ * (num_fields x rays_per_field) rays, ray (f, r) being evaluated by field f only. */
+typedef struct NgmRenderArgs {
+  NgmFieldDesc field;
+  NgmCamera cam;
+  int64_t rays_per_field;
+  const int64_t* ijs;         /* (num_fields, rays_per_field, 2) */
+  const float* c2ws;          /* (4,4) or (num_fields, rays_per_field, 4, 4) */
+  const float* near;          /* (num_fields, rays_per_field) or NULL */
+  const float* far;
+  const float* gt;
+  const float* jitter;        /* (num_fields, rays_per_field, num_samples) or NULL -> Philox */
+  const float* jitter_guided;
+  const float* positions;     /* (num_slots, 3)  global field table (_global_map_dict["positions"]) */
+  const float* orientations;  /* (num_slots, 4) */
+  const int64_t* field_slots; /* (num_fields) = field_ids; NULL = identity */
+  const float* neus_sd;       /* (num_slots) `_neus_sd` table, neus mode only (run_mapping.py:641-644) */
+  uint64_t seed, offset;
+  float near_scalar, far_scalar, range_guided;
+  float field_radius;
+  float geometry_factor, color_factor, truncation;
+  int32_t c2w_per_ray;
+  int32_t num_samples, num_samples_guided;
+  int32_t num_fields;
+  int32_t scale_mode, geometry_mode, precision;
+  int32_t overwrite_behind_camera;
+  /* outputs: Prediction (run_mapping.py:59-69); aux ones may be NULL */
+  float* rgbd;       /* (num_fields, rays_per_field, 4) */
+  float* color_var;  /* (..., 3) */
+  float* depth_var;  /* (...) */
+  float* term_prob;  /* (...) */
+  float* freespace;  uint8_t* freespace_mask; /* (..., St) dense + mask */
+  float* tsdf;       uint8_t* tsdf_mask;
+  void* workspace;
+  size_t workspace_bytes;
+} NgmRenderArgs;
+
+/* ---- entry points ---------------------------------------------------------------------- */
+int ngm_abi_version(void);
+const char* ngm_last_error(void);
+/* sizeof() of the structs above as compiled, so a binding can verify its mirror:
+ * which = 0 NgmCamera, 1 NgmFieldDesc, 2 NgmSampleArgs, 3 NgmFieldFwdArgs, 4 NgmCompositeArgs, 5 NgmRenderArgs */
+size_t ngm_struct_size(int which);
+/* number of CUDA kernels this library has launched in this process (bench.py's gpu_launches) */
+uint64_t ngm_launch_count(void);
+
+int ngm_sample_rays(const NgmSampleArgs* args, void* stream);   /* camera.py:215-292, run_mapping.py:521-547 */
+int ngm_field_fwd(const NgmFieldFwdArgs* args, void* stream);   /* models.py:143-182, 329-345 */
+int ngm_composite(const NgmCompositeArgs* args, void* stream);  /* run_mapping.py:610-639, 709-799 */
+int ngm_render_rays_fwd(const NgmRenderArgs* args, void* stream); /* run_mapping.py:440-666 (use_vmap=True) */
+
+int ngm_field_fwd_workspace_bytes(const NgmFieldFwdArgs* args, size_t* out);
+int ngm_render_workspace_bytes(const NgmRenderArgs* args, size_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NGM_B200_H_ */

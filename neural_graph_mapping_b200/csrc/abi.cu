@@ -1,0 +1,266 @@
+// extern "C" entry points of libngm_b200.so (see include/ngm_b200.h).
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace ngm {
+
+static thread_local char g_error[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+}
+
+static unsigned long long g_launches = 0;
+void count_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
+
+int num_sms() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+// kernels (one translation unit each)
+int launch_sample_rays(const NgmSampleArgs& a, cudaStream_t stream);
+int launch_composite(const NgmCompositeArgs& a, cudaStream_t stream);
+int launch_neus_isd(const float* sd, const int64_t* slots, int num_fields, float* out, cudaStream_t stream);
+int launch_field_fwd_simt(const NgmFieldFwdArgs& a, cudaStream_t stream);
+size_t field_simt_smem_bytes(const NgmFieldDesc& fd, int* act_stride, int* enc_stride);
+// fp16 tcgen05 path (field_tc.cu)
+bool field_tc_supported(const NgmFieldDesc& fd, const char** why);
+size_t field_tc_workspace_bytes(const NgmFieldDesc& fd, int num_fields);
+int launch_field_fwd_tc(const NgmFieldFwdArgs& a, cudaStream_t stream);
+int launch_render_fused_tc(const NgmRenderArgs& a, cudaStream_t stream);
+
+static int validate_field(const NgmFieldDesc& fd) {
+  NGM_CHECK_ARG(fd.num_layers >= 0 && fd.num_layers + 1 <= NGM_MAX_LINEARS, "num_layers=%d out of range [0,%d]",
+                fd.num_layers, NGM_MAX_LINEARS - 1);
+  NGM_CHECK_ARG(fd.dim_encoding > 0 && fd.dim_mlp_out > 0 && fd.dim_out > 0, "non-positive layer width");
+  NGM_CHECK_ARG(fd.skip_mode >= NGM_SKIP_NO && fd.skip_mode <= NGM_SKIP_REZERO,
+                "Skip mode %d is not available.", fd.skip_mode);  // models.py:110
+  NGM_CHECK_ARG(fd.encoding >= NGM_ENC_NERF && fd.encoding <= NGM_ENC_PERMUTO, "unknown encoding %d", fd.encoding);
+  if (fd.skip_mode == NGM_SKIP_ADD || fd.skip_mode == NGM_SKIP_REZERO)
+    NGM_CHECK_ARG(fd.dim_mlp_out >= fd.dim_encoding, "skip_mode add/rezero needs dim_mlp_out >= dim_encoding");
+  if (fd.skip_mode == NGM_SKIP_REZERO) NGM_CHECK_ARG(fd.rezero != nullptr, "skip_mode rezero without _rezero");
+  for (int i = 0; i <= fd.num_layers; ++i)
+    NGM_CHECK_ARG(fd.weights[i] && fd.biases[i], "missing _linears.%d parameters", i);
+  switch (fd.encoding) {
+    case NGM_ENC_NERF:
+      NGM_CHECK_ARG(fd.dim_encoding == 6 * fd.nerf_num_octaves, "nerf: dim_encoding != 2*3*num_octaves");
+      break;
+    case NGM_ENC_FOURIER:
+      NGM_CHECK_ARG(fd.enc_param0 && fd.dim_encoding == fd.fourier_num_features + (fd.fourier_raw_coords ? 3 : 0),
+                    "fourier: bad dims or missing weight");
+      break;
+    case NGM_ENC_TRIPLANE:
+      NGM_CHECK_ARG(fd.enc_param0 && fd.triplane_resolution >= 2 &&
+                        fd.dim_encoding == fd.triplane_components * (fd.triplane_mode == NGM_TRIPLANE_CONCAT ? 3 : 1),
+                    "triplane: bad dims or missing plane_coef");
+      break;
+    case NGM_ENC_PERMUTO:
+      NGM_CHECK_ARG(fd.enc_param0 && fd.enc_param1 && fd.permuto_scale, "permuto: missing table/shift/scale");
+      NGM_CHECK_ARG(fd.permuto_feats >= 1 && fd.permuto_feats <= 8 && fd.permuto_log2_capacity >= 1 &&
+                        fd.permuto_log2_capacity <= 30 &&
+                        fd.dim_encoding == fd.permuto_levels * fd.permuto_feats + (fd.permuto_concat_points ? 3 : 0),
+                    "permuto: unsupported dims");
+      break;
+  }
+  return NGM_OK;
+}
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct RenderWorkspace {
+  size_t points_world, distances, depths, outs, isd, tc, total;
+};
+
+static RenderWorkspace render_workspace(const NgmRenderArgs& a) {
+  RenderWorkspace w{};
+  const int St = a.num_samples + (a.gt ? a.num_samples_guided : 0);
+  const size_t n = (size_t)a.num_fields * (size_t)a.rays_per_field * (size_t)St;
+  size_t off = 0;
+  w.points_world = off; off = align_up(off + n * 3 * sizeof(float), 256);
+  w.distances = off;    off = align_up(off + n * sizeof(float), 256);
+  w.depths = off;       off = align_up(off + n * sizeof(float), 256);
+  w.outs = off;         off = align_up(off + n * 4 * sizeof(float), 256);
+  w.isd = off;          off = align_up(off + (size_t)a.num_fields * sizeof(float), 256);
+  w.tc = off;
+  if (a.precision == NGM_PREC_FP16) off = align_up(off + field_tc_workspace_bytes(a.field, a.num_fields), 256);
+  w.total = off;
+  return w;
+}
+
+}  // namespace ngm
+
+using namespace ngm;
+
+extern "C" {
+
+int ngm_abi_version(void) { return NGM_ABI_VERSION; }
+
+const char* ngm_last_error(void) { return g_error; }
+
+uint64_t ngm_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+
+size_t ngm_struct_size(int which) {
+  switch (which) {
+    case 0: return sizeof(NgmCamera);
+    case 1: return sizeof(NgmFieldDesc);
+    case 2: return sizeof(NgmSampleArgs);
+    case 3: return sizeof(NgmFieldFwdArgs);
+    case 4: return sizeof(NgmCompositeArgs);
+    case 5: return sizeof(NgmRenderArgs);
+    default: return 0;
+  }
+}
+
+int ngm_sample_rays(const NgmSampleArgs* a, void* stream) {
+  NGM_CHECK_ARG(a != nullptr, "null args");
+  NGM_CHECK_ARG(a->num_rays >= 0 && a->num_samples > 0 && a->num_samples_guided >= 0, "bad ray/sample counts");
+  NGM_CHECK_ARG(a->num_rays == 0 || (a->ijs && a->c2ws), "ijs / c2ws missing");
+  NGM_CHECK_ARG(a->cam.fx != 0.f && a->cam.fy != 0.f, "zero focal length");
+  return launch_sample_rays(*a, (cudaStream_t)stream);
+}
+
+int ngm_field_fwd_workspace_bytes(const NgmFieldFwdArgs* a, size_t* out) {
+  NGM_CHECK_ARG(a && out, "null args");
+  *out = a->precision == NGM_PREC_FP16 ? field_tc_workspace_bytes(a->field, a->num_fields) : 0;
+  return NGM_OK;
+}
+
+int ngm_field_fwd(const NgmFieldFwdArgs* a, void* stream) {
+  NGM_CHECK_ARG(a != nullptr, "null args");
+  if (int rc = validate_field(a->field)) return rc;
+  NGM_CHECK_ARG(a->num_fields >= 0 && a->points_per_field >= 0, "negative sizes");
+  if (a->num_fields == 0 || a->points_per_field == 0) return NGM_OK;
+  NGM_CHECK_ARG(a->points && a->out, "points / out missing");
+  NGM_CHECK_ARG((a->positions == nullptr) == (a->orientations == nullptr),
+                "positions and orientations must be given together");
+  NGM_CHECK_ARG(a->scale_mode >= NGM_SCALE_NO && a->scale_mode <= NGM_SCALE_UNIT_CUBE, "scale_mode=%d is not available.",
+                a->scale_mode);  // models.py:285
+  if (a->scale_mode != NGM_SCALE_NO)
+    NGM_CHECK_ARG(a->field_radius > 0.f, "scale_mode requires field_radius to be specified.");  // models.py:219
+  if (a->precision == NGM_PREC_FP16) {
+    const char* why = nullptr;
+    NGM_UNSUPPORTED(!field_tc_supported(a->field, &why), "fp16 tensor-core path unsupported: %s", why);
+    size_t need = field_tc_workspace_bytes(a->field, a->num_fields);
+    if (need > a->workspace_bytes || (need && !a->workspace)) {
+      set_error("workspace too small: need %zu B, have %zu B", need, a->workspace_bytes);
+      return NGM_ERR_WORKSPACE;
+    }
+    return launch_field_fwd_tc(*a, (cudaStream_t)stream);
+  }
+  NGM_CHECK_ARG(a->precision == NGM_PREC_FP32, "unknown precision %d", a->precision);
+  return launch_field_fwd_simt(*a, (cudaStream_t)stream);
+}
+
+int ngm_composite(const NgmCompositeArgs* a, void* stream) {
+  NGM_CHECK_ARG(a != nullptr, "null args");
+  NGM_CHECK_ARG(a->num_rays >= 0 && a->num_samples > 0, "bad ray/sample counts");
+  if (a->num_rays == 0) return NGM_OK;
+  NGM_CHECK_ARG(a->colors && a->geometries && a->distances && a->depths && a->rgbd, "missing input/output");
+  NGM_CHECK_ARG(a->geometry_mode >= NGM_GEOM_DENSITY && a->geometry_mode <= NGM_GEOM_NRGBD, "unknown geometry_mode %d",
+                a->geometry_mode);
+  if (a->geometry_mode == NGM_GEOM_NEUS)
+    NGM_CHECK_ARG(a->neus_isd && a->rays_per_isd > 0, "neus mode needs neus_isd");
+  NGM_CHECK_ARG((a->freespace == nullptr) == (a->freespace_mask == nullptr), "freespace and its mask go together");
+  NGM_CHECK_ARG((a->tsdf == nullptr) == (a->tsdf_mask == nullptr), "tsdf and its mask go together");
+  NGM_CHECK_ARG(((uintptr_t)a->rgbd & 15) == 0, "rgbd must be 16-byte aligned");
+  return launch_composite(*a, (cudaStream_t)stream);
+}
+
+int ngm_render_workspace_bytes(const NgmRenderArgs* a, size_t* out) {
+  NGM_CHECK_ARG(a && out, "null args");
+  *out = render_workspace(*a).total;
+  return NGM_OK;
+}
+
+int ngm_render_rays_fwd(const NgmRenderArgs* a, void* stream_) {
+  NGM_CHECK_ARG(a != nullptr, "null args");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (int rc = validate_field(a->field)) return rc;
+  NGM_CHECK_ARG(a->field.dim_out == 4, "the renderer needs dim_out == 4 (rgb + geometry), got %d", a->field.dim_out);
+  NGM_CHECK_ARG(a->num_fields >= 0 && a->rays_per_field >= 0 && a->num_samples > 0 && a->num_samples_guided >= 0,
+                "bad sizes");
+  const long long num_rays = (long long)a->num_fields * a->rays_per_field;
+  if (num_rays == 0) return NGM_OK;
+  NGM_CHECK_ARG(a->ijs && a->c2ws && a->positions && a->orientations && a->rgbd, "missing input/output");
+  NGM_CHECK_ARG(a->geometry_mode >= NGM_GEOM_DENSITY && a->geometry_mode <= NGM_GEOM_NRGBD, "unknown geometry_mode %d",
+                a->geometry_mode);
+  if (a->geometry_mode == NGM_GEOM_NEUS) NGM_CHECK_ARG(a->neus_sd != nullptr, "neus mode needs the _neus_sd table");
+  const RenderWorkspace w = render_workspace(*a);
+  if (w.total > a->workspace_bytes || !a->workspace) {
+    set_error("workspace too small: need %zu B, have %zu B", w.total, a->workspace_bytes);
+    return NGM_ERR_WORKSPACE;
+  }
+  if (a->precision == NGM_PREC_FP16) {
+    const char* why = nullptr;
+    NGM_UNSUPPORTED(!field_tc_supported(a->field, &why), "fp16 tensor-core path unsupported: %s", why);
+    return launch_render_fused_tc(*a, stream);
+  }
+  NGM_CHECK_ARG(a->precision == NGM_PREC_FP32, "unknown precision %d", a->precision);
+
+  // fp32 (reference-arithmetic) path: the three stage kernels over workspace intermediates.
+  char* ws = static_cast<char*>(a->workspace);
+  const int St = a->num_samples + (a->gt ? a->num_samples_guided : 0);
+  NgmSampleArgs s{};
+  s.cam = a->cam;
+  s.num_rays = num_rays;
+  s.ijs = a->ijs; s.c2ws = a->c2ws; s.near = a->near; s.far = a->far; s.gt = a->gt;
+  s.jitter = a->jitter; s.jitter_guided = a->jitter_guided;
+  s.seed = a->seed; s.offset = a->offset;
+  s.near_scalar = a->near_scalar; s.far_scalar = a->far_scalar; s.range_guided = a->range_guided;
+  s.c2w_per_ray = a->c2w_per_ray;
+  s.num_samples = a->num_samples; s.num_samples_guided = a->num_samples_guided;
+  s.points_cam = nullptr;
+  s.points_world = reinterpret_cast<float*>(ws + w.points_world);
+  s.distances = reinterpret_cast<float*>(ws + w.distances);
+  s.depths = reinterpret_cast<float*>(ws + w.depths);
+  if (int rc = launch_sample_rays(s, stream)) return rc;
+
+  NgmFieldFwdArgs f{};
+  f.field = a->field;
+  f.points_per_field = a->rays_per_field * St;
+  f.points = s.points_world;
+  f.positions = a->positions; f.orientations = a->orientations; f.field_slots = a->field_slots;
+  f.out = reinterpret_cast<float*>(ws + w.outs);
+  f.field_radius = a->field_radius;
+  f.num_fields = a->num_fields;
+  f.scale_mode = a->scale_mode;
+  f.precision = NGM_PREC_FP32;
+  if (int rc = ngm_field_fwd(&f, stream_)) return rc;
+
+  NgmCompositeArgs c{};
+  c.num_rays = num_rays;
+  c.colors = f.out; c.geometries = f.out + 3;
+  c.color_stride = 4; c.geometry_stride = 4;
+  c.distances = s.distances; c.depths = s.depths;
+  c.gt = a->gt;
+  c.num_samples = St;
+  c.geometry_mode = a->geometry_mode;
+  c.geometry_factor = a->geometry_factor; c.color_factor = a->color_factor; c.truncation = a->truncation;
+  c.overwrite_behind_camera = a->overwrite_behind_camera;
+  c.rgbd = a->rgbd; c.color_var = a->color_var; c.depth_var = a->depth_var; c.term_prob = a->term_prob;
+  c.freespace = a->freespace; c.freespace_mask = a->freespace_mask;
+  c.tsdf = a->tsdf; c.tsdf_mask = a->tsdf_mask;
+  if (a->geometry_mode == NGM_GEOM_NEUS) {
+    // neus_isds = 1 / |_neus_sd[field_ids]|  (run_mapping.py:641-644)
+    float* isd = reinterpret_cast<float*>(ws + w.isd);
+    if (int rc = launch_neus_isd(a->neus_sd, a->field_slots, a->num_fields, isd, stream)) return rc;
+    c.neus_isd = isd;
+    c.rays_per_isd = a->rays_per_field;
+  }
+  return ngm_composite(&c, stream_);
+}
+
+}  // extern "C"

@@ -1,0 +1,220 @@
+// Stage kernel: compositor.
+// Replaces the post-MLP split/masks (ngm/run_mapping.py:610-639) and
+// NeuralGraphMap._quadrature (ngm/run_mapping.py:709-799).
+//
+// HBM-bound: algorithmic bytes per ray = S*(4*b + 4 + 4) + 36  [SURVEY 8d].
+// One warp per ray; lane l owns samples l, l+32, ... so every load is a contiguous 128 B
+// (distances, depths) or 512 B (packed rgb+geometry float4) row segment.  Transmittance is a
+// warp-shuffle exclusive product scan with a running carry between 32-sample blocks; the
+// expectations are shuffle reductions; the variances use the reference's two-pass form
+// (mean first, then sum w (mean - x)^2), with the per-sample terms cached in registers for
+// S <= 128 and recomputed otherwise.
+#include "common.cuh"
+
+namespace ngm {
+
+namespace {
+
+constexpr int kWarpsPerBlock = 8;
+constexpr int kCacheBlocks = 4;  // S <= 128 keeps per-sample terms in registers
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+struct SampleTerms {
+  float w, z, c0, c1, c2;
+};
+
+struct RayCtx {
+  const NgmCompositeArgs& a;
+  long long ray;
+  int lane, S, Se;
+  float isd_gamma;  // neus: isd * geometry_factor
+  float gt;
+  bool has_gt;
+
+  // geometry of sample k after the behind-camera overwrite (run_mapping.py:614-622)
+  __device__ __forceinline__ float geometry(int k, float depth) const {
+    float g = __ldg(a.geometries + (ray * S + k) * a.geometry_stride);
+    if (a.overwrite_behind_camera && depth < 0.0f)
+      g = (a.geometry_mode == NGM_GEOM_OCCUPANCY || a.geometry_mode == NGM_GEOM_DENSITY) ? -100.0f : 1.0f;
+    return g;
+  }
+
+  // occupancy probability of sample k (run_mapping.py:746-762); k < Se
+  __device__ __forceinline__ float occupancy(int k, float g, float dist) const {
+    switch (a.geometry_mode) {
+      case NGM_GEOM_NRGBD: {
+        float t = a.geometry_factor * g;
+        return (4.0f * sigmoidf(t)) * sigmoidf(-t);
+      }
+      case NGM_GEOM_OCCUPANCY:
+        return sigmoidf(a.geometry_factor * g);
+      case NGM_GEOM_DENSITY: {
+        float dn = __ldg(a.distances + ray * S + k + 1);
+        float delta = dn - dist;
+        return 1.0f - expf(-delta * fmaxf(g, 0.0f));
+      }
+      default: {  // NGM_GEOM_NEUS
+        float zn = __ldg(a.depths + ray * S + k + 1);
+        float gn = geometry(k + 1, zn);
+        float t0 = sigmoidf(isd_gamma * g), t1 = sigmoidf(isd_gamma * gn);
+        return fmaxf((t0 - t1) / (t0 + 1e-5f), 0.0f);
+      }
+    }
+  }
+};
+
+// One 32-sample block: loads, aux outputs, occupancy, scan.  `carry` = transmittance entering
+// the block, updated on exit.
+__device__ __forceinline__ SampleTerms eval_block(const RayCtx& c, int blk, float& carry, bool write_aux) {
+  const NgmCompositeArgs& a = c.a;
+  const int k = blk * 32 + c.lane;
+  SampleTerms t{0.f, 0.f, 0.f, 0.f, 0.f};
+  float occ = 0.0f;
+  if (k < c.S) {
+    const long long idx = c.ray * c.S + k;
+    const float dist = __ldg(a.distances + idx);
+    const float z = __ldg(a.depths + idx);
+    const float g = c.geometry(k, z);
+    if (write_aux) {
+      if (a.freespace) {  // run_mapping.py:624-630
+        float thr = c.has_gt ? (c.gt - a.truncation) * (c.gt != 0.0f ? 1.0f : 0.0f) : 0.0f;
+        a.freespace[idx] = g * a.truncation;
+        a.freespace_mask[idx] = (c.has_gt && dist < thr) ? 1 : 0;
+      }
+      if (a.tsdf) {  // run_mapping.py:632-639
+        float delta = c.gt - dist;
+        a.tsdf[idx] = g * a.truncation - delta;
+        a.tsdf_mask[idx] = (c.has_gt && fabsf(delta) < a.truncation && c.gt != 0.0f) ? 1 : 0;
+      }
+    }
+    if (k < c.Se) {
+      occ = c.occupancy(k, g, dist);
+      t.z = z;
+      const float* col = a.colors + idx * a.color_stride;
+      t.c0 = a.color_factor * __ldg(col + 0);
+      t.c1 = a.color_factor * __ldg(col + 1);
+      t.c2 = a.color_factor * __ldg(col + 2);
+    }
+  }
+  // exclusive product scan of (1 - occ) across the warp, times carry (run_mapping.py:764-771)
+  float incl = 1.0f - occ;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    float n = __shfl_up_sync(0xffffffffu, incl, o);
+    if (c.lane >= o) incl *= n;
+  }
+  float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+  if (c.lane == 0) excl = 1.0f;
+  t.w = occ * (carry * excl);
+  carry *= __shfl_sync(0xffffffffu, incl, 31);
+  return t;
+}
+
+template <bool CACHE>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) composite_kernel(NgmCompositeArgs a) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = blockIdx.x * (long long)kWarpsPerBlock + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * kWarpsPerBlock;
+  const int S = a.num_samples;
+  const bool drop_last = (a.geometry_mode == NGM_GEOM_DENSITY || a.geometry_mode == NGM_GEOM_NEUS);
+  const int Se = drop_last ? S - 1 : S;
+  const int nblk = (S + 31) / 32;
+  for (long long ray = warp0; ray < a.num_rays; ray += nwarps) {
+    RayCtx c{a, ray, lane, S, Se, 0.f, 0.f, a.gt != nullptr};
+    if (a.geometry_mode == NGM_GEOM_NEUS)
+      c.isd_gamma = __ldg(a.neus_isd + ray / a.rays_per_isd) * a.geometry_factor;
+    if (c.has_gt) c.gt = __ldg(a.gt + ray);
+
+    SampleTerms cache[CACHE ? kCacheBlocks : 1];
+    float carry = 1.0f;
+    float sw = 0.f, sz = 0.f, s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    auto pass1 = [&](int b) {
+      SampleTerms t = eval_block(c, b, carry, true);
+      if (CACHE) cache[CACHE ? b : 0] = t;
+      sw += t.w;
+      sz += t.w * t.z;
+      s0 += t.w * t.c0;
+      s1 += t.w * t.c1;
+      s2 += t.w * t.c2;
+      if (a.weights) {
+        int k = b * 32 + lane;
+        if (k < S) a.weights[ray * S + k] = t.w;
+      }
+    };
+    if (CACHE) {
+#pragma unroll
+      for (int b = 0; b < kCacheBlocks; ++b)
+        if (b < nblk) pass1(b);
+    } else {
+      for (int b = 0; b < nblk; ++b) pass1(b);
+    }
+    const float P = warp_sum(sw), D = warp_sum(sz);
+    const float C0 = warp_sum(s0), C1 = warp_sum(s1), C2 = warp_sum(s2);
+
+    float vz = 0.f, v0 = 0.f, v1 = 0.f, v2 = 0.f;
+    if (a.color_var || a.depth_var) {
+      carry = 1.0f;
+      auto pass2 = [&](int b) {
+        SampleTerms t = CACHE ? cache[CACHE ? b : 0] : eval_block(c, b, carry, false);
+        float d;
+        d = D - t.z;  vz += t.w * (d * d);
+        d = C0 - t.c0; v0 += t.w * (d * d);
+        d = C1 - t.c1; v1 += t.w * (d * d);
+        d = C2 - t.c2; v2 += t.w * (d * d);
+      };
+      if (CACHE) {
+#pragma unroll
+        for (int b = 0; b < kCacheBlocks; ++b)
+          if (b < nblk) pass2(b);
+      } else {
+        for (int b = 0; b < nblk; ++b) pass2(b);
+      }
+      vz = warp_sum(vz); v0 = warp_sum(v0); v1 = warp_sum(v1); v2 = warp_sum(v2);
+    }
+    if (lane == 0) {
+      reinterpret_cast<float4*>(a.rgbd)[ray] = make_float4(C0, C1, C2, D);
+      if (a.color_var) {
+        a.color_var[ray * 3 + 0] = v0;
+        a.color_var[ray * 3 + 1] = v1;
+        a.color_var[ray * 3 + 2] = v2;
+      }
+      if (a.depth_var) a.depth_var[ray] = vz;
+      // term prob = 1 - bg = 1 - (1 - sum w)  (run_mapping.py:774,796)
+      if (a.term_prob) a.term_prob[ray] = 1.0f - (1.0f - P);
+    }
+  }
+}
+
+__global__ void neus_isd_kernel(const float* __restrict__ sd, const long long* __restrict__ slots, int n,
+                                float* __restrict__ out) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f < n) out[f] = 1.0f / fabsf(sd[slots ? slots[f] : f]);
+}
+
+}  // namespace
+
+int launch_neus_isd(const float* sd, const int64_t* slots, int num_fields, float* out, cudaStream_t stream) {
+  if (num_fields == 0) return NGM_OK;
+  neus_isd_kernel<<<(num_fields + 127) / 128, 128, 0, stream>>>(sd, reinterpret_cast<const long long*>(slots),
+                                                                num_fields, out);
+  return check_launch("neus_isd_kernel");
+}
+
+int launch_composite(const NgmCompositeArgs& a, cudaStream_t stream) {
+  if (a.num_rays == 0) return NGM_OK;
+  long long blocks = (a.num_rays + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  const long long cap = (long long)num_sms() * 64;
+  if (blocks > cap) blocks = cap;
+  if (a.num_samples <= 32 * kCacheBlocks)
+    composite_kernel<true><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, stream>>>(a);
+  else
+    composite_kernel<false><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, stream>>>(a);
+  return check_launch("composite_kernel");
+}
+
+}  // namespace ngm

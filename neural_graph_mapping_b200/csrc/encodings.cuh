@@ -1,0 +1,147 @@
+// Device-side positional encodings (fp32), one feature (or one lattice level) per call.
+// Restates ngm/positional_encodings.py: PositionalEncodingNeRF :245-272, PositionalEncodingFourier
+// :197-212, TriplaneEncoding :132-161 and the third-party permutohedral encoding wrapped at :19-66
+// (published algorithm; parity unpinned -- see oracle/permuto.py).
+#pragma once
+#include "common.cuh"
+
+namespace ngm {
+
+// feature c of sin/cos(2^o * pi * x): layout [sin: dim-major, octave-minor | cos: same].
+__device__ __forceinline__ float nerf_feature(const float* x, int c, int num_octaves, int start_octave) {
+  const int half = 3 * num_octaves;
+  const bool is_cos = c >= half;
+  const int cc = is_cos ? c - half : c;
+  const int dim = cc / num_octaves, oct = cc - dim * num_octaves;
+  const float mult = ldexpf(3.14159274101257324f, start_octave + oct);  // fl32(pi) * 2^o, exact
+  const float arg = __fmul_rn(x[dim], mult);
+  return is_cos ? cosf(arg) : sinf(arg);
+}
+
+// feature c of [x | sin(W x)] (raw_coords) or sin(W x);  w = (n,3) row-major
+__device__ __forceinline__ float fourier_feature(const float* x, int c, const float* __restrict__ w, int raw) {
+  if (raw) {
+    if (c < 3) return x[c];
+    c -= 3;
+  }
+  const float* r = w + c * 3;
+  float s = __ldg(r) * x[0];
+  s = fmaf(__ldg(r + 1), x[1], s);
+  s = fmaf(__ldg(r + 2), x[2], s);
+  return sinf(s);
+}
+
+// F.grid_sample(bilinear, align_corners=True, padding_mode="border") of one (res x res) plane
+__device__ __forceinline__ float plane_sample(const float* __restrict__ plane, int res, float gx, float gy) {
+  const float lim = (float)(res - 1);
+  float ix = ((gx + 1.0f) / 2.0f) * lim, iy = ((gy + 1.0f) / 2.0f) * lim;
+  ix = fminf(lim, fmaxf(ix, 0.0f));
+  iy = fminf(lim, fmaxf(iy, 0.0f));
+  const float fx0 = floorf(ix), fy0 = floorf(iy);
+  const int x0 = (int)fx0, y0 = (int)fy0, x1 = x0 + 1, y1 = y0 + 1;
+  const float wnw = (fx0 + 1.0f - ix) * (fy0 + 1.0f - iy), wne = (ix - fx0) * (fy0 + 1.0f - iy);
+  const float wsw = (fx0 + 1.0f - ix) * (iy - fy0), wse = (ix - fx0) * (iy - fy0);
+  float out = 0.0f;
+  out += __ldg(plane + y0 * res + x0) * wnw;  // (x0,y0) is always in bounds after clipping
+  if (x1 < res) out += __ldg(plane + y0 * res + x1) * wne;
+  if (y1 < res) out += __ldg(plane + y1 * res + x0) * wsw;
+  if (x1 < res && y1 < res) out += __ldg(plane + y1 * res + x1) * wse;
+  return out;
+}
+
+// feature c of the triplane encoding; coef = (3, C, res, res)
+__device__ __forceinline__ float triplane_feature(const float* x, int c, const float* __restrict__ coef,
+                                                   int res, int C, int mode) {
+  const int plane_elems = res * res;
+  // plane 0: (x0,x1)  plane 1: (x0,x2)  plane 2: (x1,x2); grid[...,0] indexes the last (width) dim
+  if (mode == NGM_TRIPLANE_CONCAT) {
+    const int pl = c / C, comp = c - pl * C;
+    const float gx = pl == 2 ? x[1] : x[0], gy = pl == 0 ? x[1] : x[2];
+    return plane_sample(coef + ((size_t)pl * C + comp) * plane_elems, res, gx, gy);
+  }
+  const float a = plane_sample(coef + ((size_t)0 * C + c) * plane_elems, res, x[0], x[1]);
+  const float b = plane_sample(coef + ((size_t)1 * C + c) * plane_elems, res, x[0], x[2]);
+  const float d = plane_sample(coef + ((size_t)2 * C + c) * plane_elems, res, x[1], x[2]);
+  return mode == NGM_TRIPLANE_PRODUCT ? (a * b) * d : (a + b) + d;
+}
+
+// One level of the permutohedral-lattice hash encoding for a 3-D point: writes `feats` values.
+//   table = (capacity, feats) of this level; shift/scale = 3 floats of this level.
+template <int MAXF>
+__device__ __forceinline__ void permuto_level(const float* x, const float* __restrict__ table,
+                                              const float* __restrict__ shift, const float* __restrict__ scale,
+                                              int log2_capacity, int feats, float* out) {
+  constexpr int D = 3, D1 = 4;
+  float cf[D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) cf[i] = __fmul_rn(__fadd_rn(x[i], __ldg(shift + i)), __ldg(scale + i));
+  float E[D1];
+  float sm = 0.0f;
+#pragma unroll
+  for (int i = D; i > 0; --i) {
+    E[i] = __fsub_rn(sm, __fmul_rn((float)i, cf[i - 1]));
+    sm = __fadd_rn(sm, cf[i - 1]);
+  }
+  E[0] = sm;
+  int rem0[D1], rank[D1] = {0, 0, 0, 0};
+  int sum = 0;
+#pragma unroll
+  for (int i = 0; i < D1; ++i) {
+    const float v = __fmul_rn(E[i], 1.0f / D1);
+    const float up = ceilf(v) * D1, down = floorf(v) * D1;
+    rem0[i] = (__fsub_rn(up, E[i]) < __fsub_rn(E[i], down)) ? (int)up : (int)down;
+    sum += rem0[i];
+  }
+  sum /= D1;  // C truncation
+  float resid[D1];
+#pragma unroll
+  for (int i = 0; i < D1; ++i) resid[i] = __fsub_rn(E[i], (float)rem0[i]);
+#pragma unroll
+  for (int i = 0; i < D; ++i)
+#pragma unroll
+    for (int j = i + 1; j < D1; ++j) {
+      if (resid[i] < resid[j]) rank[i]++;
+      else rank[j]++;
+    }
+#pragma unroll
+  for (int i = 0; i < D1; ++i) {
+    rank[i] += sum;
+    if (rank[i] < 0) { rank[i] += D1; rem0[i] += D1; }
+    else if (rank[i] > D) { rank[i] -= D1; rem0[i] -= D1; }
+  }
+  float bary[D + 2] = {0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < D1; ++i) {
+    const float delta = __fmul_rn(__fsub_rn(E[i], (float)rem0[i]), 1.0f / D1);
+    // bary[D - rank] += delta; bary[D + 1 - rank] -= delta  (rank in 0..3; unrolled select keeps registers)
+#pragma unroll
+    for (int r = 0; r <= D + 1; ++r) {
+      if (r == D - rank[i]) bary[r] = __fadd_rn(bary[r], delta);
+      if (r == D + 1 - rank[i]) bary[r] = __fsub_rn(bary[r], delta);
+    }
+  }
+  bary[0] = __fadd_rn(bary[0], __fadd_rn(1.0f, bary[D + 1]));
+  float acc[MAXF];
+#pragma unroll
+  for (int f = 0; f < MAXF; ++f) acc[f] = 0.0f;
+  const uint32_t mask = (1u << log2_capacity) - 1u;
+#pragma unroll
+  for (int r = 0; r < D1; ++r) {
+    uint32_t h = 0;
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      int key = rem0[i] + r;
+      if (rank[i] > D - r) key -= D1;
+      h = (h + (uint32_t)key) * 2531011u;
+    }
+    const float* fv = table + (size_t)(h & mask) * feats;
+#pragma unroll
+    for (int f = 0; f < MAXF; ++f)
+      if (f < feats) acc[f] = __fadd_rn(acc[f], __fmul_rn(bary[r], __ldg(fv + f)));
+  }
+#pragma unroll
+  for (int f = 0; f < MAXF; ++f)
+    if (f < feats) out[f] = acc[f];
+}
+
+}  // namespace ngm

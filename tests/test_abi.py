@@ -1,0 +1,75 @@
+"""CPU-side checks of the C-ABI boundary: the library loads, exports every symbol that
+include/ngm_b200.h declares, and the ctypes mirror has the C struct sizes.  No compute calls."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "ngm_b200.h")
+
+
+@pytest.fixture(scope="module")
+def lib_mod():
+    import __graft_entry__
+
+    __graft_entry__.build()
+    from neural_graph_mapping_b200 import _lib
+
+    return _lib
+
+
+def _declared_symbols():
+    src = open(HEADER).read()
+    return sorted(set(re.findall(r"^\s*(?:int|size_t|uint64_t|const char\*)\s+(ngm_\w+)\s*\(", src, flags=re.M)))
+
+
+def test_header_symbols_exported(lib_mod):
+    declared = _declared_symbols()
+    assert len(declared) >= 9
+    for name in declared:
+        assert hasattr(lib_mod.lib, name), f"{name} declared in ngm_b200.h but not exported"
+    assert sorted(lib_mod.EXPORTS) == declared
+
+
+def test_abi_version_and_struct_sizes(lib_mod):
+    assert lib_mod.lib.ngm_abi_version() == lib_mod.NGM_ABI_VERSION
+    for i, s in enumerate(lib_mod.STRUCTS):
+        assert lib_mod.lib.ngm_struct_size(i) == ctypes.sizeof(s), s.__name__
+    assert lib_mod.lib.ngm_struct_size(99) == 0
+
+
+def test_argument_errors_without_gpu(lib_mod):
+    """Validation happens before any CUDA call, so it is checkable on CPU."""
+    a = lib_mod.NgmSampleArgs()
+    a.num_rays, a.num_samples = 4, 0
+    assert lib_mod.lib.ngm_sample_rays(ctypes.byref(a), None) == -1
+    with pytest.raises(ValueError):
+        lib_mod.check(-1)
+    f = lib_mod.NgmFieldFwdArgs()
+    f.field.num_layers = 99
+    assert lib_mod.lib.ngm_field_fwd(ctypes.byref(f), None) == -1
+    assert b"num_layers" in lib_mod.lib.ngm_last_error()
+
+
+def test_no_cpu_fallback(lib_mod):
+    import torch
+
+    import neural_graph_mapping_b200 as ngm
+
+    fld = ngm.NeuralField("neural_graph_mapping_b200.positional_encodings.PositionalEncodingNeRF",
+                          {"dim_in": 3, "num_octaves": 4}, num_layers=2, dim_out=4, dim_mlp_out=32)
+    assert fld.numel() == 1989 - 1  # reference count minus _neus_sd (800+1056+132)
+    with pytest.raises(RuntimeError, match="no CPU"):
+        fld(torch.rand(8, 3))
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "neural_graph_mapping_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, fn)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", txt, flags=re.M), fn
+                assert "/root/reference" not in txt or fn.endswith((".cu", ".cuh", ".h")), fn

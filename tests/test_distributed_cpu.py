@@ -1,0 +1,68 @@
+"""Host-side multi-process logic on CPU: world_size-2 gloo run of the tile packing + all-gather
+used by the N>1 path (the render itself is GPU-only and is covered by the gpu tests)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, F, R):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import __graft_entry__
+
+    __graft_entry__.build()
+    from neural_graph_mapping_b200 import distributed as D
+
+    assert D.world_info() == (world, rank)
+    n = F * R
+    local = torch.empty(D.FLOATS_PER_RAY * n)
+    rgbd, cvar, dvar, term = D.packed_views(local, n)
+    rgbd.fill_(rank + 0.25)
+    cvar.fill_(rank + 0.5)
+    dvar.fill_(rank + 0.75)
+    term.copy_(torch.arange(n, dtype=torch.float32) + 1000 * rank)
+    buf = D.gather_tiles(local)
+    assert buf.shape == (world, D.FLOATS_PER_RAY * n)
+    for r in range(world):
+        a, b, c, d = D.packed_views(buf[r], n)
+        assert torch.all(a == r + 0.25) and torch.all(b == r + 0.5) and torch.all(c == r + 0.75)
+        assert torch.equal(d, torch.arange(n, dtype=torch.float32) + 1000 * r)
+    # balanced contiguous field shards cover [0, F) exactly once
+    cover = []
+    for r in range(world):
+        s, e = D.shard_range(F, world, r)
+        cover += list(range(s, e))
+    assert cover == list(range(F))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_gather_tiles_gloo_world2():
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, 3, 5), nprocs=2, join=True)
+
+
+def test_shard_range_uneven():
+    from neural_graph_mapping_b200 import distributed as D
+
+    assert [D.shard_range(10, 4, r) for r in range(4)] == [(0, 3), (3, 6), (6, 8), (8, 10)]
+    assert D.shard_range(256, 8, 7) == (224, 256)
+    assert D.world_info() == (1, 0)
