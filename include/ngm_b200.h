@@ -230,6 +230,12 @@ int ngm_field_fwd(const NgmFieldFwdArgs* args, void* stream);   /* models.py:143
 int ngm_composite(const NgmCompositeArgs* args, void* stream);  /* run_mapping.py:610-639, 709-799 */
 int ngm_render_rays_fwd(const NgmRenderArgs* args, void* stream); /* run_mapping.py:440-666 (use_vmap=True) */
 
+/* diagnostics: out(rows,n) = A(rows,k; fp16) x weight(n,k; fp32 -> fp16)^T + bias through the production
+ * tcgen05 plumbing (weight packing, SWIZZLE_128B descriptors, A operand in TMEM, TMEM epilogue).
+ * k % 16 == 0, 16 <= k <= 128, n <= 128; workspace >= 64 KiB. */
+int ngm_debug_tc_gemm(const float* weight, const float* bias, int n, int k, const void* a_half, int64_t rows, float* out,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
 int ngm_field_fwd_workspace_bytes(const NgmFieldFwdArgs* args, size_t* out);
 int ngm_render_workspace_bytes(const NgmRenderArgs* args, size_t* out);
 

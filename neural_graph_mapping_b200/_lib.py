@@ -101,7 +101,7 @@ class NgmRenderArgs(C.Structure):
 STRUCTS = [NgmCamera, NgmFieldDesc, NgmSampleArgs, NgmFieldFwdArgs, NgmCompositeArgs, NgmRenderArgs]
 EXPORTS = [
     "ngm_abi_version", "ngm_last_error", "ngm_struct_size", "ngm_launch_count", "ngm_sample_rays", "ngm_field_fwd", "ngm_composite",
-    "ngm_render_rays_fwd", "ngm_field_fwd_workspace_bytes", "ngm_render_workspace_bytes",
+    "ngm_render_rays_fwd", "ngm_debug_tc_gemm", "ngm_field_fwd_workspace_bytes", "ngm_render_workspace_bytes",
 ]
 
 if not os.path.exists(LIB_PATH):
@@ -120,6 +120,9 @@ for _name, _arg in [("ngm_sample_rays", NgmSampleArgs), ("ngm_field_fwd", NgmFie
                     ("ngm_composite", NgmCompositeArgs), ("ngm_render_rays_fwd", NgmRenderArgs)]:
     getattr(lib, _name).restype = C.c_int
     getattr(lib, _name).argtypes = [C.POINTER(_arg), C.c_void_p]
+lib.ngm_debug_tc_gemm.restype = C.c_int
+lib.ngm_debug_tc_gemm.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p,
+                                  C.c_void_p, C.c_size_t, C.c_void_p]
 lib.ngm_field_fwd_workspace_bytes.restype = C.c_int
 lib.ngm_field_fwd_workspace_bytes.argtypes = [C.POINTER(NgmFieldFwdArgs), C.POINTER(C.c_size_t)]
 lib.ngm_render_workspace_bytes.restype = C.c_int

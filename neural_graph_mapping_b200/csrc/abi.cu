@@ -40,7 +40,10 @@ size_t field_simt_smem_bytes(const NgmFieldDesc& fd, int* act_stride, int* enc_s
 bool field_tc_supported(const NgmFieldDesc& fd, const char** why);
 size_t field_tc_workspace_bytes(const NgmFieldDesc& fd, int num_fields);
 int launch_field_fwd_tc(const NgmFieldFwdArgs& a, cudaStream_t stream);
-int launch_render_fused_tc(const NgmRenderArgs& a, cudaStream_t stream);
+bool render_fused_tc_ok(const NgmRenderArgs& a);
+int launch_render_fused_tc(const NgmRenderArgs& a, void* tc_ws, float* isd_ws, cudaStream_t stream);
+int launch_tc_gemm_debug(const NgmFieldDesc& fd, const void* a_half, long long rows, float* out, void* workspace,
+                         cudaStream_t stream);
 
 static int validate_field(const NgmFieldDesc& fd) {
   NGM_CHECK_ARG(fd.num_layers >= 0 && fd.num_layers + 1 <= NGM_MAX_LINEARS, "num_layers=%d out of range [0,%d]",
@@ -89,11 +92,13 @@ static RenderWorkspace render_workspace(const NgmRenderArgs& a) {
   const int St = a.num_samples + (a.gt ? a.num_samples_guided : 0);
   const size_t n = (size_t)a.num_fields * (size_t)a.rays_per_field * (size_t)St;
   size_t off = 0;
-  w.points_world = off; off = align_up(off + n * 3 * sizeof(float), 256);
-  w.distances = off;    off = align_up(off + n * sizeof(float), 256);
-  w.depths = off;       off = align_up(off + n * sizeof(float), 256);
-  w.outs = off;         off = align_up(off + n * 4 * sizeof(float), 256);
-  w.isd = off;          off = align_up(off + (size_t)a.num_fields * sizeof(float), 256);
+  if (!render_fused_tc_ok(a)) {  // the fused kernel keeps every per-sample intermediate on chip
+    w.points_world = off; off = align_up(off + n * 3 * sizeof(float), 256);
+    w.distances = off;    off = align_up(off + n * sizeof(float), 256);
+    w.depths = off;       off = align_up(off + n * sizeof(float), 256);
+    w.outs = off;         off = align_up(off + n * 4 * sizeof(float), 256);
+  }
+  w.isd = off;         off = align_up(off + (size_t)a.num_fields * sizeof(float), 256);
   w.tc = off;
   if (a.precision == NGM_PREC_FP16) off = align_up(off + field_tc_workspace_bytes(a.field, a.num_fields), 256);
   w.total = off;
@@ -179,6 +184,22 @@ int ngm_composite(const NgmCompositeArgs* a, void* stream) {
   return launch_composite(*a, (cudaStream_t)stream);
 }
 
+int ngm_debug_tc_gemm(const float* weight, const float* bias, int n, int k, const void* a_half, int64_t rows, float* out,
+                      void* workspace, size_t workspace_bytes, void* stream) {
+  NGM_CHECK_ARG(weight && bias && a_half && out && workspace, "null pointer");
+  NGM_CHECK_ARG(n >= 1 && n <= 128 && k >= 16 && k <= 128 && k % 16 == 0 && rows > 0, "need 1<=n<=128, k%%16==0, 16<=k<=128");
+  NgmFieldDesc fd{};
+  fd.encoding = NGM_ENC_NERF;
+  fd.dim_encoding = k;
+  fd.num_layers = 0;
+  fd.dim_mlp_out = 16;
+  fd.dim_out = n;
+  fd.weights[0] = weight;
+  fd.biases[0] = bias;
+  NGM_CHECK_ARG(workspace_bytes >= (size_t)((k + 63) / 64) * ((n + 15) / 16 * 16) * 128 + 1024, "workspace too small");
+  return launch_tc_gemm_debug(fd, a_half, rows, out, workspace, (cudaStream_t)stream);
+}
+
 int ngm_render_workspace_bytes(const NgmRenderArgs* a, size_t* out) {
   NGM_CHECK_ARG(a && out, "null args");
   *out = render_workspace(*a).total;
@@ -206,12 +227,15 @@ int ngm_render_rays_fwd(const NgmRenderArgs* a, void* stream_) {
   if (a->precision == NGM_PREC_FP16) {
     const char* why = nullptr;
     NGM_UNSUPPORTED(!field_tc_supported(a->field, &why), "fp16 tensor-core path unsupported: %s", why);
-    return launch_render_fused_tc(*a, stream);
+  } else {
+    NGM_CHECK_ARG(a->precision == NGM_PREC_FP32, "unknown precision %d", a->precision);
   }
-  NGM_CHECK_ARG(a->precision == NGM_PREC_FP32, "unknown precision %d", a->precision);
-
-  // fp32 (reference-arithmetic) path: the three stage kernels over workspace intermediates.
   char* ws = static_cast<char*>(a->workspace);
+  if (render_fused_tc_ok(*a))  // one fused tcgen05 kernel per render batch
+    return launch_render_fused_tc(*a, ws + w.tc, reinterpret_cast<float*>(ws + w.isd), stream);
+
+  // staged path: the three stage kernels over workspace intermediates (fp32 reference arithmetic,
+  // or fp16 tensor-core field evaluation when a ray has more than 128 samples).
   const int St = a->num_samples + (a->gt ? a->num_samples_guided : 0);
   NgmSampleArgs s{};
   s.cam = a->cam;
@@ -237,7 +261,9 @@ int ngm_render_rays_fwd(const NgmRenderArgs* a, void* stream_) {
   f.field_radius = a->field_radius;
   f.num_fields = a->num_fields;
   f.scale_mode = a->scale_mode;
-  f.precision = NGM_PREC_FP32;
+  f.precision = a->precision;
+  f.workspace = ws + w.tc;
+  f.workspace_bytes = w.total - w.tc;
   if (int rc = ngm_field_fwd(&f, stream_)) return rc;
 
   NgmCompositeArgs c{};

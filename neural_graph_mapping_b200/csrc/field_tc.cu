@@ -1,20 +1,736 @@
-// fp16-operand tensor-core (tcgen05) field / fused render path -- placeholder until the kernel lands.
+// fp16-operand tensor-core path (tcgen05 / TMEM / TMA-engine bulk copies), sm_100a only.
+//
+//   * render_fused: ONE kernel per render batch = sampler -> world->local -> NeRF encoding ->
+//     per-field MLP on tcgen05 -> front-to-back alpha composite (ngm/run_mapping.py:440-666,
+//     use_vmap=True).  HBM traffic is ~60 B/ray in + 36 B/ray out; the kernel is tensor-bound.
+//   * field_fwd: the same MLP pipeline with points read from HBM and raw outputs written back
+//     (ngm/models.py:329-345) -- the stage form, also used for St > 128.
+//
+// Design (one persistent CTA per SM, 288 threads):
+//   warp 0          : loads the field's pre-swizzled fp16 weight image into shared memory with
+//                     cp.async.bulk (TMA engine) and issues every tcgen05.mma (one elected lane)
+//   warps 1-4 / 5-8 : two "tile slots".  A slot's 128 threads own the 128 rows (= sample points)
+//                     of one tile: thread <-> TMEM lane.  They generate the sample, encode it,
+//                     tcgen05.st the fp16 features as the A operand into TMEM, and after every
+//                     layer tcgen05.ld the fp32 accumulator, apply bias+ReLU (packed half2),
+//                     and tcgen05.st the next A operand.  Activations never touch shared memory
+//                     or HBM; shared memory only feeds the B operand (weights), so the MMA reads
+//                     64 B/clk of shared memory instead of 128.
+//   While slot 0 is in an epilogue the tensor pipe runs slot 1's layer and vice versa; the MMA
+//   warp polls both slots' "A ready" mbarriers and issues whichever is ready.
+// TMEM (512 columns): slot s uses columns [256 s, 256 s + 128) for the fp32 accumulator D and
+// [256 s + 128, 256 s + 192) for the fp16 A operand (K <= 128).
+#include <cuda_fp16.h>
+
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace ngm {
 
+namespace {
+
+constexpr int kThreads = 288;
+constexpr int kTmemCols = 512;
+constexpr int kSlotCols = 256;
+constexpr int kACol = 128;
+constexpr uint32_t kMaxImageBytes = 200 * 1024;
+
+struct TcLayer {
+  int n_pad, k_pad, atoms;
+  uint32_t off;  // byte offset of the layer's B image inside the field image
+};
+
+struct TcImage {
+  int num_linears;
+  TcLayer layer[NGM_MAX_LINEARS];
+  uint32_t bias_h2_off;    // uint32 half2 biases of the hidden layers: [L][W/2]
+  uint32_t bias_last_off;  // fp32 biases of the last layer: [n_last_pad]
+  uint32_t total_bytes;    // multiple of 16
+};
+
+TcImage make_image(const NgmFieldDesc& fd, int EP) {
+  TcImage im{};
+  const int L = fd.num_layers, W = fd.dim_mlp_out;
+  im.num_linears = L + 1;
+  uint32_t off = 0;
+  for (int l = 0; l <= L; ++l) {
+    TcLayer& y = im.layer[l];
+    y.n_pad = l == L ? (fd.dim_out + 15) / 16 * 16 : W;
+    y.k_pad = l == 0 ? EP : W;
+    y.atoms = (y.k_pad + 63) / 64;
+    y.off = off;
+    off += (uint32_t)y.atoms * y.n_pad * 128;
+  }
+  im.bias_h2_off = off;
+  off += (uint32_t)L * (W / 2) * 4;
+  off = (off + 15) / 16 * 16;
+  im.bias_last_off = off;
+  off += (uint32_t)im.layer[L].n_pad * 4;
+  im.total_bytes = (off + 15) / 16 * 16;
+  return im;
+}
+
+// ---- weight packing: fp32 (out,in) tables -> per-field fp16 image in the UMMA K-major SWIZZLE_128B layout ----
+struct PackParams {
+  NgmFieldDesc fd;
+  TcImage im;
+  const long long* field_slots;
+  uint8_t* images;
+  int E;
+};
+
+__global__ void __launch_bounds__(256) pack_weights_kernel(PackParams p) {
+  const int f = blockIdx.x;
+  const long long slot = p.field_slots ? p.field_slots[f] : f;
+  uint8_t* img = p.images + (size_t)f * p.im.total_bytes;
+  const int L = p.fd.num_layers, W = p.fd.dim_mlp_out;
+  for (int l = 0; l <= L; ++l) {
+    const TcLayer y = p.im.layer[l];
+    const int N = l == L ? p.fd.dim_out : W;
+    const int K = l == 0 ? p.E : W;
+    const float* Wg = p.fd.weights[l] + slot * p.fd.weight_stride[l];
+    const int chunks = y.atoms * y.n_pad * 8;  // 16-byte chunks (8 halves)
+    for (int c = threadIdx.x; c < chunks; c += blockDim.x) {
+      const int atom = c / (y.n_pad * 8);
+      const int n = (c / 8) % y.n_pad;
+      const int ck = c % 8;
+      __half h[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int k = atom * 64 + ck * 8 + i;
+        h[i] = __float2half_rn((n < N && k < K) ? __ldg(Wg + (size_t)n * K + k) : 0.0f);
+      }
+      uint8_t* dst = img + y.off + (size_t)atom * y.n_pad * 128 + (size_t)n * 128 + ((ck ^ (n & 7)) * 16);
+      *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(h);
+    }
+  }
+  uint32_t* bh = reinterpret_cast<uint32_t*>(img + p.im.bias_h2_off);
+  for (int l = 0; l < L; ++l) {
+    const float* Bg = p.fd.biases[l] + slot * p.fd.bias_stride[l];
+    for (int j = threadIdx.x; j < W / 2; j += blockDim.x)
+      bh[l * (W / 2) + j] = ptx::pack_half2(__ldg(Bg + 2 * j), __ldg(Bg + 2 * j + 1));
+  }
+  float* bl = reinterpret_cast<float*>(img + p.im.bias_last_off);
+  const float* Bg = p.fd.biases[L] + slot * p.fd.bias_stride[L];
+  for (int j = threadIdx.x; j < p.im.layer[L].n_pad; j += blockDim.x) bl[j] = j < p.fd.dim_out ? __ldg(Bg + j) : 0.0f;
+}
+
+// ---- main kernel ---------------------------------------------------------------------------------
+struct TcParams {
+  TcImage im;
+  const uint8_t* images;
+  int num_fields;
+  int E, EP, W, L, dim_out;
+  int nerf_start;
+  // field poses
+  const float* positions;
+  const float* orientations;
+  const long long* field_slots;
+  int scale_mode;
+  float field_radius;
+  // tiles
+  long long tiles_per_field, total_tiles;
+  // MODE 1 (field fwd)
+  const float* points;
+  long long points_per_field;
+  float* out;
+  const __half* raw_a;  // debug: A operand given directly, (num_fields*points_per_field, EP)
+  // MODE 0 (fused render)
+  NgmCamera cam;
+  const long long* ijs;
+  const float* c2ws;
+  const float* near;
+  const float* far;
+  const float* gt;
+  RayJitter jit;
+  float near_scalar, far_scalar, range_guided;
+  int c2w_per_ray, S, G, St, Sp, rpt;
+  long long rays_per_field;
+  int geometry_mode, overwrite;
+  float geometry_factor, color_factor, truncation;
+  const float* neus_isd;  // (num_fields)
+  float* rgbd;
+  float* color_var;
+  float* depth_var;
+  float* term_prob;
+  float* freespace;
+  uint8_t* freespace_mask;
+  float* tsdf;
+  uint8_t* tsdf_mask;
+};
+
+struct Smem {
+  uint64_t a_ready[2];
+  uint64_t d_ready[2];
+  uint64_t w_ready;
+  uint32_t tmem_base;
+  uint32_t pad_;
+  float sm_d[2][128];     // per slot: sample distance (merge exchange / density deltas)
+  float sm_g[2][128];     // per slot: geometry after the behind-camera overwrite (neus neighbour)
+  float sm_part[2][4][8]; // per slot, per warp: scan tails and partial sums
+};
+
+template <int NW>
+__device__ __forceinline__ void tmem_store_words(uint32_t addr, const uint32_t* w) {
+  static_assert(NW % 8 == 0, "word count must be a multiple of 8");
+#pragma unroll
+  for (int i = 0; i + 16 <= NW; i += 16) ptx::tmem_st16(addr + i, w + i);
+  if (NW % 16) ptx::tmem_st8(addr + NW - 8, w + NW - 8);
+}
+
+// sin(pi t), cos(pi t) with exact range reduction to [-1, 1]
+__device__ __forceinline__ void sincospi_fast(float t, float& s, float& c) {
+  const float r = fmaf(-2.0f, rintf(0.5f * t), t);
+  const float a = 3.14159265358979f * r;
+  s = __sinf(a);
+  c = __cosf(a);
+}
+
+template <int OCT>
+__device__ __forceinline__ void encode_nerf_to_tmem(uint32_t a_addr, float3 x, int start_octave, bool valid) {
+  constexpr int E = 6 * OCT;
+  constexpr int EP = (E + 15) / 16 * 16;
+  float fe[EP];
+#pragma unroll
+  for (int i = 0; i < EP; ++i) fe[i] = 0.0f;
+  const float base = valid ? exp2f((float)start_octave) : 0.0f;
+  const float xs[3] = {valid ? x.x : 0.0f, valid ? x.y : 0.0f, valid ? x.z : 0.0f};
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const float t0 = xs[d] * base;
+#pragma unroll
+    for (int o = 0; o < OCT; ++o) {
+      float s, c;
+      sincospi_fast(t0 * (float)(1 << o), s, c);
+      fe[d * OCT + o] = s;
+      fe[3 * OCT + d * OCT + o] = valid ? c : 0.0f;
+    }
+  }
+  uint32_t w[EP / 2];
+#pragma unroll
+  for (int j = 0; j < EP / 2; ++j) w[j] = ptx::pack_half2(fe[2 * j], fe[2 * j + 1]);
+  tmem_store_words<EP / 2>(a_addr, w);
+}
+
+// hidden-layer epilogue: D (fp32, W columns) -> relu(D + b) as fp16 -> A
+__device__ __forceinline__ void hidden_epilogue(uint32_t d_addr, uint32_t a_addr, const uint32_t* bias2, int W) {
+  int c = 0;
+  for (; c + 32 <= W; c += 32) {
+    uint32_t v[32];
+    ptx::tmem_ld32(d_addr + c, v);
+    ptx::tc_wait_ld();
+    uint32_t w[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      w[i] = ptx::bias_relu_half2(ptx::pack_half2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])),
+                                  bias2[c / 2 + i]);
+    ptx::tmem_st16(a_addr + c / 2, w);
+  }
+  if (c < W) {  // W % 32 == 16
+    uint32_t v[16];
+    ptx::tmem_ld16(d_addr + c, v);
+    ptx::tc_wait_ld();
+    uint32_t w[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      w[i] = ptx::bias_relu_half2(ptx::pack_half2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])),
+                                  bias2[c / 2 + i]);
+    ptx::tmem_st8(a_addr + c / 2, w);
+  }
+}
+
+__device__ __forceinline__ float seg_sum(float v, int width) {
+  for (int o = width >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---- compositor on one tile slot (128 threads, rows with ray stride Sp) --------------------------
+// ngm/run_mapping.py:610-639, 709-799.  `valid` = this row is a real sample of a real ray.
+__device__ __forceinline__ void composite_rows(const TcParams& p, Smem& sm, int s, int row, int qwarp, int lane, int barrier_id,
+                                               long long ray_global, int k, bool valid, float c0, float c1, float c2, float g,
+                                               float d, float z, float gt, bool has_gt, float isd_gamma) {
+  const int Sp = p.Sp, St = p.St;
+  const int mode = p.geometry_mode;
+  const bool drop_last = (mode == NGM_GEOM_DENSITY || mode == NGM_GEOM_NEUS);
+  const int Se = drop_last ? St - 1 : St;
+  if (p.overwrite && z < 0.0f) g = (mode == NGM_GEOM_OCCUPANCY || mode == NGM_GEOM_DENSITY) ? -100.0f : 1.0f;
+  if (valid) {
+    const long long idx = ray_global * St + k;
+    if (p.freespace) {
+      const float thr = has_gt ? (gt - p.truncation) * (gt != 0.0f ? 1.0f : 0.0f) : 0.0f;
+      p.freespace[idx] = g * p.truncation;
+      p.freespace_mask[idx] = (has_gt && d < thr) ? 1 : 0;
+    }
+    if (p.tsdf) {
+      const float delta = gt - d;
+      p.tsdf[idx] = g * p.truncation - delta;
+      p.tsdf_mask[idx] = (has_gt && fabsf(delta) < p.truncation && gt != 0.0f) ? 1 : 0;
+    }
+  }
+  float occ = 0.0f;
+  if (drop_last) {  // needs the next sample of the same ray
+    sm.sm_d[s][row] = d;
+    sm.sm_g[s][row] = g;
+    ptx::named_bar_sync(barrier_id, 128);
+    if (valid && k < Se) {
+      if (mode == NGM_GEOM_DENSITY) {
+        const float delta = sm.sm_d[s][row + 1] - d;
+        occ = 1.0f - expf(-delta * fmaxf(g, 0.0f));
+      } else {
+        const float t0 = sigmoidf(isd_gamma * g), t1 = sigmoidf(isd_gamma * sm.sm_g[s][row + 1]);
+        occ = fmaxf((t0 - t1) / (t0 + 1e-5f), 0.0f);
+      }
+    }
+  } else if (valid) {
+    if (mode == NGM_GEOM_NRGBD) {
+      const float t = p.geometry_factor * g;
+      occ = (4.0f * sigmoidf(t)) * sigmoidf(-t);
+    } else {
+      occ = sigmoidf(p.geometry_factor * g);
+    }
+  }
+  // exclusive product scan of (1 - occ) along the ray
+  const int wseg = Sp < 32 ? Sp : 32;  // segment width inside a warp
+  float incl = 1.0f - occ;
+  for (int o = 1; o < wseg; o <<= 1) {
+    const float n = __shfl_up_sync(0xffffffffu, incl, o, wseg);
+    if ((lane & (wseg - 1)) >= o) incl *= n;
+  }
+  float excl = __shfl_up_sync(0xffffffffu, incl, 1, wseg);
+  if ((lane & (wseg - 1)) == 0) excl = 1.0f;
+  const int wpr = Sp >> 5;  // warps per ray (0 when Sp < 32)
+  if (wpr > 1) {
+    if (lane == 31) sm.sm_part[s][qwarp][0] = incl;
+    ptx::named_bar_sync(barrier_id, 128);
+    float carry = 1.0f;
+    const int first = qwarp & ~(wpr - 1);
+    for (int w = first; w < qwarp; ++w) carry *= sm.sm_part[s][w][0];
+    excl *= carry;
+    ptx::named_bar_sync(barrier_id, 128);  // sm_part reused below
+  }
+  const float wgt = occ * excl;
+  float P = seg_sum(wgt, wseg), D = seg_sum(wgt * z, wseg);
+  float C0 = seg_sum(wgt * c0, wseg), C1 = seg_sum(wgt * c1, wseg), C2 = seg_sum(wgt * c2, wseg);
+  if (wpr > 1) {
+    if (lane == 0) {
+      float* q = sm.sm_part[s][qwarp];
+      q[0] = P; q[1] = D; q[2] = C0; q[3] = C1; q[4] = C2;
+    }
+    ptx::named_bar_sync(barrier_id, 128);
+    const int first = qwarp & ~(wpr - 1);
+    P = D = C0 = C1 = C2 = 0.0f;
+    for (int w = first; w < first + wpr; ++w) {
+      const float* q = sm.sm_part[s][w];
+      P += q[0]; D += q[1]; C0 += q[2]; C1 += q[3]; C2 += q[4];
+    }
+    ptx::named_bar_sync(barrier_id, 128);
+  }
+  float t;
+  t = D - z;   float vz = seg_sum(wgt * (t * t), wseg);
+  t = C0 - c0; float v0 = seg_sum(wgt * (t * t), wseg);
+  t = C1 - c1; float v1 = seg_sum(wgt * (t * t), wseg);
+  t = C2 - c2; float v2 = seg_sum(wgt * (t * t), wseg);
+  if (wpr > 1) {
+    if (lane == 0) {
+      float* q = sm.sm_part[s][qwarp];
+      q[0] = vz; q[1] = v0; q[2] = v1; q[3] = v2;
+    }
+    ptx::named_bar_sync(barrier_id, 128);
+    const int first = qwarp & ~(wpr - 1);
+    vz = v0 = v1 = v2 = 0.0f;
+    for (int w = first; w < first + wpr; ++w) {
+      const float* q = sm.sm_part[s][w];
+      vz += q[0]; v0 += q[1]; v1 += q[2]; v2 += q[3];
+    }
+  }
+  if (k == 0 && ray_global >= 0) {
+    reinterpret_cast<float4*>(p.rgbd)[ray_global] = make_float4(C0, C1, C2, D);
+    if (p.color_var) {
+      p.color_var[ray_global * 3 + 0] = v0;
+      p.color_var[ray_global * 3 + 1] = v1;
+      p.color_var[ray_global * 3 + 2] = v2;
+    }
+    if (p.depth_var) p.depth_var[ray_global] = vz;
+    if (p.term_prob) p.term_prob[ray_global] = 1.0f - (1.0f - P);
+  }
+}
+
+template <int MODE, int OCT>
+__global__ void __launch_bounds__(kThreads, 1) tc_kernel(const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // weights image first (1024-B aligned for SWIZZLE_128B), bookkeeping after it
+  uint8_t* wsm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  Smem& sm = *reinterpret_cast<Smem*>(wsm + (p.im.total_bytes + 127) / 128 * 128);
+  const uint32_t wsm_addr = ptx::smem_u32(wsm);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (warp == 0) ptx::tmem_alloc(&sm.tmem_base, kTmemCols);
+  if (tid == 32) {
+    ptx::mbar_init(&sm.a_ready[0], 128);
+    ptx::mbar_init(&sm.a_ready[1], 128);
+    ptx::mbar_init(&sm.d_ready[0], 1);
+    ptx::mbar_init(&sm.d_ready[1], 1);
+    ptx::mbar_init(&sm.w_ready, 1);
+    ptx::fence_mbar_init();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = sm.tmem_base;
+
+  // contiguous, balanced tile range of this CTA
+  const long long t_begin = p.total_tiles * blockIdx.x / gridDim.x;
+  const long long t_end = p.total_tiles * (blockIdx.x + 1) / gridDim.x;
+
+  uint32_t w_phase = 0;
+  uint32_t pa[2] = {0, 0};  // MMA warp: parity of a_ready per slot
+  uint32_t pd = 0;          // epilogue thread: parity of its slot's d_ready
+  const int L = p.L, W = p.W;
+
+  long long t = t_begin;
+  while (t < t_end) {
+    const long long f = t / p.tiles_per_field;
+    long long seg_end = (f + 1) * p.tiles_per_field;
+    if (seg_end > t_end) seg_end = t_end;
+    const int ntiles = (int)(seg_end - t);
+    const long long tile0_in_field = t - f * p.tiles_per_field;
+
+    // ---- stage this field's weight image (TMA engine) ----
+    if (tid == 0) {
+      const uint8_t* src = p.images + (size_t)f * p.im.total_bytes;
+      ptx::mbar_arrive_expect_tx(&sm.w_ready, p.im.total_bytes);
+      for (uint32_t o = 0; o < p.im.total_bytes; o += 32768) {
+        const uint32_t n = p.im.total_bytes - o < 32768 ? p.im.total_bytes - o : 32768;
+        ptx::bulk_g2s(wsm + o, src + o, n, &sm.w_ready);
+      }
+    }
+    ptx::mbar_wait(&sm.w_ready, w_phase);
+    w_phase ^= 1;
+
+    if (warp == 0) {
+      // ===================== MMA issuer =====================
+      int remaining[2] = {(ntiles + 1) / 2, ntiles / 2};
+      int layer[2] = {0, 0};
+      while (remaining[0] > 0 || remaining[1] > 0) {
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          if (remaining[s] > 0 && ptx::mbar_test(&sm.a_ready[s], pa[s])) {
+            pa[s] ^= 1;
+            ptx::tc_fence_after();
+            if (lane == 0) {
+              const TcLayer y = p.im.layer[layer[s]];
+              const uint32_t idesc = ptx::make_idesc_f16(y.n_pad);
+              const uint32_t d_addr = tmem_base + s * kSlotCols;
+              const uint32_t a_addr = d_addr + kACol;
+              const int ksteps = y.k_pad / 16;
+              for (int ks = 0; ks < ksteps; ++ks) {
+                const uint32_t boff = y.off + (uint32_t)(ks >> 2) * (uint32_t)y.n_pad * 128u + (uint32_t)(ks & 3) * 32u;
+                ptx::mma_f16_ts(d_addr, a_addr + ks * 8, ptx::make_smem_desc_sw128(wsm_addr + boff), idesc, ks > 0);
+              }
+              ptx::mma_commit(&sm.d_ready[s]);
+            }
+            __syncwarp();
+            if (++layer[s] > L) {
+              layer[s] = 0;
+              --remaining[s];
+            }
+          }
+        }
+      }
+    } else {
+      // ===================== tile-slot threads =====================
+      const int s = (warp - 1) >> 2;
+      const int qwarp = warp & 3;  // TMEM lane quadrant this warp may access
+      const int row = qwarp * 32 + lane;
+      const uint32_t d_addr = tmem_base + ((uint32_t)(qwarp * 32) << 16) + s * kSlotCols;
+      const uint32_t a_addr = d_addr + kACol;
+      const uint32_t* bias2 = reinterpret_cast<const uint32_t*>(wsm + p.im.bias_h2_off);
+      const float* bias_last = reinterpret_cast<const float*>(wsm + p.im.bias_last_off);
+      const long long slot = p.field_slots ? p.field_slots[f] : f;
+      const int barrier_id = 1 + s;
+
+      for (int ti = s; ti < ntiles; ti += 2) {
+        const long long tile_in_field = tile0_in_field + ti;
+        // ---------- front end: make the A operand of layer 0 ----------
+        float3 x = make_float3(0.f, 0.f, 0.f);
+        bool valid = false;
+        // fused-render per-row state kept for the compositor
+        long long ray_global = -1;
+        int k = 0;
+        float d = 0.f, z = 0.f, gt = 0.f;
+        if (MODE == 1) {
+          const long long gp = tile_in_field * 128 + row;
+          valid = gp < p.points_per_field;
+          if (p.raw_a) {
+            const long long rr = valid ? f * p.points_per_field + gp : 0;
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(p.raw_a + rr * p.EP);
+            for (int c = 0; c < p.EP / 2; c += 8) {
+              uint32_t w[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) w[i] = valid ? __ldg(src + c + i) : 0u;
+              ptx::tmem_st8(a_addr + c, w);
+            }
+          } else if (valid) {
+            const float* src = p.points + (f * p.points_per_field + gp) * 3;
+            x = make_float3(__ldg(src), __ldg(src + 1), __ldg(src + 2));
+          }
+        } else {
+          const int rit = row / p.Sp;
+          k = row - rit * p.Sp;
+          const long long r = tile_in_field * p.rpt + rit;
+          const bool ray_ok = r < p.rays_per_field;
+          if (ray_ok) ray_global = f * p.rays_per_field + r;
+          valid = ray_ok && k < p.St;
+          if (ray_ok) {
+            const long long ray = ray_global;
+            const float nr = p.near ? __ldg(p.near + ray) : p.near_scalar;
+            const float fr = p.far ? __ldg(p.far + ray) : p.far_scalar;
+            if (p.gt) gt = __ldg(p.gt + ray);
+            const int S = p.S, G = p.G, St = p.St;
+            if (G > 0) {
+              // depth-guided merge (run_mapping.py:521-545): own distance + rank, then exchange by rank
+              float glo, ghi;
+              guided_window(nr, fr, gt, p.range_guided, glo, ghi);
+              float dk = 0.f;
+              int pos = k;
+              if (k < S) {
+                dk = stratified_distance(nr, fr, k, S, p.jit.coarse(ray, k, S, St));
+                pos = k + count_before(dk, glo, ghi, G, true, [&](int j) { return p.jit.guided(ray, j, S, G, St); });
+              } else if (k < St) {
+                const int kg = k - S;
+                dk = stratified_distance(glo, ghi, kg, G, p.jit.guided(ray, kg, S, G, St));
+                pos = kg + count_before(dk, nr, fr, S, false, [&](int j) { return p.jit.coarse(ray, j, S, St); });
+              }
+              if (k < St) sm.sm_d[s][rit * p.Sp + pos] = dk;
+            } else if (k < St) {
+              d = stratified_distance(nr, fr, k, S, p.jit.coarse(ray, k, S, St));
+            }
+          }
+          if (p.G > 0) {
+            ptx::named_bar_sync(barrier_id, 128);
+            d = sm.sm_d[s][row];
+            ptx::named_bar_sync(barrier_id, 128);
+          }
+          if (valid) {
+            const longlong2 ij = __ldg(reinterpret_cast<const longlong2*>(p.ijs) + ray_global);
+            const float3 dir = ij_to_direction(ij.x, ij.y, p.cam);
+            const float3 pc = make_float3(dir.x * d, dir.y * d, dir.z * d);
+            z = -pc.z;
+            const float* m = p.c2ws + (p.c2w_per_ray ? ray_global * 16 : 0);
+            float mm[12];
+#pragma unroll
+            for (int i = 0; i < 12; ++i) mm[i] = __ldg(m + i);
+            x = transform_point(mm, pc);
+          }
+        }
+        if (!(MODE == 1 && p.raw_a)) {
+          if (valid && p.positions) {
+            const float* c = p.positions + slot * 3;
+            const float* q = p.orientations + slot * 4;
+            x = make_float3(x.x - __ldg(c), x.y - __ldg(c + 1), x.z - __ldg(c + 2));
+            x = quat_inv_rotate(__ldg(q), __ldg(q + 1), __ldg(q + 2), __ldg(q + 3), x);
+          }
+          if (valid) x = scale_local(x, p.scale_mode, p.field_radius);
+          encode_nerf_to_tmem<OCT>(a_addr, x, p.nerf_start, valid);
+        }
+        ptx::tc_wait_st();
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&sm.a_ready[s]);
+
+        // ---------- hidden layers ----------
+        for (int l = 0; l < L; ++l) {
+          ptx::mbar_wait(&sm.d_ready[s], pd);
+          pd ^= 1;
+          ptx::tc_fence_after();
+          hidden_epilogue(d_addr, a_addr, bias2 + l * (W / 2), W);
+          ptx::tc_wait_st();
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(&sm.a_ready[s]);
+        }
+        // ---------- last layer ----------
+        ptx::mbar_wait(&sm.d_ready[s], pd);
+        pd ^= 1;
+        ptx::tc_fence_after();
+        if (MODE == 1) {
+          const long long gp = tile_in_field * 128 + row;
+          float* o = p.out + (f * p.points_per_field + gp) * p.dim_out;
+          for (int c = 0; c < p.im.layer[L].n_pad; c += 16) {
+            uint32_t v[16];
+            ptx::tmem_ld16(d_addr + c, v);
+            ptx::tc_wait_ld();
+            if (valid) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (c + i < p.dim_out) o[c + i] = __uint_as_float(v[i]) + bias_last[c + i];
+            }
+          }
+        } else {
+          uint32_t v[4];
+          ptx::tmem_ld4(d_addr, v);
+          ptx::tc_wait_ld();
+          const float c0 = p.color_factor * (__uint_as_float(v[0]) + bias_last[0]);
+          const float c1 = p.color_factor * (__uint_as_float(v[1]) + bias_last[1]);
+          const float c2 = p.color_factor * (__uint_as_float(v[2]) + bias_last[2]);
+          const float g = __uint_as_float(v[3]) + bias_last[3];
+          const float isd_gamma = p.neus_isd ? __ldg(p.neus_isd + f) * p.geometry_factor : 0.0f;
+          composite_rows(p, sm, s, row, qwarp, lane, barrier_id, ray_global, k, valid, c0, c1, c2, g, d, z, gt,
+                         p.gt != nullptr, isd_gamma);
+        }
+        // all TMEM reads of this tile are complete (wait::ld above) before the next tile's
+        // front end overwrites A and its layer-0 MMA overwrites D.
+        ptx::tc_fence_before();
+      }
+    }
+    t = seg_end;
+    ptx::fence_proxy_async();  // generic-proxy reads of the image before the next bulk copy overwrites it
+    __syncthreads();
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) ptx::tmem_dealloc(tmem_base, kTmemCols);
+}
+
+int nerf_octaves_supported(int o) { return o == 4 || o == 8; }
+
+template <int MODE>
+int launch_tc(const TcParams& p, int octaves, size_t smem, int grid, cudaStream_t stream) {
+  auto go = [&](auto kernel) -> int {
+    NGM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kernel<<<grid, kThreads, smem, stream>>>(p);
+    return check_launch("tc_kernel");
+  };
+  switch (octaves) {
+    case 4: return go(tc_kernel<MODE, 4>);
+    case 8: return go(tc_kernel<MODE, 8>);
+    default: set_error("tcgen05 path: unsupported num_octaves %d", octaves); return NGM_ERR_UNSUPPORTED;
+  }
+}
+
+int ep_of(const NgmFieldDesc& fd) { return (fd.dim_encoding + 15) / 16 * 16; }
+
+int fill_common(TcParams& p, const NgmFieldDesc& fd, int num_fields, const float* positions, const float* orientations,
+                const int64_t* slots, int scale_mode, float radius, void* workspace, cudaStream_t stream) {
+  p.E = fd.dim_encoding;
+  p.EP = ep_of(fd);
+  p.W = fd.dim_mlp_out;
+  p.L = fd.num_layers;
+  p.dim_out = fd.dim_out;
+  p.nerf_start = fd.nerf_start_octave;
+  p.im = make_image(fd, p.EP);
+  p.images = static_cast<const uint8_t*>(workspace);
+  p.num_fields = num_fields;
+  p.positions = positions;
+  p.orientations = orientations;
+  p.field_slots = reinterpret_cast<const long long*>(slots);
+  p.scale_mode = scale_mode;
+  p.field_radius = radius;
+  PackParams pk{fd, p.im, p.field_slots, static_cast<uint8_t*>(workspace), fd.dim_encoding};
+  pack_weights_kernel<<<num_fields, 256, 0, stream>>>(pk);
+  return check_launch("pack_weights_kernel");
+}
+
+// >= 120 KB so that exactly one CTA (one 512-column TMEM allocation) is resident per SM
+size_t tc_smem_bytes(const TcImage& im) {
+  const size_t need = 1024 + (im.total_bytes + 127) / 128 * 128 + sizeof(Smem) + 128;
+  return need < 120 * 1024 ? 120 * 1024 : need;
+}
+
+}  // namespace
+
 bool field_tc_supported(const NgmFieldDesc& fd, const char** why) {
-  if (why) *why = "tcgen05 kernel not built in this revision";
-  return false;
+  const char* w = nullptr;
+  if (fd.encoding != NGM_ENC_NERF) w = "only the NeRF encoding is on the tcgen05 path in this revision";
+  else if (!nerf_octaves_supported(fd.nerf_num_octaves)) w = "num_octaves must be 4 or 8";
+  else if (fd.skip_mode != NGM_SKIP_NO) w = "skip connections are only on the fp32 path";
+  else if (fd.dim_mlp_out % 16 != 0 || fd.dim_mlp_out < 16 || fd.dim_mlp_out > 128) w = "dim_mlp_out must be a multiple of 16 in [16,128]";
+  else if (fd.dim_out > 128) w = "dim_out > 128";
+  else if (make_image(fd, ep_of(fd)).total_bytes > kMaxImageBytes) w = "weight image exceeds shared memory (too many layers)";
+  if (why) *why = w;
+  return w == nullptr;
 }
-size_t field_tc_workspace_bytes(const NgmFieldDesc&, int) { return 0; }
-int launch_field_fwd_tc(const NgmFieldFwdArgs&, cudaStream_t) {
-  set_error("tcgen05 kernel not built in this revision");
-  return NGM_ERR_UNSUPPORTED;
+
+size_t field_tc_workspace_bytes(const NgmFieldDesc& fd, int num_fields) {
+  const char* why;
+  if (!field_tc_supported(fd, &why)) return 0;
+  return (size_t)make_image(fd, ep_of(fd)).total_bytes * (size_t)(num_fields > 0 ? num_fields : 1);
 }
-int launch_render_fused_tc(const NgmRenderArgs&, cudaStream_t) {
-  set_error("tcgen05 kernel not built in this revision");
-  return NGM_ERR_UNSUPPORTED;
+
+int launch_field_fwd_tc(const NgmFieldFwdArgs& a, cudaStream_t stream) {
+  TcParams p{};
+  if (int rc = fill_common(p, a.field, a.num_fields, a.positions, a.orientations, a.field_slots, a.scale_mode,
+                           a.field_radius, a.workspace, stream))
+    return rc;
+  p.points = a.points;
+  p.points_per_field = a.points_per_field;
+  p.out = a.out;
+  p.tiles_per_field = (a.points_per_field + 127) / 128;
+  p.total_tiles = p.tiles_per_field * a.num_fields;
+  const int sms = num_sms();
+  const int grid = (int)(p.total_tiles < sms ? p.total_tiles : sms);
+  return launch_tc<1>(p, a.field.nerf_num_octaves, tc_smem_bytes(p.im), grid, stream);
+}
+
+// debug / unit-test entry: D = A (fp16, given) x W^T with the production weight packing, smem
+// descriptors, TMEM A operand and epilogue -- isolates the tcgen05 plumbing from the renderer.
+int launch_tc_gemm_debug(const NgmFieldDesc& fd, const void* a_half, long long rows, float* out, void* workspace,
+                         cudaStream_t stream) {
+  TcParams p{};
+  NgmFieldDesc f2 = fd;
+  if (int rc = fill_common(p, f2, 1, nullptr, nullptr, nullptr, NGM_SCALE_NO, 0.f, workspace, stream)) return rc;
+  p.raw_a = static_cast<const __half*>(a_half);
+  p.points_per_field = rows;
+  p.out = out;
+  p.tiles_per_field = (rows + 127) / 128;
+  p.total_tiles = p.tiles_per_field;
+  const int sms = num_sms();
+  const int grid = (int)(p.total_tiles < sms ? p.total_tiles : sms);
+  return launch_tc<1>(p, 8, tc_smem_bytes(p.im), grid, stream);
+}
+
+int launch_neus_isd(const float* sd, const int64_t* slots, int num_fields, float* out, cudaStream_t stream);
+
+bool render_fused_tc_ok(const NgmRenderArgs& a) {
+  const int St = a.num_samples + (a.gt ? a.num_samples_guided : 0);
+  const char* why;
+  return a.precision == NGM_PREC_FP16 && St <= 128 && a.field.dim_out == 4 && field_tc_supported(a.field, &why);
+}
+
+int launch_render_fused_tc(const NgmRenderArgs& a, void* tc_ws, float* isd_ws, cudaStream_t stream) {
+  TcParams p{};
+  if (int rc = fill_common(p, a.field, a.num_fields, a.positions, a.orientations, a.field_slots, a.scale_mode,
+                           a.field_radius, tc_ws, stream))
+    return rc;
+  p.cam = a.cam;
+  p.ijs = reinterpret_cast<const long long*>(a.ijs);
+  p.c2ws = a.c2ws;
+  p.near = a.near; p.far = a.far; p.gt = a.gt;
+  p.jit = RayJitter{a.jitter, a.jitter_guided, a.seed, a.offset};
+  p.near_scalar = a.near_scalar; p.far_scalar = a.far_scalar; p.range_guided = a.range_guided;
+  p.c2w_per_ray = a.c2w_per_ray;
+  p.S = a.num_samples;
+  p.G = a.gt ? a.num_samples_guided : 0;
+  p.St = p.S + p.G;
+  int Sp = 1;
+  while (Sp < p.St) Sp <<= 1;
+  p.Sp = Sp;
+  p.rpt = 128 / Sp;
+  p.rays_per_field = a.rays_per_field;
+  p.geometry_mode = a.geometry_mode;
+  p.overwrite = a.overwrite_behind_camera;
+  p.geometry_factor = a.geometry_factor; p.color_factor = a.color_factor; p.truncation = a.truncation;
+  if (a.geometry_mode == NGM_GEOM_NEUS) {
+    if (int rc = launch_neus_isd(a.neus_sd, a.field_slots, a.num_fields, isd_ws, stream)) return rc;
+    p.neus_isd = isd_ws;
+  }
+  p.rgbd = a.rgbd; p.color_var = a.color_var; p.depth_var = a.depth_var; p.term_prob = a.term_prob;
+  p.freespace = a.freespace; p.freespace_mask = a.freespace_mask; p.tsdf = a.tsdf; p.tsdf_mask = a.tsdf_mask;
+  p.tiles_per_field = (a.rays_per_field + p.rpt - 1) / p.rpt;
+  p.total_tiles = p.tiles_per_field * a.num_fields;
+  const int sms = num_sms();
+  const int grid = (int)(p.total_tiles < sms ? p.total_tiles : sms);
+  return launch_tc<0>(p, a.field.nerf_num_octaves, tc_smem_bytes(p.im), grid, stream);
 }
 
 }  // namespace ngm

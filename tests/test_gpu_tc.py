@@ -1,0 +1,170 @@
+"""GPU tests of the fp16-operand tensor-core (tcgen05) path.
+
+Tolerances (fp16 operands, fp32 accumulation; north_star: "PSNR within 0.1 dB"):
+  per-pixel colour L1 (mean) <= 2e-3, depth L1 (mean) <= 5e-3 m against the fp32 reference
+  golden vectors; the raw MLP output within 2% of its scale (max) / 0.3% (mean).
+"""
+import ctypes as C
+
+import pytest
+import torch
+
+import golden_util as G
+from oracle import restatement as R
+from tests_support import make_state, product_field_kwargs, run_vmap_case
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
+DEV = "cuda:0"
+
+
+def _gemm(n, k, rows, seed):
+    from neural_graph_mapping_b200 import _lib
+
+    g = torch.Generator().manual_seed(seed)
+    a = (torch.randn(rows, k, generator=g) * 0.5).half()
+    w = torch.randn(n, k, generator=g) * 0.3
+    b = torch.randn(n, generator=g)
+    ad, wd, bd = a.to(DEV), w.to(DEV), b.to(DEV)
+    out = torch.full((rows, n), float("nan"), device=DEV)
+    ws = torch.zeros(256 * 1024, dtype=torch.uint8, device=DEV)
+    rc = _lib.lib.ngm_debug_tc_gemm(wd.data_ptr(), bd.data_ptr(), n, k, ad.data_ptr(), rows, out.data_ptr(),
+                                    ws.data_ptr(), ws.numel(), _lib.stream_ptr(torch.device(DEV)))
+    _lib.check(rc)
+    torch.cuda.synchronize()
+    ref = a.float() @ w.half().float().T + b
+    return out.cpu(), ref
+
+
+@pytest.mark.parametrize("n,k,rows", [(128, 128, 128), (16, 128, 300), (128, 48, 257), (64, 64, 1000), (4, 32, 77),
+                                      (128, 16, 128), (100, 112, 129)])
+def test_tc_gemm_plumbing(n, k, rows):
+    """Weight packing + SWIZZLE_128B smem descriptors + A operand in TMEM + tcgen05.mma + TMEM epilogue."""
+    out, ref = _gemm(n, k, rows, seed=n * 1000 + k)
+    err = (out - ref).abs()
+    assert torch.isfinite(out).all(), "non-finite output (uninitialised rows?)"
+    assert err.max().item() < 5e-3, f"n={n} k={k}: max err {err.max().item():.3e}; " \
+        f"first bad {torch.nonzero(err > 5e-3)[:5].tolist()}"
+
+
+def test_tc_gemm_one_hot_layout():
+    """One-hot operands pin the exact (row, k) -> TMEM and (n, k) -> smem mappings."""
+    from neural_graph_mapping_b200 import _lib
+
+    n, k, rows = 128, 128, 128
+    a = torch.zeros(rows, k, dtype=torch.half)
+    a[torch.arange(rows), torch.arange(rows) % k] = 1.0  # row r selects k = r
+    b = torch.zeros(n)
+    for which, w in (("n", torch.arange(n)[:, None].expand(n, k).float()),
+                     ("k", torch.arange(k)[None, :].expand(n, k).float())):  # exact in fp16
+        ad, wd, bd = a.to(DEV), w.contiguous().to(DEV), b.to(DEV)
+        out = torch.empty(rows, n, device=DEV)
+        ws = torch.zeros(256 * 1024, dtype=torch.uint8, device=DEV)
+        _lib.check(_lib.lib.ngm_debug_tc_gemm(wd.data_ptr(), bd.data_ptr(), n, k, ad.data_ptr(), rows, out.data_ptr(),
+                                              ws.data_ptr(), ws.numel(), _lib.stream_ptr(torch.device(DEV))))
+        ref = w.T[torch.arange(rows) % k]  # out[r, n] = W[n, r]
+        assert torch.equal(out.cpu(), ref), \
+            f"W[n,k]={which}: layout mismatch, out[1,:6]={out[1, :6].tolist()} out[5,:6]={out[5, :6].tolist()}"
+
+
+def _field(fk, precision):
+    import neural_graph_mapping_b200 as ngm
+
+    return ngm.NeuralField(**product_field_kwargs(fk), precision=precision).to(DEV)
+
+
+def test_field_fwd_fp16_vs_fp32_and_reference():
+    meta, a = G.load("fields_forward")
+    name = "nerf8_w128_l4"
+    fk = meta["variants"][name]["field_kwargs"]
+    sd = {k: v.to(DEV) for k, v in G.params(a, prefix=f"{name}:param:").items()}
+    x = a[f"{name}:x"].to(DEV)
+    f16, f32 = _field(fk, "fp16"), _field(fk, "fp32")
+    f16.load_state_dict(sd, strict=False)
+    f32.load_state_dict(sd, strict=False)
+    with torch.no_grad():
+        y16, y32 = f16(x), f32(x)
+    ref = a[f"{name}:y"]
+    scale = ref.abs().max().item()
+    e = (y16.cpu() - ref).abs()
+    assert e.max().item() < 2e-2 * scale and e.mean().item() < 3e-3 * scale, (e.max().item(), e.mean().item(), scale)
+    assert (y32.cpu() - ref).abs().max().item() < 1e-4 * max(scale, 1.0)
+
+
+@pytest.mark.parametrize("W,L,O,n", [(32, 2, 4, 1000), (64, 1, 8, 129), (128, 4, 8, 4096), (16, 0, 4, 300), (48, 3, 4, 511)])
+def test_fieldset_fp16_shapes_vs_oracle(W, L, O, n):
+    """Tile tails, several fields (weight image switches), small/large widths."""
+    import neural_graph_mapping_b200 as ngm
+
+    g = torch.Generator().manual_seed(W * 7 + L)
+    F = 5
+    spec = R.FieldSpec("nerf", {"dim_in": 3, "num_octaves": O}, L, 4, W, "no")
+    params = R.stack_params([R.init_field_params(spec, g) for _ in range(F)])
+    pos = torch.randn(F, 3, generator=g)
+    q = torch.randn(F, 4, generator=g)
+    ori = q / q.norm(dim=-1, keepdim=True)
+    pts = pos[:, None] + torch.rand(F, n, 3, generator=g) * 1.6 - 0.8
+    rs = R.RenderSpec(field_radius=1.0, scale_mode="unit_cube")
+    ref = R.fieldset_forward_vmap(pts, pos, ori, spec, params, rs)
+    model = ngm.NeuralFieldSet(3, "neural_graph_mapping_b200.models.NeuralField",
+                               {"encoding_type": "neural_graph_mapping_b200.positional_encodings.PositionalEncodingNeRF",
+                                "encoding_kwargs": {"dim_in": 3, "num_octaves": O}, "num_layers": L, "dim_out": 4,
+                                "dim_mlp_out": W}, 2, 10.0, 1.0, field_radius=1.0, scale_mode="unit_cube",
+                               precision="fp16").to(DEV)
+    model.all_fields_params = {k: v.to(DEV) for k, v in params.items()}
+    model.set_vmap_fields(None)
+    with torch.no_grad():
+        y = model(pts.to(DEV), pos.to(DEV), ori.to(DEV), None, True)
+    scale = ref.abs().max().item()
+    e = (y.cpu() - ref).abs()
+    assert e.max().item() < 2e-2 * scale and e.mean().item() < 3e-3 * scale, (e.max().item(), e.mean().item(), scale)
+
+
+@pytest.mark.parametrize("name", G.VMAP_CASES)
+def test_render_fused_fp16_golden(name):
+    """The fused tcgen05 render kernel against the fp32 reference's golden outputs."""
+    meta, a = G.load(name)
+    p = run_vmap_case(meta, a, DEV, precision="fp16")
+    col = (p.rgbds[..., :3].cpu() - a["out_rgbds"][..., :3]).abs()
+    dep = (p.rgbds[..., 3].cpu() - a["out_rgbds"][..., 3]).abs()
+    assert col.mean().item() < 2e-3, f"colour L1 {col.mean().item():.2e} (max {col.max().item():.2e})"
+    assert dep.mean().item() < 5e-3, f"depth L1 {dep.mean().item():.2e} (max {dep.max().item():.2e})"
+    assert (p.term_probs.cpu() - a["out_term_probs"]).abs().mean().item() < 3e-3
+    assert (p.color_vars.cpu() - a["out_color_vars"]).abs().mean().item() < 3e-3
+    assert (p.depth_vars.cpu() - a["out_depth_vars"]).abs().mean().item() < 5e-3
+    if "out_freespace" in a:
+        assert p.freespace_geometry.shape == a["out_freespace"].shape
+        assert (p.freespace_geometry.cpu() - a["out_freespace"]).abs().mean().item() < 2e-3
+        assert (p.tsdf_residuals.cpu() - a["out_tsdf"]).abs().mean().item() < 2e-3
+
+
+@pytest.mark.parametrize("S,Sg", [(128, 0), (100, 0), (5, 0), (16, 16), (70, 30), (200, 0)])
+def test_render_fp16_vs_fp32_sizes(S, Sg):
+    """Ray strides 8..128 (1, 2 and 4 warps per ray), padded strides, the >128-sample staged path."""
+    import neural_graph_mapping_b200 as ngm
+
+    meta, a = G.load("vmap_guided_nrgbd")
+    meta = dict(meta, num_samples=S, num_samples_depth_guided=Sg)
+    g = torch.Generator().manual_seed(S + Sg)
+    F, Rr = 3, 70
+    ijs = torch.stack([torch.randint(0, 480, (F, Rr), generator=g), torch.randint(0, 640, (F, Rr), generator=g)], -1)
+    near = torch.rand(F, Rr, generator=g) * 0.5 + 0.3
+    far = near + 1.5
+    gt = near + (far - near) * torch.rand(F, Rr, generator=g)
+    jit = torch.rand(F, Rr, S, generator=g)
+    jg = torch.rand(F, Rr, max(Sg, 1), generator=g)[..., :Sg]
+    cam = ngm.Camera(**meta["camera"])
+    outs = {}
+    for prec in ("fp32", "fp16"):
+        st = make_state(meta, a, DEV, prec)
+        with torch.no_grad():
+            outs[prec] = st._render_ijs(ijs.to(DEV), a["c2ws"][:F, :1].expand(F, Rr, 4, 4).to(DEV), cam,
+                                        torch.tensor([0, 3, 1], device=DEV), True, near.to(DEV), far.to(DEV),
+                                        gt.to(DEV) if Sg else None, jitter=jit.to(DEV),
+                                        jitter_guided=jg.to(DEV) if Sg else None)
+    p32, p16 = outs["fp32"], outs["fp16"]
+    assert (p16.rgbds[..., :3] - p32.rgbds[..., :3]).abs().mean().item() < 2e-3
+    assert (p16.rgbds[..., 3] - p32.rgbds[..., 3]).abs().mean().item() < 5e-3
+    assert (p16.term_probs - p32.term_probs).abs().mean().item() < 3e-3
+    if Sg:
+        assert p16.freespace_geometry.shape == p32.freespace_geometry.shape
+        assert p16.tsdf_residuals.shape == p32.tsdf_residuals.shape
