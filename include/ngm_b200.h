@@ -216,11 +216,33 @@ typedef struct NgmRenderArgs {
   size_t workspace_bytes;
 } NgmRenderArgs;
 
+/* ---- field set, kNN blend ----------------------------------------------------------------
+ * Replaces NeuralFieldSet.forward with use_vmap=False (ngm/models.py:347-405): K nearest field
+ * centres per point (pytorch3d knn_points), radius mask on the nearest (:369), per-neighbour
+ * local coordinates (:377-381), softmax(-distance_factor*d) blend (:384,399), outside fill (:401).
+ * dim_out must be 4 (the reference hard-codes 4 at :388). */
+typedef struct NgmKnnFwdArgs {
+  NgmFieldDesc field;
+  int64_t num_points;
+  const float* points;        /* (num_points, 3) world coordinates */
+  const float* positions;     /* (num_fields, 3) */
+  const float* orientations;  /* (num_fields, 4) */
+  const int64_t* field_slots; /* (num_fields) parameter-table row of field i (= field_ids), NULL = identity */
+  float* out;                 /* (num_points, 4) */
+  void* workspace;
+  size_t workspace_bytes;
+  float field_radius;   /* radius of the inside test (the `field_radius` argument of forward) */
+  float scale_radius;   /* the class radius used by _scale_local_points (models.py:381) */
+  float distance_factor, outside_value;
+  int32_t num_fields, num_knn, scale_mode, precision;
+} NgmKnnFwdArgs;
+
 /* ---- entry points ---------------------------------------------------------------------- */
 int ngm_abi_version(void);
 const char* ngm_last_error(void);
 /* sizeof() of the structs above as compiled, so a binding can verify its mirror:
- * which = 0 NgmCamera, 1 NgmFieldDesc, 2 NgmSampleArgs, 3 NgmFieldFwdArgs, 4 NgmCompositeArgs, 5 NgmRenderArgs */
+ * which = 0 NgmCamera, 1 NgmFieldDesc, 2 NgmSampleArgs, 3 NgmFieldFwdArgs, 4 NgmCompositeArgs, 5 NgmRenderArgs,
+ * 6 NgmKnnFwdArgs */
 size_t ngm_struct_size(int which);
 /* number of CUDA kernels this library has launched in this process (bench.py's gpu_launches) */
 uint64_t ngm_launch_count(void);
@@ -229,6 +251,8 @@ int ngm_sample_rays(const NgmSampleArgs* args, void* stream);   /* camera.py:215
 int ngm_field_fwd(const NgmFieldFwdArgs* args, void* stream);   /* models.py:143-182, 329-345 */
 int ngm_composite(const NgmCompositeArgs* args, void* stream);  /* run_mapping.py:610-639, 709-799 */
 int ngm_render_rays_fwd(const NgmRenderArgs* args, void* stream); /* run_mapping.py:440-666 (use_vmap=True) */
+int ngm_fieldset_knn_fwd(const NgmKnnFwdArgs* args, void* stream); /* models.py:347-405 (use_vmap=False) */
+int ngm_fieldset_knn_workspace_bytes(const NgmKnnFwdArgs* args, size_t* out);
 
 /* diagnostics: out(rows,n) = A(rows,k; fp16) x weight(n,k; fp32 -> fp16)^T + bias through the production
  * tcgen05 plumbing (weight packing, SWIZZLE_128B descriptors, A operand in TMEM, TMEM epilogue).

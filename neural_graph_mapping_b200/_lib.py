@@ -98,10 +98,20 @@ class NgmRenderArgs(C.Structure):
     ]
 
 
-STRUCTS = [NgmCamera, NgmFieldDesc, NgmSampleArgs, NgmFieldFwdArgs, NgmCompositeArgs, NgmRenderArgs]
+class NgmKnnFwdArgs(C.Structure):
+    _fields_ = [
+        ("field", NgmFieldDesc), ("num_points", C.c_int64), ("points", _fp), ("positions", _fp), ("orientations", _fp),
+        ("field_slots", _fp), ("out", _fp), ("workspace", _fp), ("workspace_bytes", C.c_size_t),
+        ("field_radius", C.c_float), ("scale_radius", C.c_float), ("distance_factor", C.c_float),
+        ("outside_value", C.c_float), ("num_fields", C.c_int32), ("num_knn", C.c_int32), ("scale_mode", C.c_int32),
+        ("precision", C.c_int32),
+    ]
+
+
+STRUCTS = [NgmCamera, NgmFieldDesc, NgmSampleArgs, NgmFieldFwdArgs, NgmCompositeArgs, NgmRenderArgs, NgmKnnFwdArgs]
 EXPORTS = [
     "ngm_abi_version", "ngm_last_error", "ngm_struct_size", "ngm_launch_count", "ngm_sample_rays", "ngm_field_fwd", "ngm_composite",
-    "ngm_render_rays_fwd", "ngm_debug_tc_gemm", "ngm_field_fwd_workspace_bytes", "ngm_render_workspace_bytes",
+    "ngm_render_rays_fwd", "ngm_debug_tc_gemm", "ngm_fieldset_knn_fwd", "ngm_fieldset_knn_workspace_bytes", "ngm_field_fwd_workspace_bytes", "ngm_render_workspace_bytes",
 ]
 
 if not os.path.exists(LIB_PATH):
@@ -117,9 +127,12 @@ lib.ngm_struct_size.restype = C.c_size_t
 lib.ngm_struct_size.argtypes = [C.c_int]
 lib.ngm_launch_count.restype = C.c_uint64
 for _name, _arg in [("ngm_sample_rays", NgmSampleArgs), ("ngm_field_fwd", NgmFieldFwdArgs),
-                    ("ngm_composite", NgmCompositeArgs), ("ngm_render_rays_fwd", NgmRenderArgs)]:
+                    ("ngm_composite", NgmCompositeArgs), ("ngm_render_rays_fwd", NgmRenderArgs),
+                    ("ngm_fieldset_knn_fwd", NgmKnnFwdArgs)]:
     getattr(lib, _name).restype = C.c_int
     getattr(lib, _name).argtypes = [C.POINTER(_arg), C.c_void_p]
+lib.ngm_fieldset_knn_workspace_bytes.restype = C.c_int
+lib.ngm_fieldset_knn_workspace_bytes.argtypes = [C.POINTER(NgmKnnFwdArgs), C.POINTER(C.c_size_t)]
 lib.ngm_debug_tc_gemm.restype = C.c_int
 lib.ngm_debug_tc_gemm.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p,
                                   C.c_void_p, C.c_size_t, C.c_void_p]

@@ -45,6 +45,9 @@ int launch_render_fused_tc(const NgmRenderArgs& a, void* tc_ws, float* isd_ws, c
 int launch_tc_gemm_debug(const NgmFieldDesc& fd, const void* a_half, long long rows, float* out, void* workspace,
                          cudaStream_t stream);
 
+size_t knn_workspace_bytes(long long num_points, int num_knn, int num_fields);
+int launch_fieldset_knn(const NgmKnnFwdArgs& a, cudaStream_t stream);
+
 static int validate_field(const NgmFieldDesc& fd) {
   NGM_CHECK_ARG(fd.num_layers >= 0 && fd.num_layers + 1 <= NGM_MAX_LINEARS, "num_layers=%d out of range [0,%d]",
                 fd.num_layers, NGM_MAX_LINEARS - 1);
@@ -125,6 +128,7 @@ size_t ngm_struct_size(int which) {
     case 3: return sizeof(NgmFieldFwdArgs);
     case 4: return sizeof(NgmCompositeArgs);
     case 5: return sizeof(NgmRenderArgs);
+    case 6: return sizeof(NgmKnnFwdArgs);
     default: return 0;
   }
 }
@@ -182,6 +186,35 @@ int ngm_composite(const NgmCompositeArgs* a, void* stream) {
   NGM_CHECK_ARG((a->tsdf == nullptr) == (a->tsdf_mask == nullptr), "tsdf and its mask go together");
   NGM_CHECK_ARG(((uintptr_t)a->rgbd & 15) == 0, "rgbd must be 16-byte aligned");
   return launch_composite(*a, (cudaStream_t)stream);
+}
+
+int ngm_fieldset_knn_workspace_bytes(const NgmKnnFwdArgs* a, size_t* out) {
+  NGM_CHECK_ARG(a && out, "null args");
+  NGM_CHECK_ARG(a->num_points >= 0 && a->num_fields >= 1 && a->num_knn >= 1, "bad sizes");
+  *out = knn_workspace_bytes(a->num_points, a->num_knn, a->num_fields);
+  return NGM_OK;
+}
+
+int ngm_fieldset_knn_fwd(const NgmKnnFwdArgs* a, void* stream) {
+  NGM_CHECK_ARG(a != nullptr, "null args");
+  if (int rc = validate_field(a->field)) return rc;
+  NGM_CHECK_ARG(a->field.dim_out == 4, "the kNN blend path needs dim_out == 4 (models.py:388), got %d", a->field.dim_out);
+  NGM_CHECK_ARG(a->num_points >= 0 && a->num_fields >= 1, "bad sizes");
+  NGM_CHECK_ARG(a->num_knn >= 1 && a->num_knn <= 8, "num_knn must be in [1, 8], got %d", a->num_knn);
+  const int K = a->num_knn < a->num_fields ? a->num_knn : a->num_fields;
+  NGM_CHECK_ARG(a->num_points * (long long)K < (1ll << 31), "num_points * K must fit in int32; evaluate in blocks");
+  if (a->num_points == 0) return NGM_OK;
+  NGM_CHECK_ARG(a->points && a->positions && a->orientations && a->out, "missing input/output");
+  NGM_CHECK_ARG(a->scale_mode >= NGM_SCALE_NO && a->scale_mode <= NGM_SCALE_UNIT_CUBE, "scale_mode=%d is not available.",
+                a->scale_mode);
+  NGM_CHECK_ARG(((uintptr_t)a->out & 15) == 0, "out must be 16-byte aligned");
+  NGM_UNSUPPORTED(a->precision != NGM_PREC_FP32, "the kNN path evaluates the fields in fp32 in this revision");
+  const size_t need = knn_workspace_bytes(a->num_points, a->num_knn, a->num_fields);
+  if (need > a->workspace_bytes || !a->workspace) {
+    set_error("workspace too small: need %zu B, have %zu B", need, a->workspace_bytes);
+    return NGM_ERR_WORKSPACE;
+  }
+  return launch_fieldset_knn(*a, (cudaStream_t)stream);
 }
 
 int ngm_debug_tc_gemm(const float* weight, const float* bias, int n, int k, const void* a_half, int64_t rows, float* out,

@@ -42,6 +42,12 @@ struct SimtParams {
   float field_radius;
   int scale_mode;
   int act_stride, enc_stride;
+  // gather mode (kNN path, models.py:386-396): rows are (point, neighbour) entries bucketed by field
+  const int* entries;        // [sum counts]  entry = point * K + k
+  const int* entry_offsets;  // [F + 1]
+  const int* tile_offsets;   // [F + 1]  tiles of 128 entries per field
+  int knn_k;
+  int num_fields;
 };
 
 __device__ __forceinline__ void encode_tile(const SimtParams& p, long long slot, const float (*xs)[4],
@@ -99,21 +105,40 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_fwd_simt_kernel(SimtParams 
   for (int idx = tid; idx < 2 * TP * AS; idx += NTHREADS) act0[idx] = 0.0f;
   __syncthreads();
 
-  for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-    const long long f = tile / p.tiles_per_field;
-    const long long p0 = (tile - f * p.tiles_per_field) * TP;
-    const long long slot = p.field_slots ? p.field_slots[f] : f;
+  const bool gather = p.entries != nullptr;
+  const long long total_tiles = gather ? (long long)p.tile_offsets[p.num_fields] : p.total_tiles;
+  for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    long long f, p0;
+    int ent_base = 0, ent_cnt = 0;
+    if (gather) {
+      int lo = 0, hi = p.num_fields;  // largest f with tile_offsets[f] <= tile
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (p.tile_offsets[mid] <= tile) lo = mid; else hi = mid;
+      }
+      f = lo;
+      ent_base = p.entry_offsets[f] + (int)(tile - p.tile_offsets[f]) * TP;
+      ent_cnt = min(TP, p.entry_offsets[f + 1] - ent_base);
+      p0 = 0;
+    } else {
+      f = tile / p.tiles_per_field;
+      p0 = (tile - f * p.tiles_per_field) * TP;
+    }
+    const long long slot = p.field_slots ? p.field_slots[f] : f;   // row in the parameter tables
+    const long long pose_slot = gather ? f : slot;                 // row in positions / orientations
 
     // ---- local coordinates (models.py:331-339) ----
     if (tid < TP) {
       float3 x = make_float3(0.f, 0.f, 0.f);
       const long long gp = p0 + tid;
-      if (gp < p.points_per_field) {
-        const float* src = p.points + (f * p.points_per_field + gp) * 3;
+      const bool row_ok = gather ? tid < ent_cnt : gp < p.points_per_field;
+      if (row_ok) {
+        const float* src = gather ? p.points + (long long)(__ldg(p.entries + ent_base + tid) / p.knn_k) * 3
+                                  : p.points + (f * p.points_per_field + gp) * 3;
         x = make_float3(__ldg(src), __ldg(src + 1), __ldg(src + 2));
         if (p.positions) {
-          const float* c = p.positions + slot * 3;
-          const float* q = p.orientations + slot * 4;
+          const float* c = p.positions + pose_slot * 3;
+          const float* q = p.orientations + pose_slot * 4;
           x = make_float3(x.x - __ldg(c), x.y - __ldg(c + 1), x.z - __ldg(c + 2));
           x = quat_inv_rotate(__ldg(q), __ldg(q + 1), __ldg(q + 2), __ldg(q + 3), x);
         }
@@ -198,8 +223,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_fwd_simt_kernel(SimtParams 
               const int n = nb + half * NT + j;
               float v = acc[j] + __ldg(Bg + n);
               if (last) {
-                const long long gp = p0 + pt;
-                if (gp < p.points_per_field) p.out[(f * p.points_per_field + gp) * fd.dim_out + n] = v;
+                if (gather) {
+                  if (pt < ent_cnt) p.out[(long long)__ldg(p.entries + ent_base + pt) * fd.dim_out + n] = v;
+                } else {
+                  const long long gp = p0 + pt;
+                  if (gp < p.points_per_field) p.out[(f * p.points_per_field + gp) * fd.dim_out + n] = v;
+                }
               } else {
                 v = fmaxf(v, 0.0f);
                 if (fd.skip_mode == NGM_SKIP_ADD) {
@@ -240,9 +269,24 @@ size_t field_simt_smem_bytes(const NgmFieldDesc& fd, int* act_stride, int* enc_s
   return sizeof(float) * ((size_t)TP * 4 + NPASS * KC + 2 * (size_t)TP * AS + (size_t)TP * ES);
 }
 
+int launch_field_fwd_simt_gather(const NgmFieldFwdArgs& a, const int* entries, const int* entry_offsets,
+                                 const int* tile_offsets, int knn_k, long long max_tiles, cudaStream_t stream);
+
 int launch_field_fwd_simt(const NgmFieldFwdArgs& a, cudaStream_t stream) {
-  if (a.num_fields == 0 || a.points_per_field == 0) return NGM_OK;
+  return launch_field_fwd_simt_gather(a, nullptr, nullptr, nullptr, 1, 0, stream);
+}
+
+// `entries` != nullptr: gather mode.  a.points = (num_points,3) world points, a.positions/orientations = pose of
+// field f at row f, a.field_slots = parameter row of field f, a.out = (num_points*K, dim_out) per-entry outputs.
+int launch_field_fwd_simt_gather(const NgmFieldFwdArgs& a, const int* entries, const int* entry_offsets,
+                                 const int* tile_offsets, int knn_k, long long max_tiles, cudaStream_t stream) {
+  if (a.num_fields == 0 || (!entries && a.points_per_field == 0)) return NGM_OK;
   SimtParams p;
+  p.entries = entries;
+  p.entry_offsets = entry_offsets;
+  p.tile_offsets = tile_offsets;
+  p.knn_k = knn_k;
+  p.num_fields = a.num_fields;
   p.fd = a.field;
   p.points = a.points;
   p.positions = a.positions;
@@ -262,7 +306,8 @@ int launch_field_fwd_simt(const NgmFieldFwdArgs& a, cudaStream_t stream) {
     NGM_CUDA(cudaFuncSetAttribute(field_fwd_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  p.total_tiles = p.tiles_per_field * a.num_fields;
+  p.total_tiles = entries ? max_tiles : p.tiles_per_field * a.num_fields;
+  if (p.total_tiles <= 0) return NGM_OK;
   const long long cap = (long long)num_sms() * 64;
   const unsigned grid = (unsigned)(p.total_tiles < cap ? p.total_tiles : cap);
   field_fwd_simt_kernel<<<grid, NTHREADS, smem, stream>>>(p);

@@ -211,3 +211,87 @@ def test_render_errors_match_reference():
         st._render_ijs(a["ijs"].to(DEV), a["c2ws"].to(DEV), cam, None, True)
     with pytest.raises(RuntimeError, match="no CPU"):
         st._render_ijs(a["ijs"], a["c2ws"], cam, a["field_ids"], True)
+
+
+# ---------------------------------------------------------------- kNN path (a7, a15)
+@pytest.mark.parametrize("name", G.KNN_CASES)
+def test_render_knn_golden(name):
+    """_render_ijs(use_vmap=False): all fields, K=2 softmax blend, outside fill (models.py:347-405)."""
+    import neural_graph_mapping_b200 as ngm
+
+    meta, a = G.load(name)
+    st = make_state(meta, a, DEV)
+    st.eval()
+    cam = ngm.Camera(**meta["camera"])
+    with torch.no_grad():
+        p = st._render_ijs(a["ijs"].to(DEV), a["c2ws"].to(DEV), cam, jitter=a["jitter"].to(DEV))
+        out = st._model(a["knn_query"].to(DEV), a["positions"].to(DEV), a["orientations"].to(DEV), None, False)
+    _close(out, a["knn_out"], 3e-5, 3e-5, "fieldset kNN")
+    _close(p.rgbds[..., :3], a["out_rgbds"][..., :3], 3e-5, 3e-5, "colour")
+    _close(p.rgbds[..., 3], a["out_rgbds"][..., 3], 1e-4, 3e-5, "depth")
+    _close(p.color_vars, a["out_color_vars"], 3e-5, 3e-5, "colour var")
+    _close(p.depth_vars, a["out_depth_vars"], 1e-4, 3e-5, "depth var")
+    _close(p.term_probs, a["out_term_probs"], 3e-5, 3e-5, "term")
+
+
+@pytest.mark.parametrize("F,K,n", [(1, 2, 300), (3, 1, 1000), (40, 2, 5000), (1500, 3, 4000)])
+def test_fieldset_knn_vs_oracle(F, K, n):
+    """Field counts below K, K=1/3, more centres than one shared-memory chunk, field_ids remap."""
+    import neural_graph_mapping_b200 as ngm
+
+    g = torch.Generator().manual_seed(F * 10 + K)
+    spec = R.FieldSpec("nerf", {"dim_in": 3, "num_octaves": 4}, 1, 4, 16, "no")
+    n_tab = min(F, 8)  # a small parameter table; field i uses row field_ids[i]
+    params = R.stack_params([R.init_field_params(spec, g) for _ in range(n_tab)])
+    pos = torch.randn(F, 3, generator=g) * (1.0 if F < 100 else 6.0)
+    q = torch.randn(F, 4, generator=g)
+    ori = q / q.norm(dim=-1, keepdim=True)
+    fid = torch.randint(0, n_tab, (F,), generator=g)
+    pts = torch.randn(n, 3, generator=g) * (1.5 if F < 100 else 6.0)
+    rs = R.RenderSpec(field_radius=1.0, scale_mode="unit_cube", num_knn=K, distance_factor=10.0, outside_value=1.0)
+    ref = R.fieldset_forward_knn(pts, pos, ori, fid, spec, params, rs)
+    model = ngm.NeuralFieldSet(3, "neural_graph_mapping_b200.models.NeuralField",
+                               {"encoding_type": "neural_graph_mapping_b200.positional_encodings.PositionalEncodingNeRF",
+                                "encoding_kwargs": {"dim_in": 3, "num_octaves": 4}, "num_layers": 1, "dim_out": 4,
+                                "dim_mlp_out": 16}, K, 10.0, 1.0, field_radius=1.0, scale_mode="unit_cube").to(DEV)
+    model.all_fields_params = {k: v.to(DEV) for k, v in params.items()}
+    with torch.no_grad():
+        y = model(pts.to(DEV), pos.to(DEV), ori.to(DEV), fid.to(DEV), False)
+    # points whose two nearest centres are (nearly) equidistant may legitimately pick another neighbour order
+    d = torch.cdist(pts, pos)
+    srt = torch.sort(d, dim=-1)[0]
+    margin = torch.ones(n, dtype=torch.bool)
+    for j in range(min(K, F - 1)):
+        margin &= (srt[:, j + 1] - srt[:, j]).abs() > 1e-5
+    margin &= (srt[:, 0] - 1.0).abs() > 1e-5
+    _close(y.cpu()[margin], ref[margin], 3e-5, 3e-5, "kNN fieldset")
+    inside = (ref != 1.0).any(-1).float().mean().item()
+    assert 0.0 < inside <= 1.0
+
+
+def test_render_image_knn():
+    """render_image = pixel grid in pixel_block_size chunks through _render_ijs (run_mapping.py:402-437)."""
+    import neural_graph_mapping_b200 as ngm
+
+    meta, a = G.load("knn_render")
+    meta = dict(meta)
+    meta["config"] = dict(meta["config"], pixel_block_size=1000)
+    st = make_state(meta, a, DEV)
+    st.eval()
+    cam = ngm.Camera(64, 48, 55.4, 55.4, 31.5, 23.5)
+    torch.manual_seed(0)
+    rgbds, dvars = st.render_image(a["c2ws"].to(DEV), cam)
+    assert rgbds.shape == (48, 64, 4) and dvars.shape == (48, 64)
+    assert torch.isfinite(rgbds).all() and torch.isfinite(dvars).all()
+    # same render with the noise injected: oracle parity on the full image
+    g = torch.Generator().manual_seed(9)
+    jit = torch.rand(48 * 64, meta["num_samples"], generator=g)
+    ijs = torch.cartesian_prod(torch.arange(48), torch.arange(64))
+    with torch.no_grad():
+        p = st._render_ijs(ijs.to(DEV), a["c2ws"].to(DEV), cam, jitter=jit.to(DEV))
+    fs, rs = G.field_spec(meta["field_kwargs"]), G.render_spec(meta)
+    cs = R.CameraSpec(64, 48, 55.4, 55.4, 31.5, 23.5)
+    ref = R.render_rays(ijs, a["c2ws"], cs, rs, fs, G.params(a), a["positions"], a["orientations"], jitter=jit)
+    _close(p.rgbds, ref.rgbds, 1e-4, 5e-5, "image rgbd")
+    psnr = R.psnr(p.rgbds[..., :3].cpu().reshape(48, 64, 3), ref.rgbds[..., :3].reshape(48, 64, 3))
+    assert psnr > 80.0, psnr
