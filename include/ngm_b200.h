@@ -113,8 +113,8 @@ typedef struct NgmSampleArgs {
   const float* near;    /* (num_rays) or NULL -> near_scalar */
   const float* far;     /* (num_rays) or NULL -> far_scalar */
   const float* gt;      /* (num_rays) or NULL; 0.0 = unavailable (run_mapping.py:522-526) */
-  const float* jitter;        /* (num_rays, num_samples) U[0,1) or NULL -> Philox(seed, offset) */
-  const float* jitter_guided; /* (num_rays, num_samples_guided) or NULL -> Philox */
+  const float* jitter;        /* (num_rays, num_samples) U[0,1) or NULL -> counter-hash RNG(seed, offset) */
+  const float* jitter_guided; /* (num_rays, num_samples_guided) or NULL -> in-kernel RNG */
   uint64_t seed, offset;
   float near_scalar, far_scalar, range_guided;
   int32_t c2w_per_ray;
@@ -190,7 +190,7 @@ typedef struct NgmRenderArgs {
   const float* near;          /* (num_fields, rays_per_field) or NULL */
   const float* far;
   const float* gt;
-  const float* jitter;        /* (num_fields, rays_per_field, num_samples) or NULL -> Philox */
+  const float* jitter;        /* (num_fields, rays_per_field, num_samples) or NULL -> in-kernel RNG */
   const float* jitter_guided;
   const float* positions;     /* (num_slots, 3)  global field table (_global_map_dict["positions"]) */
   const float* orientations;  /* (num_slots, 4) */

@@ -6,18 +6,19 @@
 //   * field_fwd: the same MLP pipeline with points read from HBM and raw outputs written back
 //     (ngm/models.py:329-345) -- the stage form, also used for St > 128.
 //
-// Design (one persistent CTA per SM, 288 threads):
-//   warp 0          : loads the field's pre-swizzled fp16 weight image into shared memory with
-//                     cp.async.bulk (TMA engine) and issues every tcgen05.mma (one elected lane)
-//   warps 1-4 / 5-8 : two "tile slots".  A slot's 128 threads own the 128 rows (= sample points)
-//                     of one tile: thread <-> TMEM lane.  They generate the sample, encode it,
+// Design (one persistent CTA per SM, 576 threads):
+//   warps 0 / 1     : MMA issuers of tile slot 0 / 1 (one elected lane issues tcgen05.mma after a
+//                     blocking mbarrier wait); warp 0 also loads the field's pre-swizzled fp16 weight
+//                     image into shared memory with cp.async.bulk (TMA engine)
+//   warps 2-9/10-17 : two "tile slots".  A slot's 256 threads own the 128 rows (= sample points)
+//                     of one tile, two threads per row (thread <-> TMEM lane, each thread one half
+//                     of the columns).  They generate the sample, encode it,
 //                     tcgen05.st the fp16 features as the A operand into TMEM, and after every
 //                     layer tcgen05.ld the fp32 accumulator, apply bias+ReLU (packed half2),
 //                     and tcgen05.st the next A operand.  Activations never touch shared memory
 //                     or HBM; shared memory only feeds the B operand (weights), so the MMA reads
 //                     64 B/clk of shared memory instead of 128.
-//   While slot 0 is in an epilogue the tensor pipe runs slot 1's layer and vice versa; the MMA
-//   warp polls both slots' "A ready" mbarriers and issues whichever is ready.
+//   While slot 0 is in an epilogue the tensor pipe runs slot 1's layer and vice versa.
 // TMEM (512 columns): slot s uses columns [256 s, 256 s + 128) for the fp32 accumulator D and
 // [256 s + 128, 256 s + 192) for the fp16 A operand (K <= 128).
 #include <cuda_fp16.h>
@@ -29,7 +30,7 @@ namespace ngm {
 
 namespace {
 
-constexpr int kThreads = 288;
+constexpr int kThreads = 576;
 constexpr int kTmemCols = 512;
 constexpr int kSlotCols = 256;
 constexpr int kACol = 128;
@@ -144,7 +145,7 @@ struct TcParams {
   const float* gt;
   RayJitter jit;
   float near_scalar, far_scalar, range_guided;
-  int c2w_per_ray, S, G, St, Sp, rpt;
+  int c2w_per_ray, S, G, St, Sp, sp_shift, rpt;
   long long rays_per_field;
   int geometry_mode, overwrite;
   float geometry_factor, color_factor, truncation;
@@ -159,26 +160,24 @@ struct TcParams {
   uint8_t* tsdf_mask;
 };
 
+constexpr int kMaxRaysPerTile = 16;  // Sp >= 8
+constexpr int kRayFloats = 12;       // o_local[3], dir_local[3], zscale, near, far, gt, valid, pad
+
 struct Smem {
   uint64_t a_ready[2];
   uint64_t d_ready[2];
   uint64_t w_ready;
   uint32_t tmem_base;
   uint32_t pad_;
-  float sm_d[2][128];     // per slot: sample distance (merge exchange / density deltas)
-  float sm_g[2][128];     // per slot: geometry after the behind-camera overwrite (neus neighbour)
-  float sm_part[2][4][8]; // per slot, per warp: scan tails and partial sums
+  float ray[2][2][kMaxRaysPerTile][kRayFloats];  // [slot][double buffer][ray in tile][param]
+  float sm_d[2][128];      // per slot: sample distance (merge exchange / density deltas)
+  float sm_g[2][128];      // per slot: geometry after the behind-camera overwrite (neus neighbour)
+  float sm_part[2][4][8];  // per slot, per quadrant: scan tails and partial sums
 };
 
-template <int NW>
-__device__ __forceinline__ void tmem_store_words(uint32_t addr, const uint32_t* w) {
-  static_assert(NW % 8 == 0, "word count must be a multiple of 8");
-#pragma unroll
-  for (int i = 0; i + 16 <= NW; i += 16) ptx::tmem_st16(addr + i, w + i);
-  if (NW % 16) ptx::tmem_st8(addr + NW - 8, w + NW - 8);
-}
+__device__ __forceinline__ float fast_sigmoid(float x) { return __frcp_rn(1.0f + __expf(-x)); }
 
-// sin(pi t), cos(pi t) with exact range reduction to [-1, 1]
+// sin(pi t), cos(pi t) with exact range reduction to [-1, 1], MUFU evaluation
 __device__ __forceinline__ void sincospi_fast(float t, float& s, float& c) {
   const float r = fmaf(-2.0f, rintf(0.5f * t), t);
   const float a = 3.14159265358979f * r;
@@ -186,55 +185,78 @@ __device__ __forceinline__ void sincospi_fast(float t, float& s, float& c) {
   c = __cosf(a);
 }
 
+// NeRF features of one row -> fp16 -> TMEM A operand.  Both threads of a row (h = 0, 1) evaluate the
+// sines and cosines (octaves 0 and 4 directly, the rest by the double-angle recurrence: the error at
+// most doubles per octave, 3 steps -> < 1e-5, far below fp16 resolution); thread h = 0 stores the sine
+// half of the feature vector, h = 1 the cosine half plus the zero padding up to EP.
 template <int OCT>
-__device__ __forceinline__ void encode_nerf_to_tmem(uint32_t a_addr, float3 x, int start_octave, bool valid) {
+__device__ __forceinline__ void encode_nerf_to_tmem(uint32_t a_addr, float3 x, int start_octave, int h) {
   constexpr int E = 6 * OCT;
   constexpr int EP = (E + 15) / 16 * 16;
-  float fe[EP];
-#pragma unroll
-  for (int i = 0; i < EP; ++i) fe[i] = 0.0f;
-  const float base = valid ? exp2f((float)start_octave) : 0.0f;
-  const float xs[3] = {valid ? x.x : 0.0f, valid ? x.y : 0.0f, valid ? x.z : 0.0f};
+  constexpr int HW = 3 * OCT;  // features per half
+  static_assert(HW % 2 == 0, "OCT must be even");
+  const float base = exp2f((float)start_octave);
+  const float xs[3] = {x.x, x.y, x.z};
+  float fe[HW];
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
     const float t0 = xs[d] * base;
+    float s = 0.f, c = 1.f;
 #pragma unroll
     for (int o = 0; o < OCT; ++o) {
-      float s, c;
-      sincospi_fast(t0 * (float)(1 << o), s, c);
-      fe[d * OCT + o] = s;
-      fe[3 * OCT + d * OCT + o] = valid ? c : 0.0f;
+      if (o % 4 == 0) {
+        sincospi_fast(t0 * (float)(1 << o), s, c);
+      } else {
+        const float s2 = 2.0f * s * c;
+        c = fmaf(-2.0f * s, s, 1.0f);
+        s = s2;
+      }
+      fe[d * OCT + o] = h ? c : s;
     }
   }
-  uint32_t w[EP / 2];
+  constexpr int NWH = HW / 2;            // words per half
+  constexpr int NPAD = (EP - E) / 2;     // zero words after the cosine half
+  uint32_t w[NWH + NPAD];
 #pragma unroll
-  for (int j = 0; j < EP / 2; ++j) w[j] = ptx::pack_half2(fe[2 * j], fe[2 * j + 1]);
-  tmem_store_words<EP / 2>(a_addr, w);
+  for (int j = 0; j < NWH; ++j) w[j] = ptx::pack_half2(fe[2 * j], fe[2 * j + 1]);
+#pragma unroll
+  for (int j = 0; j < NPAD; ++j) w[NWH + j] = 0u;
+  if (h == 0) {
+    ptx::tmem_store_n<NWH>(a_addr, w);
+  } else {
+    ptx::tmem_store_n<NWH + NPAD>(a_addr + NWH, w);
+  }
 }
 
-// hidden-layer epilogue: D (fp32, W columns) -> relu(D + b) as fp16 -> A
-__device__ __forceinline__ void hidden_epilogue(uint32_t d_addr, uint32_t a_addr, const uint32_t* bias2, int W) {
-  int c = 0;
-  for (; c + 32 <= W; c += 32) {
+// 16 accumulator columns -> relu(x + b) as 8 packed half2 words
+__device__ __forceinline__ void cvt16(const uint32_t* v, const uint32_t* bias2, uint32_t* w) {
+  const uint4 b0 = *reinterpret_cast<const uint4*>(bias2);
+  const uint4 b1 = *reinterpret_cast<const uint4*>(bias2 + 4);
+  const uint32_t b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    w[i] = ptx::bias_relu_half2(ptx::pack_half2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), b[i]);
+}
+
+// hidden-layer epilogue of one thread: accumulator columns [c0, c0 + n) -> A words [c0/2, (c0+n)/2)
+__device__ __forceinline__ void hidden_epilogue(uint32_t d_addr, uint32_t a_addr, const uint32_t* bias2, int c0, int n) {
+  int c = c0;
+  const int end = c0 + n;
+  for (; c + 32 <= end; c += 32) {
     uint32_t v[32];
     ptx::tmem_ld32(d_addr + c, v);
     ptx::tc_wait_ld();
     uint32_t w[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i)
-      w[i] = ptx::bias_relu_half2(ptx::pack_half2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])),
-                                  bias2[c / 2 + i]);
+    cvt16(v, bias2 + c / 2, w);
+    cvt16(v + 16, bias2 + c / 2 + 8, w + 8);
     ptx::tmem_st16(a_addr + c / 2, w);
   }
-  if (c < W) {  // W % 32 == 16
+  if (c < end) {  // 16 columns left
     uint32_t v[16];
     ptx::tmem_ld16(d_addr + c, v);
     ptx::tc_wait_ld();
     uint32_t w[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-      w[i] = ptx::bias_relu_half2(ptx::pack_half2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])),
-                                  bias2[c / 2 + i]);
+    cvt16(v, bias2 + c / 2, w);
     ptx::tmem_st8(a_addr + c / 2, w);
   }
 }
@@ -244,7 +266,45 @@ __device__ __forceinline__ float seg_sum(float v, int width) {
   return v;
 }
 
-// ---- compositor on one tile slot (128 threads, rows with ray stride Sp) --------------------------
+// Per-ray quantities of the fused renderer, computed once per ray (one tile ahead) instead of per
+// sample: the sample point in scaled field-local coordinates is o + d * dir (algebraically the
+// reference's  scale(q^-1 (R (dir d) + t - c)), run_mapping.py:547 + models.py:331-339).
+__device__ __forceinline__ void compute_ray_params(const TcParams& p, long long f, long long slot, long long r, float* out) {
+  const bool ok = r < p.rays_per_field;
+  float o[3] = {0.f, 0.f, 0.f}, dl[3] = {0.f, 0.f, 0.f};
+  float zs = 0.f, nr = 0.f, fr = 0.f, gt = 0.f;
+  if (ok) {
+    const long long ray = f * p.rays_per_field + r;
+    nr = p.near ? __ldg(p.near + ray) : p.near_scalar;
+    fr = p.far ? __ldg(p.far + ray) : p.far_scalar;
+    if (p.gt) gt = __ldg(p.gt + ray);
+    const longlong2 ij = __ldg(reinterpret_cast<const longlong2*>(p.ijs) + ray);
+    const float3 dir = ij_to_direction(ij.x, ij.y, p.cam);
+    zs = -dir.z;
+    const float* m = p.c2ws + (p.c2w_per_ray ? ray * 16 : 0);
+    float mm[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) mm[i] = __ldg(m + i);
+    float3 dw = make_float3(mm[0] * dir.x + mm[1] * dir.y + mm[2] * dir.z, mm[4] * dir.x + mm[5] * dir.y + mm[6] * dir.z,
+                            mm[8] * dir.x + mm[9] * dir.y + mm[10] * dir.z);
+    const float* c = p.positions + slot * 3;
+    const float* q = p.orientations + slot * 4;
+    float3 ow = make_float3(mm[3] - __ldg(c), mm[7] - __ldg(c + 1), mm[11] - __ldg(c + 2));
+    const float qw = __ldg(q), qx = __ldg(q + 1), qy = __ldg(q + 2), qz = __ldg(q + 3);
+    ow = quat_inv_rotate(qw, qx, qy, qz, ow);
+    dw = quat_inv_rotate(qw, qx, qy, qz, dw);
+    float sc = 1.0f, sh = 0.0f;
+    if (p.scale_mode == NGM_SCALE_UNIT_CUBE) { sc = 1.0f / (2.0f * p.field_radius); sh = 0.5f; }
+    else if (p.scale_mode == NGM_SCALE_UNIT_BALL) sc = 1.0f / p.field_radius;
+    o[0] = fmaf(ow.x, sc, sh); o[1] = fmaf(ow.y, sc, sh); o[2] = fmaf(ow.z, sc, sh);
+    dl[0] = dw.x * sc; dl[1] = dw.y * sc; dl[2] = dw.z * sc;
+  }
+  out[0] = o[0]; out[1] = o[1]; out[2] = o[2];
+  out[3] = dl[0]; out[4] = dl[1]; out[5] = dl[2];
+  out[6] = zs; out[7] = nr; out[8] = fr; out[9] = gt; out[10] = ok ? 1.0f : 0.0f; out[11] = 0.f;
+}
+
+// ---- compositor on one tile slot (the 128 h==0 threads, rows with ray stride Sp) -----------------
 // ngm/run_mapping.py:610-639, 709-799.  `valid` = this row is a real sample of a real ray.
 __device__ __forceinline__ void composite_rows(const TcParams& p, Smem& sm, int s, int row, int qwarp, int lane, int barrier_id,
                                                long long ray_global, int k, bool valid, float c0, float c1, float c2, float g,
@@ -275,18 +335,19 @@ __device__ __forceinline__ void composite_rows(const TcParams& p, Smem& sm, int 
     if (valid && k < Se) {
       if (mode == NGM_GEOM_DENSITY) {
         const float delta = sm.sm_d[s][row + 1] - d;
-        occ = 1.0f - expf(-delta * fmaxf(g, 0.0f));
+        occ = 1.0f - __expf(-delta * fmaxf(g, 0.0f));
       } else {
-        const float t0 = sigmoidf(isd_gamma * g), t1 = sigmoidf(isd_gamma * sm.sm_g[s][row + 1]);
-        occ = fmaxf((t0 - t1) / (t0 + 1e-5f), 0.0f);
+        const float t0 = fast_sigmoid(isd_gamma * g), t1 = fast_sigmoid(isd_gamma * sm.sm_g[s][row + 1]);
+        occ = fmaxf(__fdividef(t0 - t1, t0 + 1e-5f), 0.0f);
       }
     }
   } else if (valid) {
-    if (mode == NGM_GEOM_NRGBD) {
-      const float t = p.geometry_factor * g;
-      occ = (4.0f * sigmoidf(t)) * sigmoidf(-t);
+    if (mode == NGM_GEOM_NRGBD) {  // 4 s(t) s(-t) = 4u / (1+u)^2, u = exp(-|t|)
+      const float u = __expf(-fabsf(p.geometry_factor * g));
+      const float r = __frcp_rn(1.0f + u);
+      occ = 4.0f * u * r * r;
     } else {
-      occ = sigmoidf(p.geometry_factor * g);
+      occ = fast_sigmoid(p.geometry_factor * g);
     }
   }
   // exclusive product scan of (1 - occ) along the ray
@@ -355,6 +416,10 @@ __device__ __forceinline__ void composite_rows(const TcParams& p, Smem& sm, int 
   }
 }
 
+// Thread layout (576 threads, one CTA per SM):
+//   warp 0  : MMA issuer of slot 0 (+ weight-image loader)     warp 1 : MMA issuer of slot 1
+//   warps 2-9  : slot 0   (warp w: TMEM quadrant w % 4, column half h = ((w-2) / 4) & 1)
+//   warps 10-17: slot 1
 template <int MODE, int OCT>
 __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -366,9 +431,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const TcParams p) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (warp == 0) ptx::tmem_alloc(&sm.tmem_base, kTmemCols);
-  if (tid == 32) {
-    ptx::mbar_init(&sm.a_ready[0], 128);
-    ptx::mbar_init(&sm.a_ready[1], 128);
+  if (tid == 64) {
+    ptx::mbar_init(&sm.a_ready[0], 256);
+    ptx::mbar_init(&sm.a_ready[1], 256);
     ptx::mbar_init(&sm.d_ready[0], 1);
     ptx::mbar_init(&sm.d_ready[1], 1);
     ptx::mbar_init(&sm.w_ready, 1);
@@ -384,8 +449,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const TcParams p) {
   const long long t_end = p.total_tiles * (blockIdx.x + 1) / gridDim.x;
 
   uint32_t w_phase = 0;
-  uint32_t pa[2] = {0, 0};  // MMA warp: parity of a_ready per slot
-  uint32_t pd = 0;          // epilogue thread: parity of its slot's d_ready
+  uint32_t pa = 0;  // MMA issuer: parity of its slot's a_ready
+  uint32_t pd = 0;  // slot thread: parity of its slot's d_ready
   const int L = p.L, W = p.W;
 
   long long t = t_begin;
@@ -405,57 +470,61 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const TcParams p) {
         ptx::bulk_g2s(wsm + o, src + o, n, &sm.w_ready);
       }
     }
-    ptx::mbar_wait(&sm.w_ready, w_phase);
-    w_phase ^= 1;
 
-    if (warp == 0) {
-      // ===================== MMA issuer =====================
-      int remaining[2] = {(ntiles + 1) / 2, ntiles / 2};
-      int layer[2] = {0, 0};
-      while (remaining[0] > 0 || remaining[1] > 0) {
-#pragma unroll
-        for (int s = 0; s < 2; ++s) {
-          if (remaining[s] > 0 && ptx::mbar_test(&sm.a_ready[s], pa[s])) {
-            pa[s] ^= 1;
-            ptx::tc_fence_after();
-            if (lane == 0) {
-              const TcLayer y = p.im.layer[layer[s]];
-              const uint32_t idesc = ptx::make_idesc_f16(y.n_pad);
-              const uint32_t d_addr = tmem_base + s * kSlotCols;
-              const uint32_t a_addr = d_addr + kACol;
-              const int ksteps = y.k_pad / 16;
-              for (int ks = 0; ks < ksteps; ++ks) {
-                const uint32_t boff = y.off + (uint32_t)(ks >> 2) * (uint32_t)y.n_pad * 128u + (uint32_t)(ks & 3) * 32u;
-                ptx::mma_f16_ts(d_addr, a_addr + ks * 8, ptx::make_smem_desc_sw128(wsm_addr + boff), idesc, ks > 0);
-              }
-              ptx::mma_commit(&sm.d_ready[s]);
+    if (warp < 2) {
+      // ===================== MMA issuer of slot `warp` =====================
+      const int s = warp;
+      ptx::mbar_wait(&sm.w_ready, w_phase);
+      const int my_tiles = s == 0 ? (ntiles + 1) / 2 : ntiles / 2;
+      const uint32_t d_addr = tmem_base + s * kSlotCols;
+      const uint32_t a_addr = d_addr + kACol;
+      for (int it = 0; it < my_tiles; ++it) {
+        for (int l = 0; l <= L; ++l) {
+          ptx::mbar_wait(&sm.a_ready[s], pa);  // blocking (hardware-suspended) wait: no issue slots burnt
+          pa ^= 1;
+          ptx::tc_fence_after();
+          if (lane == 0) {
+            const TcLayer y = p.im.layer[l];
+            const uint32_t idesc = ptx::make_idesc_f16(y.n_pad);
+            const int ksteps = y.k_pad / 16;
+            for (int ks = 0; ks < ksteps; ++ks) {
+              const uint32_t boff = y.off + (uint32_t)(ks >> 2) * (uint32_t)y.n_pad * 128u + (uint32_t)(ks & 3) * 32u;
+              ptx::mma_f16_ts(d_addr, a_addr + ks * 8, ptx::make_smem_desc_sw128(wsm_addr + boff), idesc, ks > 0);
             }
-            __syncwarp();
-            if (++layer[s] > L) {
-              layer[s] = 0;
-              --remaining[s];
-            }
+            ptx::mma_commit(&sm.d_ready[s]);
           }
+          __syncwarp();
         }
       }
     } else {
       // ===================== tile-slot threads =====================
-      const int s = (warp - 1) >> 2;
-      const int qwarp = warp & 3;  // TMEM lane quadrant this warp may access
+      const int s = (warp - 2) >> 3;
+      const int h = ((warp - 2) >> 2) & 1;  // column half of this thread
+      const int qwarp = warp & 3;           // TMEM lane quadrant this warp may access
       const int row = qwarp * 32 + lane;
       const uint32_t d_addr = tmem_base + ((uint32_t)(qwarp * 32) << 16) + s * kSlotCols;
       const uint32_t a_addr = d_addr + kACol;
       const uint32_t* bias2 = reinterpret_cast<const uint32_t*>(wsm + p.im.bias_h2_off);
       const float* bias_last = reinterpret_cast<const float*>(wsm + p.im.bias_last_off);
       const long long slot = p.field_slots ? p.field_slots[f] : f;
-      const int barrier_id = 1 + s;
+      const int bar_slot = 1 + s;  // 256 threads of the slot
+      const int bar_comp = 3 + s;  // the 128 h == 0 threads (compositor)
+      // column split of the hidden epilogues: multiples of 16, h = 0 takes the (larger) first part
+      const int w0 = ((W / 16 + 1) / 2) * 16;
+      const int my_c0 = h ? w0 : 0, my_n = h ? W - w0 : w0;
 
-      for (int ti = s; ti < ntiles; ti += 2) {
+      if (MODE == 0) {  // ray parameters of this slot's first tile (later tiles are prepared one tile ahead)
+        if (h == 1 && row < p.rpt && s < ntiles)
+          compute_ray_params(p, f, slot, (tile0_in_field + s) * p.rpt + row, sm.ray[s][0][row]);
+      }
+      ptx::mbar_wait(&sm.w_ready, w_phase);  // biases live in the image
+
+      int buf = 0;
+      for (int ti = s; ti < ntiles; ti += 2, buf ^= 1) {
         const long long tile_in_field = tile0_in_field + ti;
         // ---------- front end: make the A operand of layer 0 ----------
         float3 x = make_float3(0.f, 0.f, 0.f);
         bool valid = false;
-        // fused-render per-row state kept for the compositor
         long long ray_global = -1;
         int k = 0;
         float d = 0.f, z = 0.f, gt = 0.f;
@@ -463,77 +532,72 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const TcParams p) {
           const long long gp = tile_in_field * 128 + row;
           valid = gp < p.points_per_field;
           if (p.raw_a) {
-            const long long rr = valid ? f * p.points_per_field + gp : 0;
-            const uint32_t* src = reinterpret_cast<const uint32_t*>(p.raw_a + rr * p.EP);
-            for (int c = 0; c < p.EP / 2; c += 8) {
-              uint32_t w[8];
+            if (h == 0) {
+              const long long rr = valid ? f * p.points_per_field + gp : 0;
+              const uint32_t* src = reinterpret_cast<const uint32_t*>(p.raw_a + rr * p.EP);
+              for (int c = 0; c < p.EP / 2; c += 8) {
+                uint32_t w[8];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) w[i] = valid ? __ldg(src + c + i) : 0u;
-              ptx::tmem_st8(a_addr + c, w);
+                for (int i = 0; i < 8; ++i) w[i] = valid ? __ldg(src + c + i) : 0u;
+                ptx::tmem_st8(a_addr + c, w);
+              }
             }
           } else if (valid) {
             const float* src = p.points + (f * p.points_per_field + gp) * 3;
             x = make_float3(__ldg(src), __ldg(src + 1), __ldg(src + 2));
+            if (p.positions) {
+              const float* c = p.positions + slot * 3;
+              const float* q = p.orientations + slot * 4;
+              x = make_float3(x.x - __ldg(c), x.y - __ldg(c + 1), x.z - __ldg(c + 2));
+              x = quat_inv_rotate(__ldg(q), __ldg(q + 1), __ldg(q + 2), __ldg(q + 3), x);
+            }
+            x = scale_local(x, p.scale_mode, p.field_radius);
           }
         } else {
-          const int rit = row / p.Sp;
-          k = row - rit * p.Sp;
+          ptx::named_bar_sync(bar_slot, 256);  // ray parameters written one tile ago are visible
+          // prepare the next tile of this slot while this one runs
+          if (h == 1 && row < p.rpt && ti + 2 < ntiles)
+            compute_ray_params(p, f, slot, (tile_in_field + 2) * p.rpt + row, sm.ray[s][buf ^ 1][row]);
+          const int rit = row >> p.sp_shift;
+          k = row & (p.Sp - 1);
+          const float* rp = sm.ray[s][buf][rit];
+          const bool ray_ok = rp[10] != 0.0f;
           const long long r = tile_in_field * p.rpt + rit;
-          const bool ray_ok = r < p.rays_per_field;
           if (ray_ok) ray_global = f * p.rays_per_field + r;
           valid = ray_ok && k < p.St;
-          if (ray_ok) {
-            const long long ray = ray_global;
-            const float nr = p.near ? __ldg(p.near + ray) : p.near_scalar;
-            const float fr = p.far ? __ldg(p.far + ray) : p.far_scalar;
-            if (p.gt) gt = __ldg(p.gt + ray);
-            const int S = p.S, G = p.G, St = p.St;
-            if (G > 0) {
-              // depth-guided merge (run_mapping.py:521-545): own distance + rank, then exchange by rank
+          const float nr = rp[7], fr = rp[8];
+          gt = rp[9];
+          const int S = p.S, G = p.G, St = p.St;
+          if (G > 0) {
+            // depth-guided merge (run_mapping.py:521-545): own distance + rank, then exchange by rank
+            if (h == 0 && ray_ok && k < St) {
+              const long long ray = ray_global;
               float glo, ghi;
               guided_window(nr, fr, gt, p.range_guided, glo, ghi);
-              float dk = 0.f;
-              int pos = k;
+              float dk;
+              int pos;
               if (k < S) {
                 dk = stratified_distance(nr, fr, k, S, p.jit.coarse(ray, k, S, St));
                 pos = k + count_before(dk, glo, ghi, G, true, [&](int j) { return p.jit.guided(ray, j, S, G, St); });
-              } else if (k < St) {
+              } else {
                 const int kg = k - S;
                 dk = stratified_distance(glo, ghi, kg, G, p.jit.guided(ray, kg, S, G, St));
                 pos = kg + count_before(dk, nr, fr, S, false, [&](int j) { return p.jit.coarse(ray, j, S, St); });
               }
-              if (k < St) sm.sm_d[s][rit * p.Sp + pos] = dk;
-            } else if (k < St) {
-              d = stratified_distance(nr, fr, k, S, p.jit.coarse(ray, k, S, St));
+              sm.sm_d[s][rit * p.Sp + pos] = dk;
             }
-          }
-          if (p.G > 0) {
-            ptx::named_bar_sync(barrier_id, 128);
+            ptx::named_bar_sync(bar_slot, 256);
             d = sm.sm_d[s][row];
-            ptx::named_bar_sync(barrier_id, 128);
+            ptx::named_bar_sync(bar_slot, 256);
+          } else if (valid) {
+            d = stratified_distance(nr, fr, k, S, p.jit.coarse(ray_global, k, S, St));
           }
           if (valid) {
-            const longlong2 ij = __ldg(reinterpret_cast<const longlong2*>(p.ijs) + ray_global);
-            const float3 dir = ij_to_direction(ij.x, ij.y, p.cam);
-            const float3 pc = make_float3(dir.x * d, dir.y * d, dir.z * d);
-            z = -pc.z;
-            const float* m = p.c2ws + (p.c2w_per_ray ? ray_global * 16 : 0);
-            float mm[12];
-#pragma unroll
-            for (int i = 0; i < 12; ++i) mm[i] = __ldg(m + i);
-            x = transform_point(mm, pc);
+            x = make_float3(fmaf(d, rp[3], rp[0]), fmaf(d, rp[4], rp[1]), fmaf(d, rp[5], rp[2]));
+            z = d * rp[6];
           }
         }
-        if (!(MODE == 1 && p.raw_a)) {
-          if (valid && p.positions) {
-            const float* c = p.positions + slot * 3;
-            const float* q = p.orientations + slot * 4;
-            x = make_float3(x.x - __ldg(c), x.y - __ldg(c + 1), x.z - __ldg(c + 2));
-            x = quat_inv_rotate(__ldg(q), __ldg(q + 1), __ldg(q + 2), __ldg(q + 3), x);
-          }
-          if (valid) x = scale_local(x, p.scale_mode, p.field_radius);
-          encode_nerf_to_tmem<OCT>(a_addr, x, p.nerf_start, valid);
-        }
+        if (!(MODE == 1 && p.raw_a)) encode_nerf_to_tmem<OCT>(a_addr, x, p.nerf_start, h);
         ptx::tc_wait_st();
         ptx::tc_fence_before();
         ptx::mbar_arrive(&sm.a_ready[s]);
@@ -543,7 +607,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const TcParams p) {
           ptx::mbar_wait(&sm.d_ready[s], pd);
           pd ^= 1;
           ptx::tc_fence_after();
-          hidden_epilogue(d_addr, a_addr, bias2 + l * (W / 2), W);
+          if (my_n > 0) hidden_epilogue(d_addr, a_addr, bias2 + l * (W / 2), my_c0, my_n);
           ptx::tc_wait_st();
           ptx::tc_fence_before();
           ptx::mbar_arrive(&sm.a_ready[s]);
@@ -552,36 +616,40 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const TcParams p) {
         ptx::mbar_wait(&sm.d_ready[s], pd);
         pd ^= 1;
         ptx::tc_fence_after();
-        if (MODE == 1) {
-          const long long gp = tile_in_field * 128 + row;
-          float* o = p.out + (f * p.points_per_field + gp) * p.dim_out;
-          for (int c = 0; c < p.im.layer[L].n_pad; c += 16) {
-            uint32_t v[16];
-            ptx::tmem_ld16(d_addr + c, v);
-            ptx::tc_wait_ld();
-            if (valid) {
+        if (h == 0) {
+          if (MODE == 1) {
+            const long long gp = tile_in_field * 128 + row;
+            float* o = p.out + (f * p.points_per_field + gp) * p.dim_out;
+            for (int c = 0; c < p.im.layer[L].n_pad; c += 16) {
+              uint32_t v[16];
+              ptx::tmem_ld16(d_addr + c, v);
+              ptx::tc_wait_ld();
+              if (valid) {
 #pragma unroll
-              for (int i = 0; i < 16; ++i)
-                if (c + i < p.dim_out) o[c + i] = __uint_as_float(v[i]) + bias_last[c + i];
+                for (int i = 0; i < 16; ++i)
+                  if (c + i < p.dim_out) o[c + i] = __uint_as_float(v[i]) + bias_last[c + i];
+              }
             }
+          } else {
+            uint32_t v[4];
+            ptx::tmem_ld4(d_addr, v);
+            ptx::tc_wait_ld();
+            const float c0 = p.color_factor * (__uint_as_float(v[0]) + bias_last[0]);
+            const float c1 = p.color_factor * (__uint_as_float(v[1]) + bias_last[1]);
+            const float c2 = p.color_factor * (__uint_as_float(v[2]) + bias_last[2]);
+            const float g = __uint_as_float(v[3]) + bias_last[3];
+            const float isd_gamma = p.neus_isd ? __ldg(p.neus_isd + f) * p.geometry_factor : 0.0f;
+            composite_rows(p, sm, s, row, qwarp, lane, bar_comp, ray_global, k, valid, c0, c1, c2, g, d, z, gt,
+                           p.gt != nullptr, isd_gamma);
           }
-        } else {
-          uint32_t v[4];
-          ptx::tmem_ld4(d_addr, v);
-          ptx::tc_wait_ld();
-          const float c0 = p.color_factor * (__uint_as_float(v[0]) + bias_last[0]);
-          const float c1 = p.color_factor * (__uint_as_float(v[1]) + bias_last[1]);
-          const float c2 = p.color_factor * (__uint_as_float(v[2]) + bias_last[2]);
-          const float g = __uint_as_float(v[3]) + bias_last[3];
-          const float isd_gamma = p.neus_isd ? __ldg(p.neus_isd + f) * p.geometry_factor : 0.0f;
-          composite_rows(p, sm, s, row, qwarp, lane, barrier_id, ray_global, k, valid, c0, c1, c2, g, d, z, gt,
-                         p.gt != nullptr, isd_gamma);
         }
-        // all TMEM reads of this tile are complete (wait::ld above) before the next tile's
-        // front end overwrites A and its layer-0 MMA overwrites D.
+        // every TMEM read of this tile has completed (wait::ld) before this thread's next front end
+        // overwrites A; the next layer-0 MMA (which overwrites D) is issued only after all 256
+        // threads of the slot have arrived on a_ready again.
         ptx::tc_fence_before();
       }
     }
+    w_phase ^= 1;
     t = seg_end;
     ptx::fence_proxy_async();  // generic-proxy reads of the image before the next bulk copy overwrites it
     __syncthreads();
@@ -712,9 +780,10 @@ int launch_render_fused_tc(const NgmRenderArgs& a, void* tc_ws, float* isd_ws, c
   p.S = a.num_samples;
   p.G = a.gt ? a.num_samples_guided : 0;
   p.St = p.S + p.G;
-  int Sp = 1;
-  while (Sp < p.St) Sp <<= 1;
+  int Sp = 8, shift = 3;  // ray stride in rows: power of two >= max(St, 8)
+  while (Sp < p.St) { Sp <<= 1; ++shift; }
   p.Sp = Sp;
+  p.sp_shift = shift;
   p.rpt = 128 / Sp;
   p.rays_per_field = a.rays_per_field;
   p.geometry_mode = a.geometry_mode;

@@ -149,6 +149,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t addr, uint32_t (&r)[32]) {
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(addr));
 }
+__device__ __forceinline__ void tmem_st1(uint32_t addr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(addr), "r"(r[0]) : "memory");
+}
+__device__ __forceinline__ void tmem_st2(uint32_t addr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};" ::"r"(addr), "r"(r[0]), "r"(r[1]) : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t addr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3])
+               : "memory");
+}
 __device__ __forceinline__ void tmem_st8(uint32_t addr, const uint32_t* r) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(addr), "r"(r[0]),
                "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
@@ -160,6 +171,26 @@ __device__ __forceinline__ void tmem_st16(uint32_t addr, const uint32_t* r) {
       "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
       "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
+}
+
+// store N consecutive words (compile-time N) as a sequence of x16/x8/x4/x2/x1 stores
+template <int N>
+__device__ __forceinline__ void tmem_store_n(uint32_t addr, const uint32_t* r) {
+  if constexpr (N >= 16) {
+    tmem_st16(addr, r);
+    tmem_store_n<N - 16>(addr + 16, r + 16);
+  } else if constexpr (N >= 8) {
+    tmem_st8(addr, r);
+    tmem_store_n<N - 8>(addr + 8, r + 8);
+  } else if constexpr (N >= 4) {
+    tmem_st4(addr, r);
+    tmem_store_n<N - 4>(addr + 4, r + 4);
+  } else if constexpr (N >= 2) {
+    tmem_st2(addr, r);
+    tmem_store_n<N - 2>(addr + 2, r + 2);
+  } else if constexpr (N == 1) {
+    tmem_st1(addr, r);
+  }
 }
 
 // two fp32 -> packed half2 (lo = a, hi = b), round-to-nearest
