@@ -260,6 +260,10 @@ int ngm_fieldset_knn_workspace_bytes(const NgmKnnFwdArgs* args, size_t* out);
 int ngm_debug_tc_gemm(const float* weight, const float* bias, int n, int k, const void* a_half, int64_t rows, float* out,
                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* diagnostics: with NGM_TC_TRACE=1 in the environment, CTA 0 of every tcgen05 launch records (event, clock)
+ * pairs; this copies them to HOST memory (synchronises the device); returns the event count. */
+int ngm_debug_tc_trace(uint64_t* host_out, int max_events);
+
 int ngm_field_fwd_workspace_bytes(const NgmFieldFwdArgs* args, size_t* out);
 int ngm_render_workspace_bytes(const NgmRenderArgs* args, size_t* out);
 

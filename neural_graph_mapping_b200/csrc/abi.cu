@@ -48,6 +48,8 @@ int launch_tc_gemm_debug(const NgmFieldDesc& fd, const void* a_half, long long r
 size_t knn_workspace_bytes(long long num_points, int num_knn, int num_fields);
 int launch_fieldset_knn(const NgmKnnFwdArgs& a, cudaStream_t stream);
 
+int tc_trace_read(unsigned long long* out, int max_events);
+
 static int validate_field(const NgmFieldDesc& fd) {
   NGM_CHECK_ARG(fd.num_layers >= 0 && fd.num_layers + 1 <= NGM_MAX_LINEARS, "num_layers=%d out of range [0,%d]",
                 fd.num_layers, NGM_MAX_LINEARS - 1);
@@ -215,6 +217,11 @@ int ngm_fieldset_knn_fwd(const NgmKnnFwdArgs* a, void* stream) {
     return NGM_ERR_WORKSPACE;
   }
   return launch_fieldset_knn(*a, (cudaStream_t)stream);
+}
+
+int ngm_debug_tc_trace(uint64_t* host_out, int max_events) {
+  NGM_CHECK_ARG(host_out && max_events > 0, "null args");
+  return tc_trace_read(reinterpret_cast<unsigned long long*>(host_out), max_events);
 }
 
 int ngm_debug_tc_gemm(const float* weight, const float* bias, int n, int k, const void* a_half, int64_t rows, float* out,

@@ -22,6 +22,7 @@
 // TMEM (512 columns): slot s uses columns [256 s, 256 s + 128) for the fp32 accumulator D and
 // [256 s + 128, 256 s + 192) for the fp16 A operand (K <= 128).
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "tc_ptx.cuh"
@@ -158,6 +159,7 @@ struct TcParams {
   uint8_t* freespace_mask;
   float* tsdf;
   uint8_t* tsdf_mask;
+  int trace;
 };
 
 constexpr int kMaxRaysPerTile = 16;  // Sp >= 8
@@ -416,6 +418,20 @@ __device__ __forceinline__ void composite_rows(const TcParams& p, Smem& sm, int 
   }
 }
 
+// ---- optional phase trace (diagnostics; enabled by NGM_TC_TRACE=1, block 0 only) ----------------
+__device__ unsigned long long g_trace[16384];
+__device__ unsigned int g_trace_n;
+__device__ __forceinline__ void trace_ev(int on, unsigned ev) {
+  if (on && blockIdx.x == 0) {
+    const unsigned i = atomicAdd(&g_trace_n, 1u);
+    if (i < 16384u) g_trace[i] = ((unsigned long long)ev << 48) | ((unsigned long long)clock64() & 0xFFFFFFFFFFFFull);
+  }
+}
+// event id = role(4b: 0 issuer, 1 slot thread) | slot(1b) | phase(4b) | layer(4b)
+__device__ __forceinline__ unsigned ev_id(int role, int slot, int phase, int layer) {
+  return (unsigned)((role << 12) | (slot << 8) | (phase << 4) | layer);
+}
+
 // Thread layout (576 threads, one CTA per SM):
 //   warp 0  : MMA issuer of slot 0 (+ weight-image loader)     warp 1 : MMA issuer of slot 1
 //   warps 2-9  : slot 0   (warp w: TMEM quadrant w % 4, column half h = ((w-2) / 4) & 1)
@@ -483,6 +499,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const TcParams p) {
           ptx::mbar_wait(&sm.a_ready[s], pa);  // blocking (hardware-suspended) wait: no issue slots burnt
           pa ^= 1;
           ptx::tc_fence_after();
+          if (lane == 0) trace_ev(p.trace, ev_id(0, s, 0, l));
           if (lane == 0) {
             const TcLayer y = p.im.layer[l];
             const uint32_t idesc = ptx::make_idesc_f16(y.n_pad);
@@ -492,6 +509,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const TcParams p) {
               ptx::mma_f16_ts(d_addr, a_addr + ks * 8, ptx::make_smem_desc_sw128(wsm_addr + boff), idesc, ks > 0);
             }
             ptx::mma_commit(&sm.d_ready[s]);
+            trace_ev(p.trace, ev_id(0, s, 1, l));
           }
           __syncwarp();
         }
@@ -519,9 +537,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const TcParams p) {
       }
       ptx::mbar_wait(&sm.w_ready, w_phase);  // biases live in the image
 
+      const int tr = p.trace && lane == 0 && ((warp - 2) & 7) == 0;  // one leader thread per slot
       int buf = 0;
       for (int ti = s; ti < ntiles; ti += 2, buf ^= 1) {
         const long long tile_in_field = tile0_in_field + ti;
+        trace_ev(tr, ev_id(1, s, 0, 0));
         // ---------- front end: make the A operand of layer 0 ----------
         float3 x = make_float3(0.f, 0.f, 0.f);
         bool valid = false;
@@ -597,25 +617,30 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const TcParams p) {
             z = d * rp[6];
           }
         }
+        trace_ev(tr, ev_id(1, s, 1, 0));
         if (!(MODE == 1 && p.raw_a)) encode_nerf_to_tmem<OCT>(a_addr, x, p.nerf_start, h);
         ptx::tc_wait_st();
         ptx::tc_fence_before();
         ptx::mbar_arrive(&sm.a_ready[s]);
+        trace_ev(tr, ev_id(1, s, 2, 0));
 
         // ---------- hidden layers ----------
         for (int l = 0; l < L; ++l) {
           ptx::mbar_wait(&sm.d_ready[s], pd);
           pd ^= 1;
           ptx::tc_fence_after();
+          trace_ev(tr, ev_id(1, s, 3, l));
           if (my_n > 0) hidden_epilogue(d_addr, a_addr, bias2 + l * (W / 2), my_c0, my_n);
           ptx::tc_wait_st();
           ptx::tc_fence_before();
           ptx::mbar_arrive(&sm.a_ready[s]);
+          trace_ev(tr, ev_id(1, s, 4, l));
         }
         // ---------- last layer ----------
         ptx::mbar_wait(&sm.d_ready[s], pd);
         pd ^= 1;
         ptx::tc_fence_after();
+        trace_ev(tr, ev_id(1, s, 5, 0));
         if (h == 0) {
           if (MODE == 1) {
             const long long gp = tile_in_field * 128 + row;
@@ -643,6 +668,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const TcParams p) {
                            p.gt != nullptr, isd_gamma);
           }
         }
+        trace_ev(tr, ev_id(1, s, 6, 0));
         // every TMEM read of this tile has completed (wait::ld) before this thread's next front end
         // overwrites A; the next layer-0 MMA (which overwrites D) is issued only after all 256
         // threads of the slot have arrived on a_ready again.
@@ -662,8 +688,20 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const TcParams p) {
 
 int nerf_octaves_supported(int o) { return o == 4 || o == 8; }
 
+int tc_trace_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("NGM_TC_TRACE"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v;
+}
+
 template <int MODE>
-int launch_tc(const TcParams& p, int octaves, size_t smem, int grid, cudaStream_t stream) {
+int launch_tc(const TcParams& p_in, int octaves, size_t smem, int grid, cudaStream_t stream) {
+  TcParams p = p_in;
+  p.trace = tc_trace_enabled();
+  if (p.trace) {
+    unsigned zero = 0;
+    cudaMemcpyToSymbolAsync(g_trace_n, &zero, sizeof(zero), 0, cudaMemcpyHostToDevice, stream);
+  }
   auto go = [&](auto kernel) -> int {
     NGM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kernel<<<grid, kThreads, smem, stream>>>(p);
@@ -755,6 +793,17 @@ int launch_tc_gemm_debug(const NgmFieldDesc& fd, const void* a_half, long long r
   const int sms = num_sms();
   const int grid = (int)(p.total_tiles < sms ? p.total_tiles : sms);
   return launch_tc<1>(p, 8, tc_smem_bytes(p.im), grid, stream);
+}
+
+// diagnostics: copy the phase trace of the last traced launch to the host (synchronises the device)
+int tc_trace_read(unsigned long long* out, int max_events) {
+  unsigned n = 0;
+  if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+  if (cudaMemcpyFromSymbol(&n, g_trace_n, sizeof(n)) != cudaSuccess) return -1;
+  if (n > 16384u) n = 16384u;
+  if ((int)n > max_events) n = (unsigned)max_events;
+  if (n && cudaMemcpyFromSymbol(out, g_trace, n * sizeof(unsigned long long)) != cudaSuccess) return -1;
+  return (int)n;
 }
 
 int launch_neus_isd(const float* sd, const int64_t* slots, int num_fields, float* out, cudaStream_t stream);

@@ -1,0 +1,52 @@
+"""Phase trace of the fused tcgen05 render kernel (diagnostics).  Run on a GPU box:
+    NGM_TC_TRACE=1 python tools/tc_trace.py
+Prints, for CTA 0, the cycles between consecutive phase events of each role/slot."""
+import collections
+import ctypes as C
+import os
+import sys
+
+os.environ["NGM_TC_TRACE"] = "1"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+import bench  # noqa: E402
+import neural_graph_mapping_b200 as ngm  # noqa: E402
+from neural_graph_mapping_b200 import _lib  # noqa: E402
+
+dev = "cuda:0"
+sc = bench.synthetic_scene(1)
+st = ngm.RenderState(bench.config_dict(dev, "fp16"))
+st.set_fields(sc["params"], sc["positions"], sc["orientations"])
+cam = ngm.Camera(**bench.CAMERA)
+dz = {k: sc[k].to(dev) for k in ("ijs", "c2w", "near", "far", "field_ids")}
+with torch.no_grad():
+    for _ in range(3):
+        st._render_ijs(dz["ijs"], dz["c2w"], cam, dz["field_ids"], True, dz["near"], dz["far"])
+torch.cuda.synchronize()
+buf = (C.c_uint64 * 16384)()
+n = _lib.lib.ngm_debug_tc_trace(buf, 16384)
+ev = sorted(((buf[i] & 0xFFFFFFFFFFFF), buf[i] >> 48) for i in range(n))
+print("events", n)
+names = {(0, 0): "issuer: a_ready wait done", (0, 1): "issuer: issued+commit", (1, 0): "slot: tile start",
+         (1, 1): "slot: sample ready (pre-encode)", (1, 2): "slot: A0 stored+arrived", (1, 3): "slot: d_ready (hidden)",
+         (1, 4): "slot: hidden epilogue done", (1, 5): "slot: d_ready (last)", (1, 6): "slot: tile done"}
+last = {}
+dur = collections.defaultdict(list)
+for clk, e in ev:
+    role, slot, phase, layer = e >> 12, (e >> 8) & 1, (e >> 4) & 15, e & 15
+    key = (role, slot)
+    if key in last:
+        pclk, pphase, player = last[key]
+        dur[(role, slot, pphase, player, phase, layer)].append(clk - pclk)
+    last[key] = (clk, phase, layer)
+for k in sorted(dur):
+    role, slot, p0, l0, p1, l1 = k
+    v = sorted(dur[k])
+    med = v[len(v) // 2]
+    print(f"role {role} slot {slot}: [{names[(role, p0)]} L{l0}] -> [{names[(role, p1)]} L{l1}]  n={len(v):4d} "
+          f"median {med:7d}  p10 {v[len(v) // 10]:7d}  p90 {v[len(v) * 9 // 10]:7d}")
+t0, t1 = ev[0][0], ev[-1][0]
+tiles = sum(1 for _, e in ev if (e >> 12) == 1 and ((e >> 4) & 15) == 6)
+print(f"CTA 0: {tiles} tiles in {t1 - t0} cycles -> {(t1 - t0) / max(tiles, 1):.0f} cycles/tile (both slots)")
