@@ -166,15 +166,18 @@ constexpr int kMaxRaysPerTile = 16;  // Sp >= 8
 constexpr int kRayFloats = 12;       // o_local[3], dir_local[3], zscale, near, far, gt, valid, pad
 
 struct Smem {
-  uint64_t a_ready[2];
-  uint64_t d_ready[2];
+  uint64_t a0_ready[2];  // layer-0 A operand stored (front-end threads) + previous tile's last D read (compositor threads)
+  uint64_t a_ready[2];   // hidden-layer A operand stored (all 256 threads of the slot)
+  uint64_t d_ready[2];   // accumulator complete (tcgen05.commit)
   uint64_t w_ready;
   uint32_t tmem_base;
   uint32_t pad_;
-  float ray[2][2][kMaxRaysPerTile][kRayFloats];  // [slot][double buffer][ray in tile][param]
-  float sm_d[2][128];      // per slot: sample distance (merge exchange / density deltas)
+  float ray[2][4][kMaxRaysPerTile][kRayFloats];  // [slot][ring of 4 tiles][ray in tile][param]
+  float rowdata[2][2][128][2];  // [slot][tile parity][row]{distance, depth}: front end -> compositor
+  float sm_x[2][128];      // per slot: front end, depth-guided merge exchange
+  float sm_d[2][128];      // per slot: compositor, sample distance (density deltas)
   float sm_g[2][128];      // per slot: geometry after the behind-camera overwrite (neus neighbour)
-  float sm_part[2][4][8];  // per slot, per quadrant: scan tails and partial sums
+  float sm_part[2][2][4][12];  // per slot, per exchange step, per quadrant: scan tails / partial sums
 };
 
 __device__ __forceinline__ float fast_sigmoid(float x) { return __frcp_rn(1.0f + __expf(-x)); }
@@ -187,19 +190,18 @@ __device__ __forceinline__ void sincospi_fast(float t, float& s, float& c) {
   c = __cosf(a);
 }
 
-// NeRF features of one row -> fp16 -> TMEM A operand.  Both threads of a row (h = 0, 1) evaluate the
-// sines and cosines (octaves 0 and 4 directly, the rest by the double-angle recurrence: the error at
-// most doubles per octave, 3 steps -> < 1e-5, far below fp16 resolution); thread h = 0 stores the sine
-// half of the feature vector, h = 1 the cosine half plus the zero padding up to EP.
+// NeRF features of one row -> fp16 -> TMEM A operand (one thread per row).  Octaves 0 and 4 are
+// evaluated directly (exact range reduction + MUFU), the others by the double-angle recurrence: the
+// error at most doubles per octave, 3 steps -> < 1e-5, far below fp16 resolution.
 template <int OCT>
-__device__ __forceinline__ void encode_nerf_to_tmem(uint32_t a_addr, float3 x, int start_octave, int h) {
+__device__ __forceinline__ void encode_nerf_to_tmem(uint32_t a_addr, float3 x, int start_octave) {
   constexpr int E = 6 * OCT;
   constexpr int EP = (E + 15) / 16 * 16;
-  constexpr int HW = 3 * OCT;  // features per half
-  static_assert(HW % 2 == 0, "OCT must be even");
   const float base = exp2f((float)start_octave);
   const float xs[3] = {x.x, x.y, x.z};
-  float fe[HW];
+  float fe[EP];
+#pragma unroll
+  for (int i = E; i < EP; ++i) fe[i] = 0.0f;
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
     const float t0 = xs[d] * base;
@@ -213,21 +215,14 @@ __device__ __forceinline__ void encode_nerf_to_tmem(uint32_t a_addr, float3 x, i
         c = fmaf(-2.0f * s, s, 1.0f);
         s = s2;
       }
-      fe[d * OCT + o] = h ? c : s;
+      fe[d * OCT + o] = s;
+      fe[3 * OCT + d * OCT + o] = c;
     }
   }
-  constexpr int NWH = HW / 2;            // words per half
-  constexpr int NPAD = (EP - E) / 2;     // zero words after the cosine half
-  uint32_t w[NWH + NPAD];
+  uint32_t w[EP / 2];
 #pragma unroll
-  for (int j = 0; j < NWH; ++j) w[j] = ptx::pack_half2(fe[2 * j], fe[2 * j + 1]);
-#pragma unroll
-  for (int j = 0; j < NPAD; ++j) w[NWH + j] = 0u;
-  if (h == 0) {
-    ptx::tmem_store_n<NWH>(a_addr, w);
-  } else {
-    ptx::tmem_store_n<NWH + NPAD>(a_addr + NWH, w);
-  }
+  for (int j = 0; j < EP / 2; ++j) w[j] = ptx::pack_half2(fe[2 * j], fe[2 * j + 1]);
+  ptx::tmem_store_n<EP / 2>(a_addr, w);
 }
 
 // 16 accumulator columns -> relu(x + b) as 8 packed half2 words
@@ -268,7 +263,7 @@ __device__ __forceinline__ float seg_sum(float v, int width) {
   return v;
 }
 
-// Per-ray quantities of the fused renderer, computed once per ray (one tile ahead) instead of per
+// Per-ray quantities of the fused renderer, computed once per ray (two tiles ahead) instead of per
 // sample: the sample point in scaled field-local coordinates is o + d * dir (algebraically the
 // reference's  scale(q^-1 (R (dir d) + t - c)), run_mapping.py:547 + models.py:331-339).
 __device__ __forceinline__ void compute_ray_params(const TcParams& p, long long f, long long slot, long long r, float* out) {
@@ -306,8 +301,19 @@ __device__ __forceinline__ void compute_ray_params(const TcParams& p, long long 
   out[6] = zs; out[7] = nr; out[8] = fr; out[9] = gt; out[10] = ok ? 1.0f : 0.0f; out[11] = 0.f;
 }
 
-// ---- compositor on one tile slot (the 128 h==0 threads, rows with ray stride Sp) -----------------
+template <int WSEG>
+__device__ __forceinline__ float seg_sum(float v) {
+#pragma unroll
+  for (int o = WSEG >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---- compositor on one tile slot (the 128 h == 0 threads, rows with ray stride Sp) ----------------
 // ngm/run_mapping.py:610-639, 709-799.  `valid` = this row is a real sample of a real ray.
+// WSEG = min(Sp, 32): lanes of one ray inside a warp.  Rays of 64 / 128 rows span 2 / 4 warps and
+// exchange the scan tail and the partial moments through shared memory (two named barriers).
+// The variances use Sum w (m - x)^2 = Sum w x^2 - m^2 (2 - Sum w), so one reduction pass suffices.
+template <int WSEG>
 __device__ __forceinline__ void composite_rows(const TcParams& p, Smem& sm, int s, int row, int qwarp, int lane, int barrier_id,
                                                long long ray_global, int k, bool valid, float c0, float c1, float c2, float g,
                                                float d, float z, float gt, bool has_gt, float isd_gamma) {
@@ -316,7 +322,7 @@ __device__ __forceinline__ void composite_rows(const TcParams& p, Smem& sm, int 
   const bool drop_last = (mode == NGM_GEOM_DENSITY || mode == NGM_GEOM_NEUS);
   const int Se = drop_last ? St - 1 : St;
   if (p.overwrite && z < 0.0f) g = (mode == NGM_GEOM_OCCUPANCY || mode == NGM_GEOM_DENSITY) ? -100.0f : 1.0f;
-  if (valid) {
+  if (valid && (p.freespace || p.tsdf)) {
     const long long idx = ray_global * St + k;
     if (p.freespace) {
       const float thr = has_gt ? (gt - p.truncation) * (gt != 0.0f ? 1.0f : 0.0f) : 0.0f;
@@ -353,67 +359,54 @@ __device__ __forceinline__ void composite_rows(const TcParams& p, Smem& sm, int 
     }
   }
   // exclusive product scan of (1 - occ) along the ray
-  const int wseg = Sp < 32 ? Sp : 32;  // segment width inside a warp
   float incl = 1.0f - occ;
-  for (int o = 1; o < wseg; o <<= 1) {
-    const float n = __shfl_up_sync(0xffffffffu, incl, o, wseg);
-    if ((lane & (wseg - 1)) >= o) incl *= n;
+#pragma unroll
+  for (int o = 1; o < WSEG; o <<= 1) {
+    const float n = __shfl_up_sync(0xffffffffu, incl, o, WSEG);
+    if ((lane & (WSEG - 1)) >= o) incl *= n;
   }
-  float excl = __shfl_up_sync(0xffffffffu, incl, 1, wseg);
-  if ((lane & (wseg - 1)) == 0) excl = 1.0f;
-  const int wpr = Sp >> 5;  // warps per ray (0 when Sp < 32)
-  if (wpr > 1) {
-    if (lane == 31) sm.sm_part[s][qwarp][0] = incl;
+  float excl = __shfl_up_sync(0xffffffffu, incl, 1, WSEG);
+  if ((lane & (WSEG - 1)) == 0) excl = 1.0f;
+  const int wpr = Sp >> 5;  // warps per ray (0 or 1: the ray lives inside one warp)
+  const int first = wpr > 1 ? (qwarp & ~(wpr - 1)) : qwarp;
+  if (WSEG == 32 && wpr > 1) {
+    if (lane == 31) sm.sm_part[s][0][qwarp][0] = incl;
     ptx::named_bar_sync(barrier_id, 128);
     float carry = 1.0f;
-    const int first = qwarp & ~(wpr - 1);
-    for (int w = first; w < qwarp; ++w) carry *= sm.sm_part[s][w][0];
+    for (int w = first; w < qwarp; ++w) carry *= sm.sm_part[s][0][w][0];
     excl *= carry;
-    ptx::named_bar_sync(barrier_id, 128);  // sm_part reused below
   }
   const float wgt = occ * excl;
-  float P = seg_sum(wgt, wseg), D = seg_sum(wgt * z, wseg);
-  float C0 = seg_sum(wgt * c0, wseg), C1 = seg_sum(wgt * c1, wseg), C2 = seg_sum(wgt * c2, wseg);
-  if (wpr > 1) {
+  float m[9];
+  m[0] = wgt;        m[1] = wgt * z;    m[2] = wgt * c0;   m[3] = wgt * c1;   m[4] = wgt * c2;
+  m[5] = m[1] * z;   m[6] = m[2] * c0;  m[7] = m[3] * c1;  m[8] = m[4] * c2;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) m[i] = seg_sum<WSEG>(m[i]);
+  if (WSEG == 32 && wpr > 1) {
     if (lane == 0) {
-      float* q = sm.sm_part[s][qwarp];
-      q[0] = P; q[1] = D; q[2] = C0; q[3] = C1; q[4] = C2;
+      float* q = sm.sm_part[s][1][qwarp];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) q[i] = m[i];
     }
     ptx::named_bar_sync(barrier_id, 128);
-    const int first = qwarp & ~(wpr - 1);
-    P = D = C0 = C1 = C2 = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) m[i] = 0.0f;
     for (int w = first; w < first + wpr; ++w) {
-      const float* q = sm.sm_part[s][w];
-      P += q[0]; D += q[1]; C0 += q[2]; C1 += q[3]; C2 += q[4];
-    }
-    ptx::named_bar_sync(barrier_id, 128);
-  }
-  float t;
-  t = D - z;   float vz = seg_sum(wgt * (t * t), wseg);
-  t = C0 - c0; float v0 = seg_sum(wgt * (t * t), wseg);
-  t = C1 - c1; float v1 = seg_sum(wgt * (t * t), wseg);
-  t = C2 - c2; float v2 = seg_sum(wgt * (t * t), wseg);
-  if (wpr > 1) {
-    if (lane == 0) {
-      float* q = sm.sm_part[s][qwarp];
-      q[0] = vz; q[1] = v0; q[2] = v1; q[3] = v2;
-    }
-    ptx::named_bar_sync(barrier_id, 128);
-    const int first = qwarp & ~(wpr - 1);
-    vz = v0 = v1 = v2 = 0.0f;
-    for (int w = first; w < first + wpr; ++w) {
-      const float* q = sm.sm_part[s][w];
-      vz += q[0]; v0 += q[1]; v1 += q[2]; v2 += q[3];
+      const float* q = sm.sm_part[s][1][w];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) m[i] += q[i];
     }
   }
   if (k == 0 && ray_global >= 0) {
+    const float P = m[0], D = m[1], C0 = m[2], C1 = m[3], C2 = m[4];
+    const float t2 = 2.0f - P;
     reinterpret_cast<float4*>(p.rgbd)[ray_global] = make_float4(C0, C1, C2, D);
     if (p.color_var) {
-      p.color_var[ray_global * 3 + 0] = v0;
-      p.color_var[ray_global * 3 + 1] = v1;
-      p.color_var[ray_global * 3 + 2] = v2;
+      p.color_var[ray_global * 3 + 0] = fmaxf(fmaf(-C0 * C0, t2, m[6]), 0.0f);
+      p.color_var[ray_global * 3 + 1] = fmaxf(fmaf(-C1 * C1, t2, m[7]), 0.0f);
+      p.color_var[ray_global * 3 + 2] = fmaxf(fmaf(-C2 * C2, t2, m[8]), 0.0f);
     }
-    if (p.depth_var) p.depth_var[ray_global] = vz;
+    if (p.depth_var) p.depth_var[ray_global] = fmaxf(fmaf(-D * D, t2, m[5]), 0.0f);
     if (p.term_prob) p.term_prob[ray_global] = 1.0f - (1.0f - P);
   }
 }
@@ -427,20 +420,37 @@ __device__ __forceinline__ void trace_ev(int on, unsigned ev) {
     if (i < 16384u) g_trace[i] = ((unsigned long long)ev << 48) | ((unsigned long long)clock64() & 0xFFFFFFFFFFFFull);
   }
 }
-// event id = role(4b: 0 issuer, 1 slot thread) | slot(1b) | phase(4b) | layer(4b)
+// event id = role(4b: 0 issuer, 1 front-end thread, 2 compositor thread) | slot(1b) | phase(4b) | layer(4b)
 __device__ __forceinline__ unsigned ev_id(int role, int slot, int phase, int layer) {
   return (unsigned)((role << 12) | (slot << 8) | (phase << 4) | layer);
 }
 
+// all operands warp-uniform -> the compiler keeps them in uniform registers and issues UTCHMMA directly
+__device__ __forceinline__ void issue_layer(uint32_t d_addr, uint32_t a_addr, uint64_t desc0, uint32_t atom_stride16,
+                                            uint32_t idesc, int ksteps) {
+#pragma unroll
+  for (int ks = 0; ks < 8; ++ks) {
+    if (ks < ksteps) {
+      const uint64_t desc = desc0 + (uint64_t)((ks & 3) * 2u + (ks >> 2) * atom_stride16);
+      ptx::mma_f16_ts(d_addr, a_addr + ks * 8, desc, idesc, ks > 0 ? 1u : 0u);
+    }
+  }
+}
+
 // Thread layout (576 threads, one CTA per SM):
 //   warp 0  : MMA issuer of slot 0 (+ weight-image loader)     warp 1 : MMA issuer of slot 1
-//   warps 2-9  : slot 0   (warp w: TMEM quadrant w % 4, column half h = ((w-2) / 4) & 1)
+//   warps 2-9  : slot 0   (warp w: TMEM quadrant w % 4, half h = ((w-2) / 4) & 1)
 //   warps 10-17: slot 1
+// Within a slot both halves share the hidden-layer epilogues (h = 0: first column half, h = 1: second);
+// h = 1 threads additionally run the FRONT END of the slot's next tile (sample, encode, A operand of
+// layer 0) while the h = 0 threads run the COMPOSITOR of the current tile -- the two overlap.
 template <int MODE, int OCT>
 __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const TcParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  // weights image first (1024-B aligned for SWIZZLE_128B), bookkeeping after it
-  uint8_t* wsm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  // weights image first (1024-B aligned for SWIZZLE_128B), bookkeeping after it; plain pointer
+  // arithmetic on smem_raw keeps the shared address space (LDS/STS, not generic LD/ST)
+  const uint32_t raw_addr = ptx::smem_u32(smem_raw);
+  uint8_t* wsm = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
   Smem& sm = *reinterpret_cast<Smem*>(wsm + (p.im.total_bytes + 127) / 128 * 128);
   const uint32_t wsm_addr = ptx::smem_u32(wsm);
 
@@ -448,10 +458,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const TcParams p) {
 
   if (warp == 0) ptx::tmem_alloc(&sm.tmem_base, kTmemCols);
   if (tid == 64) {
-    ptx::mbar_init(&sm.a_ready[0], 256);
-    ptx::mbar_init(&sm.a_ready[1], 256);
-    ptx::mbar_init(&sm.d_ready[0], 1);
-    ptx::mbar_init(&sm.d_ready[1], 1);
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&sm.a0_ready[s], 256);
+      ptx::mbar_init(&sm.a_ready[s], 256);
+      ptx::mbar_init(&sm.d_ready[s], 1);
+    }
     ptx::mbar_init(&sm.w_ready, 1);
     ptx::fence_mbar_init();
   }
@@ -465,8 +476,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const TcParams p) {
   const long long t_end = p.total_tiles * (blockIdx.x + 1) / gridDim.x;
 
   uint32_t w_phase = 0;
-  uint32_t pa = 0;  // MMA issuer: parity of its slot's a_ready
-  uint32_t pd = 0;  // slot thread: parity of its slot's d_ready
+  uint32_t pa0 = 0, pa = 0;  // MMA issuer: parities of its slot's a0_ready / a_ready
+  uint32_t pd = 0;           // slot thread: parity of its slot's d_ready
   const int L = p.L, W = p.W;
 
   long long t = t_begin;
@@ -492,32 +503,32 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const TcParams p) {
       const int s = warp;
       ptx::mbar_wait(&sm.w_ready, w_phase);
       const int my_tiles = s == 0 ? (ntiles + 1) / 2 : ntiles / 2;
-      const uint32_t d_addr = tmem_base + s * kSlotCols;
+      // broadcast -> provably warp-uniform operands (uniform registers, no per-lane waterfall)
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t wsm_u = __shfl_sync(0xffffffffu, wsm_addr, 0);
+      const uint32_t d_addr = tmem_u + s * kSlotCols;
       const uint32_t a_addr = d_addr + kACol;
       for (int it = 0; it < my_tiles; ++it) {
         for (int l = 0; l <= L; ++l) {
-          ptx::mbar_wait(&sm.a_ready[s], pa);  // blocking (hardware-suspended) wait: no issue slots burnt
-          pa ^= 1;
+          if (l == 0) { ptx::mbar_wait_lean(&sm.a0_ready[s], pa0); pa0 ^= 1; }
+          else        { ptx::mbar_wait_lean(&sm.a_ready[s], pa);   pa ^= 1; }
           ptx::tc_fence_after();
-          if (lane == 0) trace_ev(p.trace, ev_id(0, s, 0, l));
-          if (lane == 0) {
-            const TcLayer y = p.im.layer[l];
-            const uint32_t idesc = ptx::make_idesc_f16(y.n_pad);
-            const int ksteps = y.k_pad / 16;
-            for (int ks = 0; ks < ksteps; ++ks) {
-              const uint32_t boff = y.off + (uint32_t)(ks >> 2) * (uint32_t)y.n_pad * 128u + (uint32_t)(ks & 3) * 32u;
-              ptx::mma_f16_ts(d_addr, a_addr + ks * 8, ptx::make_smem_desc_sw128(wsm_addr + boff), idesc, ks > 0);
-            }
+          trace_ev(p.trace && lane == 0, ev_id(0, s, 0, l));
+          const TcLayer y = p.im.layer[l];
+          const uint64_t desc0 = ptx::make_smem_desc_sw128(wsm_u + y.off);
+          const uint32_t idesc = ptx::make_idesc_f16(y.n_pad);
+          if (ptx::elect_one()) {
+            issue_layer(d_addr, a_addr, desc0, (uint32_t)y.n_pad * 8u, idesc, y.k_pad / 16);
             ptx::mma_commit(&sm.d_ready[s]);
-            trace_ev(p.trace, ev_id(0, s, 1, l));
           }
           __syncwarp();
+          trace_ev(p.trace && lane == 0, ev_id(0, s, 1, l));
         }
       }
     } else {
       // ===================== tile-slot threads =====================
       const int s = (warp - 2) >> 3;
-      const int h = ((warp - 2) >> 2) & 1;  // column half of this thread
+      const int h = ((warp - 2) >> 2) & 1;  // 0: compositor half, 1: front-end half
       const int qwarp = warp & 3;           // TMEM lane quadrant this warp may access
       const int row = qwarp * 32 + lane;
       const uint32_t d_addr = tmem_base + ((uint32_t)(qwarp * 32) << 16) + s * kSlotCols;
@@ -526,41 +537,28 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const TcParams p) {
       const float* bias_last = reinterpret_cast<const float*>(wsm + p.im.bias_last_off);
       const long long slot = p.field_slots ? p.field_slots[f] : f;
       const int bar_slot = 1 + s;  // 256 threads of the slot
-      const int bar_comp = 3 + s;  // the 128 h == 0 threads (compositor)
+      const int bar_half = 3 + 2 * s + h;  // the 128 threads of this half (compositor or front end)
       // column split of the hidden epilogues: multiples of 16, h = 0 takes the (larger) first part
       const int w0 = ((W / 16 + 1) / 2) * 16;
       const int my_c0 = h ? w0 : 0, my_n = h ? W - w0 : w0;
+      const int tr = p.trace && lane == 0 && qwarp == 2;  // one leader thread per half
 
-      if (MODE == 0) {  // ray parameters of this slot's first tile (later tiles are prepared one tile ahead)
-        if (h == 1 && row < p.rpt && s < ntiles)
-          compute_ray_params(p, f, slot, (tile0_in_field + s) * p.rpt + row, sm.ray[s][0][row]);
-      }
-      ptx::mbar_wait(&sm.w_ready, w_phase);  // biases live in the image
-
-      const int tr = p.trace && lane == 0 && ((warp - 2) & 7) == 0;  // one leader thread per slot
-      int buf = 0;
-      for (int ti = s; ti < ntiles; ti += 2, buf ^= 1) {
+      // front end of tile `ti` (h == 1 threads): writes the layer-0 A operand and the row data
+      auto front_end = [&](int ti, int ring, int par) {
         const long long tile_in_field = tile0_in_field + ti;
         trace_ev(tr, ev_id(1, s, 0, 0));
-        // ---------- front end: make the A operand of layer 0 ----------
         float3 x = make_float3(0.f, 0.f, 0.f);
-        bool valid = false;
-        long long ray_global = -1;
-        int k = 0;
-        float d = 0.f, z = 0.f, gt = 0.f;
         if (MODE == 1) {
           const long long gp = tile_in_field * 128 + row;
-          valid = gp < p.points_per_field;
+          const bool valid = gp < p.points_per_field;
           if (p.raw_a) {
-            if (h == 0) {
-              const long long rr = valid ? f * p.points_per_field + gp : 0;
-              const uint32_t* src = reinterpret_cast<const uint32_t*>(p.raw_a + rr * p.EP);
-              for (int c = 0; c < p.EP / 2; c += 8) {
-                uint32_t w[8];
+            const long long rr = valid ? f * p.points_per_field + gp : 0;
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(p.raw_a + rr * p.EP);
+            for (int c = 0; c < p.EP / 2; c += 8) {
+              uint32_t w[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) w[i] = valid ? __ldg(src + c + i) : 0u;
-                ptx::tmem_st8(a_addr + c, w);
-              }
+              for (int i = 0; i < 8; ++i) w[i] = valid ? __ldg(src + c + i) : 0u;
+              ptx::tmem_st8(a_addr + c, w);
             }
           } else if (valid) {
             const float* src = p.points + (f * p.points_per_field + gp) * 3;
@@ -574,24 +572,18 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const TcParams p) {
             x = scale_local(x, p.scale_mode, p.field_radius);
           }
         } else {
-          ptx::named_bar_sync(bar_slot, 256);  // ray parameters written one tile ago are visible
-          // prepare the next tile of this slot while this one runs
-          if (h == 1 && row < p.rpt && ti + 2 < ntiles)
-            compute_ray_params(p, f, slot, (tile_in_field + 2) * p.rpt + row, sm.ray[s][buf ^ 1][row]);
           const int rit = row >> p.sp_shift;
-          k = row & (p.Sp - 1);
-          const float* rp = sm.ray[s][buf][rit];
+          const int k = row & (p.Sp - 1);
+          const float* rp = sm.ray[s][ring][rit];
           const bool ray_ok = rp[10] != 0.0f;
-          const long long r = tile_in_field * p.rpt + rit;
-          if (ray_ok) ray_global = f * p.rays_per_field + r;
-          valid = ray_ok && k < p.St;
-          const float nr = rp[7], fr = rp[8];
-          gt = rp[9];
+          const long long ray = f * p.rays_per_field + tile_in_field * p.rpt + rit;
+          const bool valid = ray_ok && k < p.St;
+          const float nr = rp[7], fr = rp[8], gt = rp[9];
           const int S = p.S, G = p.G, St = p.St;
+          float d = 0.f;
           if (G > 0) {
             // depth-guided merge (run_mapping.py:521-545): own distance + rank, then exchange by rank
-            if (h == 0 && ray_ok && k < St) {
-              const long long ray = ray_global;
+            if (valid) {
               float glo, ghi;
               guided_window(nr, fr, gt, p.range_guided, glo, ghi);
               float dk;
@@ -604,46 +596,80 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const TcParams p) {
                 dk = stratified_distance(glo, ghi, kg, G, p.jit.guided(ray, kg, S, G, St));
                 pos = kg + count_before(dk, nr, fr, S, false, [&](int j) { return p.jit.coarse(ray, j, S, St); });
               }
-              sm.sm_d[s][rit * p.Sp + pos] = dk;
+              sm.sm_x[s][rit * p.Sp + pos] = dk;
             }
-            ptx::named_bar_sync(bar_slot, 256);
-            d = sm.sm_d[s][row];
-            ptx::named_bar_sync(bar_slot, 256);
+            ptx::named_bar_sync(bar_half, 128);
+            d = sm.sm_x[s][row];
+            ptx::named_bar_sync(bar_half, 128);
           } else if (valid) {
-            d = stratified_distance(nr, fr, k, S, p.jit.coarse(ray_global, k, S, St));
+            d = stratified_distance(nr, fr, k, S, p.jit.coarse(ray, k, S, St));
           }
+          float z = 0.f;
           if (valid) {
             x = make_float3(fmaf(d, rp[3], rp[0]), fmaf(d, rp[4], rp[1]), fmaf(d, rp[5], rp[2]));
             z = d * rp[6];
           }
+          *reinterpret_cast<float2*>(sm.rowdata[s][par][row]) = make_float2(d, z);
         }
         trace_ev(tr, ev_id(1, s, 1, 0));
-        if (!(MODE == 1 && p.raw_a)) encode_nerf_to_tmem<OCT>(a_addr, x, p.nerf_start, h);
+        if (!(MODE == 1 && p.raw_a)) encode_nerf_to_tmem<OCT>(a_addr, x, p.nerf_start);
         ptx::tc_wait_st();
         ptx::tc_fence_before();
-        ptx::mbar_arrive(&sm.a_ready[s]);
+        ptx::mbar_arrive(&sm.a0_ready[s]);
         trace_ev(tr, ev_id(1, s, 2, 0));
+      };
 
-        // ---------- hidden layers ----------
-        for (int l = 0; l < L; ++l) {
-          ptx::mbar_wait(&sm.d_ready[s], pd);
+      if (MODE == 0 && h == 1) {  // ray parameters of this slot's first two tiles (later ones two tiles ahead)
+        if (row < p.rpt) {
+          if (s < ntiles) compute_ray_params(p, f, slot, (tile0_in_field + s) * p.rpt + row, sm.ray[s][0][row]);
+          if (s + 2 < ntiles) compute_ray_params(p, f, slot, (tile0_in_field + s + 2) * p.rpt + row, sm.ray[s][1][row]);
+        }
+        ptx::named_bar_sync(bar_half, 128);
+      }
+      ptx::mbar_wait(&sm.w_ready, w_phase);  // biases live in the image
+
+      // Software-pipelined tile loop: iteration `ti` runs the MLP layers of tile ti, then -- concurrently --
+      // the compositor of tile ti (h == 0 threads) and the front end of tile ti + 2 (h == 1 threads).
+      // The first iteration (ti = s - 2) is virtual: it only launches the front end of the first tile.
+      int ring = 3, par = 1;  // ring slot (of 4) of the ray parameters / parity of the row data of tile ti
+      for (int ti = s - 2; ti < ntiles; ti += 2) {
+        const bool real = ti >= 0;
+        const bool has_next = ti + 2 < ntiles;
+        const int nring = (ring + 1) & 3, npar = par ^ 1;
+        const long long tile_in_field = tile0_in_field + ti;
+        if (real) {
+          if (MODE == 0 && h == 1 && row < p.rpt && ti + 4 < ntiles)  // off the critical path: layer 0's MMA runs now
+            compute_ray_params(p, f, slot, (tile_in_field + 4) * p.rpt + row, sm.ray[s][(ring + 2) & 3][row]);
+          // ---------- hidden layers (both halves) ----------
+          for (int l = 0; l < L; ++l) {
+            ptx::mbar_wait_lean(&sm.d_ready[s], pd);
+            pd ^= 1;
+            ptx::tc_fence_after();
+            trace_ev(tr, ev_id(1 + (h == 0), s, 3, l));
+            if (my_n > 0) hidden_epilogue(d_addr, a_addr, bias2 + l * (W / 2), my_c0, my_n);
+            ptx::tc_wait_st();
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(&sm.a_ready[s]);
+            trace_ev(tr, ev_id(1 + (h == 0), s, 4, l));
+          }
+          // ---------- last layer ----------
+          ptx::mbar_wait_lean(&sm.d_ready[s], pd);
           pd ^= 1;
           ptx::tc_fence_after();
-          trace_ev(tr, ev_id(1, s, 3, l));
-          if (my_n > 0) hidden_epilogue(d_addr, a_addr, bias2 + l * (W / 2), my_c0, my_n);
-          ptx::tc_wait_st();
-          ptx::tc_fence_before();
-          ptx::mbar_arrive(&sm.a_ready[s]);
-          trace_ev(tr, ev_id(1, s, 4, l));
+          trace_ev(tr, ev_id(1 + (h == 0), s, 5, 0));
+          // row data / ray parameters written by the front-end half are visible to the compositor half
+          ptx::named_bar_sync(bar_slot, 256);
         }
-        // ---------- last layer ----------
-        ptx::mbar_wait(&sm.d_ready[s], pd);
-        pd ^= 1;
-        ptx::tc_fence_after();
-        trace_ev(tr, ev_id(1, s, 5, 0));
-        if (h == 0) {
+        if (h == 1) {
+          // the A region is free (every MMA of tile ti has completed): front end of the next tile,
+          // concurrent with this tile's compositor on the h == 0 threads
+          if (has_next) front_end(ti + 2, nring, npar);
+        } else if (!real) {
+          if (has_next) ptx::mbar_arrive(&sm.a0_ready[s]);  // first tile: no accumulator to drain
+        } else {
           if (MODE == 1) {
             const long long gp = tile_in_field * 128 + row;
+            const bool valid = gp < p.points_per_field;
             float* o = p.out + (f * p.points_per_field + gp) * p.dim_out;
             for (int c = 0; c < p.im.layer[L].n_pad; c += 16) {
               uint32_t v[16];
@@ -655,24 +681,41 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const TcParams p) {
                   if (c + i < p.dim_out) o[c + i] = __uint_as_float(v[i]) + bias_last[c + i];
               }
             }
+            ptx::tc_fence_before();
+            if (has_next) ptx::mbar_arrive(&sm.a0_ready[s]);
           } else {
             uint32_t v[4];
             ptx::tmem_ld4(d_addr, v);
             ptx::tc_wait_ld();
+            ptx::tc_fence_before();
+            if (has_next) ptx::mbar_arrive(&sm.a0_ready[s]);  // the next layer-0 MMA may overwrite the accumulator
+            const int rit = row >> p.sp_shift;
+            const int k = row & (p.Sp - 1);
+            const float* rp = sm.ray[s][ring][rit];
+            const bool ray_ok = rp[10] != 0.0f;
+            const long long ray_global = ray_ok ? f * p.rays_per_field + tile_in_field * p.rpt + rit : -1;
+            const bool valid = ray_ok && k < p.St;
+            const float gt = rp[9];
+            const float2 dz = *reinterpret_cast<const float2*>(sm.rowdata[s][par][row]);
             const float c0 = p.color_factor * (__uint_as_float(v[0]) + bias_last[0]);
             const float c1 = p.color_factor * (__uint_as_float(v[1]) + bias_last[1]);
             const float c2 = p.color_factor * (__uint_as_float(v[2]) + bias_last[2]);
             const float g = __uint_as_float(v[3]) + bias_last[3];
             const float isd_gamma = p.neus_isd ? __ldg(p.neus_isd + f) * p.geometry_factor : 0.0f;
-            composite_rows(p, sm, s, row, qwarp, lane, bar_comp, ray_global, k, valid, c0, c1, c2, g, d, z, gt,
-                           p.gt != nullptr, isd_gamma);
+            if (p.Sp >= 32)
+              composite_rows<32>(p, sm, s, row, qwarp, lane, bar_half, ray_global, k, valid, c0, c1, c2, g, dz.x, dz.y, gt,
+                                 p.gt != nullptr, isd_gamma);
+            else if (p.Sp == 16)
+              composite_rows<16>(p, sm, s, row, qwarp, lane, bar_half, ray_global, k, valid, c0, c1, c2, g, dz.x, dz.y, gt,
+                                 p.gt != nullptr, isd_gamma);
+            else
+              composite_rows<8>(p, sm, s, row, qwarp, lane, bar_half, ray_global, k, valid, c0, c1, c2, g, dz.x, dz.y, gt,
+                                p.gt != nullptr, isd_gamma);
           }
+          trace_ev(tr, ev_id(2, s, 6, 0));
         }
-        trace_ev(tr, ev_id(1, s, 6, 0));
-        // every TMEM read of this tile has completed (wait::ld) before this thread's next front end
-        // overwrites A; the next layer-0 MMA (which overwrites D) is issued only after all 256
-        // threads of the slot have arrived on a_ready again.
-        ptx::tc_fence_before();
+        ring = nring;
+        par = npar;
       }
     }
     w_phase ^= 1;

@@ -77,6 +77,31 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Unbounded-in-time but iteration-bounded wait with the smallest possible loop body (used on the
+// kernel's critical paths): a waiting warp costs ~4 issue slots per wake-up instead of ~13.
+__device__ __forceinline__ void mbar_wait_lean(uint64_t* bar, uint32_t parity) {
+  uint32_t it = 0;
+#pragma unroll 1
+  while (!mbar_try_hint(bar, parity, 0x989680u)) {
+    if (++it == 0x4000000u) {  // ~10^8 wake-ups: a protocol bug, not a slow tile
+      printf("ngm: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x,
+             smem_u32(bar), parity);
+      __trap();
+    }
+  }
+}
+
+// one lane of the (converged) warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // named barrier among a subset of warps
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
