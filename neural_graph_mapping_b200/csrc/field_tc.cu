@@ -35,6 +35,7 @@ constexpr int kThreads = 576;
 constexpr int kTmemCols = 512;
 constexpr int kSlotCols = 256;
 constexpr int kACol = 128;
+constexpr int kStageCol = 192;  // layer-0 A operand of the slot's NEXT tile (<= 32 columns: K <= 64)
 constexpr uint32_t kMaxImageBytes = 200 * 1024;
 
 struct TcLayer {
@@ -173,7 +174,7 @@ struct Smem {
   uint32_t tmem_base;
   uint32_t pad_;
   float ray[2][4][kMaxRaysPerTile][kRayFloats];  // [slot][ring of 4 tiles][ray in tile][param]
-  float rowdata[2][2][128][2];  // [slot][tile parity][row]{distance, depth}: front end -> compositor
+  float rowdata[2][3][128][2];  // [slot][ring of 3 tiles][row]{distance, depth}: front end -> compositor
   float sm_x[2][128];      // per slot: front end, depth-guided merge exchange
   float sm_d[2][128];      // per slot: compositor, sample distance (density deltas)
   float sm_g[2][128];      // per slot: geometry after the behind-camera overwrite (neus neighbour)
@@ -518,7 +519,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const TcParams p) {
           const uint64_t desc0 = ptx::make_smem_desc_sw128(wsm_u + y.off);
           const uint32_t idesc = ptx::make_idesc_f16(y.n_pad);
           if (ptx::elect_one()) {
-            issue_layer(d_addr, a_addr, desc0, (uint32_t)y.n_pad * 8u, idesc, y.k_pad / 16);
+            issue_layer(d_addr, l == 0 ? d_addr + kStageCol : a_addr, desc0, (uint32_t)y.n_pad * 8u, idesc, y.k_pad / 16);
             ptx::mma_commit(&sm.d_ready[s]);
           }
           __syncwarp();
@@ -543,33 +544,27 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const TcParams p) {
       const int my_c0 = h ? w0 : 0, my_n = h ? W - w0 : w0;
       const int tr = p.trace && lane == 0 && qwarp == 2;  // one leader thread per half
 
-      // front end of tile `ti` (h == 1 threads): writes the layer-0 A operand and the row data
-      auto front_end = [&](int ti, int ring, int par) {
+      const uint32_t a0_addr = d_addr + kStageCol;  // staging columns: layer-0 A operand of the NEXT tile
+      float3 fx = make_float3(0.f, 0.f, 0.f);        // sample point of this row for the next tile (fe_a -> fe_b)
+
+      // Front end of tile `ti` (h == 1 threads), in two parts that are slotted into the waits for
+      // the CURRENT tile's MMAs:  fe_a = sample point + row data,  fe_b = encoding -> staging -> arrive.
+      auto fe_a = [&](int ti, int ring, int par) {
         const long long tile_in_field = tile0_in_field + ti;
         trace_ev(tr, ev_id(1, s, 0, 0));
-        float3 x = make_float3(0.f, 0.f, 0.f);
+        fx = make_float3(0.f, 0.f, 0.f);
         if (MODE == 1) {
           const long long gp = tile_in_field * 128 + row;
-          const bool valid = gp < p.points_per_field;
-          if (p.raw_a) {
-            const long long rr = valid ? f * p.points_per_field + gp : 0;
-            const uint32_t* src = reinterpret_cast<const uint32_t*>(p.raw_a + rr * p.EP);
-            for (int c = 0; c < p.EP / 2; c += 8) {
-              uint32_t w[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) w[i] = valid ? __ldg(src + c + i) : 0u;
-              ptx::tmem_st8(a_addr + c, w);
-            }
-          } else if (valid) {
+          if (!p.raw_a && gp < p.points_per_field) {
             const float* src = p.points + (f * p.points_per_field + gp) * 3;
-            x = make_float3(__ldg(src), __ldg(src + 1), __ldg(src + 2));
+            float3 x = make_float3(__ldg(src), __ldg(src + 1), __ldg(src + 2));
             if (p.positions) {
               const float* c = p.positions + slot * 3;
               const float* q = p.orientations + slot * 4;
               x = make_float3(x.x - __ldg(c), x.y - __ldg(c + 1), x.z - __ldg(c + 2));
               x = quat_inv_rotate(__ldg(q), __ldg(q + 1), __ldg(q + 2), __ldg(q + 3), x);
             }
-            x = scale_local(x, p.scale_mode, p.field_radius);
+            fx = scale_local(x, p.scale_mode, p.field_radius);
           }
         } else {
           const int rit = row >> p.sp_shift;
@@ -606,13 +601,28 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const TcParams p) {
           }
           float z = 0.f;
           if (valid) {
-            x = make_float3(fmaf(d, rp[3], rp[0]), fmaf(d, rp[4], rp[1]), fmaf(d, rp[5], rp[2]));
+            fx = make_float3(fmaf(d, rp[3], rp[0]), fmaf(d, rp[4], rp[1]), fmaf(d, rp[5], rp[2]));
             z = d * rp[6];
           }
           *reinterpret_cast<float2*>(sm.rowdata[s][par][row]) = make_float2(d, z);
         }
         trace_ev(tr, ev_id(1, s, 1, 0));
-        if (!(MODE == 1 && p.raw_a)) encode_nerf_to_tmem<OCT>(a_addr, x, p.nerf_start);
+      };
+      auto fe_b = [&](int ti) {
+        if (MODE == 1 && p.raw_a) {
+          const long long gp = (tile0_in_field + ti) * 128 + row;
+          const bool valid = gp < p.points_per_field;
+          const long long rr = valid ? f * p.points_per_field + gp : 0;
+          const uint32_t* src = reinterpret_cast<const uint32_t*>(p.raw_a + rr * p.EP);
+          for (int c = 0; c < p.EP / 2; c += 8) {
+            uint32_t w[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) w[i] = valid ? __ldg(src + c + i) : 0u;
+            ptx::tmem_st8(a0_addr + c, w);
+          }
+        } else {
+          encode_nerf_to_tmem<OCT>(a0_addr, fx, p.nerf_start);
+        }
         ptx::tc_wait_st();
         ptx::tc_fence_before();
         ptx::mbar_arrive(&sm.a0_ready[s]);
@@ -628,91 +638,95 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const TcParams p) {
       }
       ptx::mbar_wait(&sm.w_ready, w_phase);  // biases live in the image
 
-      // Software-pipelined tile loop: iteration `ti` runs the MLP layers of tile ti, then -- concurrently --
-      // the compositor of tile ti (h == 0 threads) and the front end of tile ti + 2 (h == 1 threads).
-      // The first iteration (ti = s - 2) is virtual: it only launches the front end of the first tile.
-      int ring = 3, par = 1;  // ring slot (of 4) of the ray parameters / parity of the row data of tile ti
+      // Software-pipelined tile loop.  Iteration `ti` runs the MLP layers of tile ti; the front end of the
+      // slot's next tile (ti + 2) is slotted into the waits for tile ti's MMAs (h == 1 threads: fe_a after
+      // the first epilogue, fe_b after the second), and the compositor of tile ti (h == 0 threads) runs
+      // after the last layer while the next tile's layer 0 is already on the tensor pipe.
+      // The first iteration (ti = s - 2) is virtual: it only runs the front end of the first tile.
+      int ring = 3, par = 2;  // ring slot (of 4) of the ray parameters / ring slot (of 3) of the row data of tile ti
       for (int ti = s - 2; ti < ntiles; ti += 2) {
         const bool real = ti >= 0;
         const bool has_next = ti + 2 < ntiles;
-        const int nring = (ring + 1) & 3, npar = par ^ 1;
+        const int nring = (ring + 1) & 3, npar = par == 2 ? 0 : par + 1;
         const long long tile_in_field = tile0_in_field + ti;
-        if (real) {
-          if (MODE == 0 && h == 1 && row < p.rpt && ti + 4 < ntiles)  // off the critical path: layer 0's MMA runs now
-            compute_ray_params(p, f, slot, (tile_in_field + 4) * p.rpt + row, sm.ray[s][(ring + 2) & 3][row]);
-          // ---------- hidden layers (both halves) ----------
-          for (int l = 0; l < L; ++l) {
+        const int nsteps = real ? L + 1 : 1;
+        const int step_b = real ? (L < 1 ? L : 1) : 0;  // fe_a at step 0, fe_b at step min(1, L)
+        if (real && MODE == 0 && h == 1 && row < p.rpt && ti + 4 < ntiles)  // off the critical path: layer 0's MMA runs now
+          compute_ray_params(p, f, slot, (tile_in_field + 4) * p.rpt + row, sm.ray[s][(ring + 2) & 3][row]);
+        for (int l = 0; l < nsteps; ++l) {
+          if (real) {
             ptx::mbar_wait_lean(&sm.d_ready[s], pd);
             pd ^= 1;
             ptx::tc_fence_after();
-            trace_ev(tr, ev_id(1 + (h == 0), s, 3, l));
-            if (my_n > 0) hidden_epilogue(d_addr, a_addr, bias2 + l * (W / 2), my_c0, my_n);
-            ptx::tc_wait_st();
-            ptx::tc_fence_before();
-            ptx::mbar_arrive(&sm.a_ready[s]);
-            trace_ev(tr, ev_id(1 + (h == 0), s, 4, l));
-          }
-          // ---------- last layer ----------
-          ptx::mbar_wait_lean(&sm.d_ready[s], pd);
-          pd ^= 1;
-          ptx::tc_fence_after();
-          trace_ev(tr, ev_id(1 + (h == 0), s, 5, 0));
-          // row data / ray parameters written by the front-end half are visible to the compositor half
-          ptx::named_bar_sync(bar_slot, 256);
-        }
-        if (h == 1) {
-          // the A region is free (every MMA of tile ti has completed): front end of the next tile,
-          // concurrent with this tile's compositor on the h == 0 threads
-          if (has_next) front_end(ti + 2, nring, npar);
-        } else if (!real) {
-          if (has_next) ptx::mbar_arrive(&sm.a0_ready[s]);  // first tile: no accumulator to drain
-        } else {
-          if (MODE == 1) {
-            const long long gp = tile_in_field * 128 + row;
-            const bool valid = gp < p.points_per_field;
-            float* o = p.out + (f * p.points_per_field + gp) * p.dim_out;
-            for (int c = 0; c < p.im.layer[L].n_pad; c += 16) {
-              uint32_t v[16];
-              ptx::tmem_ld16(d_addr + c, v);
-              ptx::tc_wait_ld();
-              if (valid) {
+            if (l < L) {
+              // ---------- hidden layer l (both halves) ----------
+              trace_ev(tr, ev_id(1 + (h == 0), s, 3, l));
+              if (my_n > 0) hidden_epilogue(d_addr, a_addr, bias2 + l * (W / 2), my_c0, my_n);
+              ptx::tc_wait_st();
+              ptx::tc_fence_before();
+              ptx::mbar_arrive(&sm.a_ready[s]);
+              trace_ev(tr, ev_id(1 + (h == 0), s, 4, l));
+            } else {
+              // ---------- last layer ----------
+              trace_ev(tr, ev_id(1 + (h == 0), s, 5, 0));
+              // row data / ray parameters written by the front-end half are visible to the compositor half
+              ptx::named_bar_sync(bar_slot, 256);
+              if (h == 0) {
+                if (MODE == 1) {
+                  const long long gp = tile_in_field * 128 + row;
+                  const bool valid = gp < p.points_per_field;
+                  float* o = p.out + (f * p.points_per_field + gp) * p.dim_out;
+                  for (int c = 0; c < p.im.layer[L].n_pad; c += 16) {
+                    uint32_t v[16];
+                    ptx::tmem_ld16(d_addr + c, v);
+                    ptx::tc_wait_ld();
+                    if (valid) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i)
-                  if (c + i < p.dim_out) o[c + i] = __uint_as_float(v[i]) + bias_last[c + i];
+                      for (int i = 0; i < 16; ++i)
+                        if (c + i < p.dim_out) o[c + i] = __uint_as_float(v[i]) + bias_last[c + i];
+                    }
+                  }
+                  ptx::tc_fence_before();
+                  if (has_next) ptx::mbar_arrive(&sm.a0_ready[s]);
+                } else {
+                  uint32_t v[4];
+                  ptx::tmem_ld4(d_addr, v);
+                  const int rit = row >> p.sp_shift;
+                  const int k = row & (p.Sp - 1);
+                  const float* rp = sm.ray[s][ring][rit];
+                  const bool ray_ok = rp[10] != 0.0f;
+                  const float gt = rp[9];
+                  const float2 dz = *reinterpret_cast<const float2*>(sm.rowdata[s][par][row]);
+                  ptx::tc_wait_ld();
+                  ptx::tc_fence_before();
+                  if (has_next) ptx::mbar_arrive(&sm.a0_ready[s]);  // the next layer-0 MMA may overwrite the accumulator
+                  const long long ray_global = ray_ok ? f * p.rays_per_field + tile_in_field * p.rpt + rit : -1;
+                  const bool valid = ray_ok && k < p.St;
+                  const float c0 = p.color_factor * (__uint_as_float(v[0]) + bias_last[0]);
+                  const float c1 = p.color_factor * (__uint_as_float(v[1]) + bias_last[1]);
+                  const float c2 = p.color_factor * (__uint_as_float(v[2]) + bias_last[2]);
+                  const float g = __uint_as_float(v[3]) + bias_last[3];
+                  const float isd_gamma = p.neus_isd ? __ldg(p.neus_isd + f) * p.geometry_factor : 0.0f;
+                  if (p.Sp >= 32)
+                    composite_rows<32>(p, sm, s, row, qwarp, lane, bar_half, ray_global, k, valid, c0, c1, c2, g, dz.x, dz.y,
+                                       gt, p.gt != nullptr, isd_gamma);
+                  else if (p.Sp == 16)
+                    composite_rows<16>(p, sm, s, row, qwarp, lane, bar_half, ray_global, k, valid, c0, c1, c2, g, dz.x, dz.y,
+                                       gt, p.gt != nullptr, isd_gamma);
+                  else
+                    composite_rows<8>(p, sm, s, row, qwarp, lane, bar_half, ray_global, k, valid, c0, c1, c2, g, dz.x, dz.y,
+                                      gt, p.gt != nullptr, isd_gamma);
+                }
+                trace_ev(tr, ev_id(2, s, 6, 0));
               }
             }
-            ptx::tc_fence_before();
-            if (has_next) ptx::mbar_arrive(&sm.a0_ready[s]);
-          } else {
-            uint32_t v[4];
-            ptx::tmem_ld4(d_addr, v);
-            ptx::tc_wait_ld();
-            ptx::tc_fence_before();
-            if (has_next) ptx::mbar_arrive(&sm.a0_ready[s]);  // the next layer-0 MMA may overwrite the accumulator
-            const int rit = row >> p.sp_shift;
-            const int k = row & (p.Sp - 1);
-            const float* rp = sm.ray[s][ring][rit];
-            const bool ray_ok = rp[10] != 0.0f;
-            const long long ray_global = ray_ok ? f * p.rays_per_field + tile_in_field * p.rpt + rit : -1;
-            const bool valid = ray_ok && k < p.St;
-            const float gt = rp[9];
-            const float2 dz = *reinterpret_cast<const float2*>(sm.rowdata[s][par][row]);
-            const float c0 = p.color_factor * (__uint_as_float(v[0]) + bias_last[0]);
-            const float c1 = p.color_factor * (__uint_as_float(v[1]) + bias_last[1]);
-            const float c2 = p.color_factor * (__uint_as_float(v[2]) + bias_last[2]);
-            const float g = __uint_as_float(v[3]) + bias_last[3];
-            const float isd_gamma = p.neus_isd ? __ldg(p.neus_isd + f) * p.geometry_factor : 0.0f;
-            if (p.Sp >= 32)
-              composite_rows<32>(p, sm, s, row, qwarp, lane, bar_half, ray_global, k, valid, c0, c1, c2, g, dz.x, dz.y, gt,
-                                 p.gt != nullptr, isd_gamma);
-            else if (p.Sp == 16)
-              composite_rows<16>(p, sm, s, row, qwarp, lane, bar_half, ray_global, k, valid, c0, c1, c2, g, dz.x, dz.y, gt,
-                                 p.gt != nullptr, isd_gamma);
-            else
-              composite_rows<8>(p, sm, s, row, qwarp, lane, bar_half, ray_global, k, valid, c0, c1, c2, g, dz.x, dz.y, gt,
-                                p.gt != nullptr, isd_gamma);
+          } else if (h == 0) {
+            if (has_next) ptx::mbar_arrive(&sm.a0_ready[s]);  // first tile: no accumulator to drain
           }
-          trace_ev(tr, ev_id(2, s, 6, 0));
+          if (h == 1 && has_next) {
+            if (l == 0) fe_a(ti + 2, nring, npar);
+            if (l == step_b) fe_b(ti + 2);
+          }
         }
         ring = nring;
         par = npar;

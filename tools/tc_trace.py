@@ -29,9 +29,20 @@ buf = (C.c_uint64 * 16384)()
 n = _lib.lib.ngm_debug_tc_trace(buf, 16384)
 ev = sorted(((buf[i] & 0xFFFFFFFFFFFF), buf[i] >> 48) for i in range(n))
 print("events", n)
-names = {(0, 0): "issuer: a_ready wait done", (0, 1): "issuer: issued+commit", (1, 0): "slot: tile start",
-         (1, 1): "slot: sample ready (pre-encode)", (1, 2): "slot: A0 stored+arrived", (1, 3): "slot: d_ready (hidden)",
-         (1, 4): "slot: hidden epilogue done", (1, 5): "slot: d_ready (last)", (1, 6): "slot: tile done"}
+PH = {0: "FE start", 1: "sample ready (pre-encode)", 2: "A0 stored+arrived", 3: "d_ready (hidden)",
+      4: "hidden epilogue done", 5: "d_ready (last)", 6: "compositor done"}
+ROLE = {0: "issuer", 1: "front-end half", 2: "compositor half"}
+
+
+class _N(dict):
+    def __missing__(self, k):
+        role, ph = k
+        if role == 0:
+            return "issuer: " + ("a_ready wait done" if ph == 0 else "issued+commit")
+        return f"{ROLE.get(role, role)}: {PH.get(ph, ph)}"
+
+
+names = _N()
 last = {}
 dur = collections.defaultdict(list)
 for clk, e in ev:
@@ -48,5 +59,5 @@ for k in sorted(dur):
     print(f"role {role} slot {slot}: [{names[(role, p0)]} L{l0}] -> [{names[(role, p1)]} L{l1}]  n={len(v):4d} "
           f"median {med:7d}  p10 {v[len(v) // 10]:7d}  p90 {v[len(v) * 9 // 10]:7d}")
 t0, t1 = ev[0][0], ev[-1][0]
-tiles = sum(1 for _, e in ev if (e >> 12) == 1 and ((e >> 4) & 15) == 6)
+tiles = sum(1 for _, e in ev if (e >> 12) == 2 and ((e >> 4) & 15) == 6)
 print(f"CTA 0: {tiles} tiles in {t1 - t0} cycles -> {(t1 - t0) / max(tiles, 1):.0f} cycles/tile (both slots)")
