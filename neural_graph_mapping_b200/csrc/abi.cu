@@ -49,6 +49,7 @@ size_t knn_workspace_bytes(long long num_points, int num_knn, int num_fields);
 int launch_fieldset_knn(const NgmKnnFwdArgs& a, cudaStream_t stream);
 
 int tc_trace_read(unsigned long long* out, int max_events);
+int tmem_bw_bench(int warps, int iters, int mode, unsigned long long* host_cycles);
 
 static int validate_field(const NgmFieldDesc& fd) {
   NGM_CHECK_ARG(fd.num_layers >= 0 && fd.num_layers + 1 <= NGM_MAX_LINEARS, "num_layers=%d out of range [0,%d]",
@@ -217,6 +218,11 @@ int ngm_fieldset_knn_fwd(const NgmKnnFwdArgs* a, void* stream) {
     return NGM_ERR_WORKSPACE;
   }
   return launch_fieldset_knn(*a, (cudaStream_t)stream);
+}
+
+int ngm_debug_tmem_bw(int warps, int iters, int mode, uint64_t* host_cycles) {
+  NGM_CHECK_ARG(warps >= 1 && warps <= 32 && iters > 0 && host_cycles, "bad args");
+  return tmem_bw_bench(warps, iters, mode, reinterpret_cast<unsigned long long*>(host_cycles));
 }
 
 int ngm_debug_tc_trace(uint64_t* host_out, int max_events) {

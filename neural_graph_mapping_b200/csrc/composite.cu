@@ -6,9 +6,7 @@
 // One warp per ray; lane l owns samples l, l+32, ... so every load is a contiguous 128 B
 // (distances, depths) or 512 B (packed rgb+geometry float4) row segment.  Transmittance is a
 // warp-shuffle exclusive product scan with a running carry between 32-sample blocks; the
-// expectations are shuffle reductions; the variances use the reference's two-pass form
-// (mean first, then sum w (mean - x)^2), with the per-sample terms cached in registers for
-// S <= 128 and recomputed otherwise.
+// expectations and second moments are shuffle reductions (one pass; variances from the moments).
 #include "common.cuh"
 
 namespace ngm {
@@ -16,7 +14,6 @@ namespace ngm {
 namespace {
 
 constexpr int kWarpsPerBlock = 8;
-constexpr int kCacheBlocks = 4;  // S <= 128 keeps per-sample terms in registers
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -48,8 +45,10 @@ struct RayCtx {
   __device__ __forceinline__ float occupancy(int k, float g, float dist) const {
     switch (a.geometry_mode) {
       case NGM_GEOM_NRGBD: {
-        float t = a.geometry_factor * g;
-        return (4.0f * sigmoidf(t)) * sigmoidf(-t);
+        // 4 s(t) s(-t) = 4u / (1 + u)^2 with u = exp(-|t|): one exponential, no overflow
+        const float u = expf(-fabsf(a.geometry_factor * g));
+        const float q = 1.0f + u;
+        return (4.0f * u) / (q * q);
       }
       case NGM_GEOM_OCCUPANCY:
         return sigmoidf(a.geometry_factor * g);
@@ -70,7 +69,7 @@ struct RayCtx {
 
 // One 32-sample block: loads, aux outputs, occupancy, scan.  `carry` = transmittance entering
 // the block, updated on exit.
-__device__ __forceinline__ SampleTerms eval_block(const RayCtx& c, int blk, float& carry, bool write_aux) {
+__device__ __forceinline__ SampleTerms eval_block(const RayCtx& c, int blk, float& carry) {
   const NgmCompositeArgs& a = c.a;
   const int k = blk * 32 + c.lane;
   SampleTerms t{0.f, 0.f, 0.f, 0.f, 0.f};
@@ -80,25 +79,28 @@ __device__ __forceinline__ SampleTerms eval_block(const RayCtx& c, int blk, floa
     const float dist = __ldg(a.distances + idx);
     const float z = __ldg(a.depths + idx);
     const float g = c.geometry(k, z);
-    if (write_aux) {
-      if (a.freespace) {  // run_mapping.py:624-630
-        float thr = c.has_gt ? (c.gt - a.truncation) * (c.gt != 0.0f ? 1.0f : 0.0f) : 0.0f;
-        a.freespace[idx] = g * a.truncation;
-        a.freespace_mask[idx] = (c.has_gt && dist < thr) ? 1 : 0;
-      }
-      if (a.tsdf) {  // run_mapping.py:632-639
-        float delta = c.gt - dist;
-        a.tsdf[idx] = g * a.truncation - delta;
-        a.tsdf_mask[idx] = (c.has_gt && fabsf(delta) < a.truncation && c.gt != 0.0f) ? 1 : 0;
-      }
+    if (a.freespace) {  // run_mapping.py:624-630
+      float thr = c.has_gt ? (c.gt - a.truncation) * (c.gt != 0.0f ? 1.0f : 0.0f) : 0.0f;
+      a.freespace[idx] = g * a.truncation;
+      a.freespace_mask[idx] = (c.has_gt && dist < thr) ? 1 : 0;
+    }
+    if (a.tsdf) {  // run_mapping.py:632-639
+      float delta = c.gt - dist;
+      a.tsdf[idx] = g * a.truncation - delta;
+      a.tsdf_mask[idx] = (c.has_gt && fabsf(delta) < a.truncation && c.gt != 0.0f) ? 1 : 0;
     }
     if (k < c.Se) {
       occ = c.occupancy(k, g, dist);
       t.z = z;
       const float* col = a.colors + idx * a.color_stride;
-      t.c0 = a.color_factor * __ldg(col + 0);
-      t.c1 = a.color_factor * __ldg(col + 1);
-      t.c2 = a.color_factor * __ldg(col + 2);
+      if (a.color_stride == 4) {  // packed MLP output: one 16-byte load
+        const float4 v = __ldg(reinterpret_cast<const float4*>(col));
+        t.c0 = a.color_factor * v.x; t.c1 = a.color_factor * v.y; t.c2 = a.color_factor * v.z;
+      } else {
+        t.c0 = a.color_factor * __ldg(col + 0);
+        t.c1 = a.color_factor * __ldg(col + 1);
+        t.c2 = a.color_factor * __ldg(col + 2);
+      }
     }
   }
   // exclusive product scan of (1 - occ) across the warp, times carry (run_mapping.py:764-771)
@@ -115,7 +117,9 @@ __device__ __forceinline__ SampleTerms eval_block(const RayCtx& c, int blk, floa
   return t;
 }
 
-template <bool CACHE>
+// One pass per ray: per-lane partial moments over the ray's 32-sample blocks, then nine warp
+// reductions.  The variances use  Sum w (m - x)^2 = Sum w x^2 - m^2 (2 - Sum w)  (exact algebra;
+// the fp32 cancellation error is ~1e-7 of the colour / depth scale).
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) composite_kernel(NgmCompositeArgs a) {
   const int lane = threadIdx.x & 31;
   const long long warp0 = blockIdx.x * (long long)kWarpsPerBlock + (threadIdx.x >> 5);
@@ -129,61 +133,30 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) composite_kernel(NgmCompo
     if (a.geometry_mode == NGM_GEOM_NEUS)
       c.isd_gamma = __ldg(a.neus_isd + ray / a.rays_per_isd) * a.geometry_factor;
     if (c.has_gt) c.gt = __ldg(a.gt + ray);
-
-    SampleTerms cache[CACHE ? kCacheBlocks : 1];
     float carry = 1.0f;
-    float sw = 0.f, sz = 0.f, s0 = 0.f, s1 = 0.f, s2 = 0.f;
-    auto pass1 = [&](int b) {
-      SampleTerms t = eval_block(c, b, carry, true);
-      if (CACHE) cache[CACHE ? b : 0] = t;
-      sw += t.w;
-      sz += t.w * t.z;
-      s0 += t.w * t.c0;
-      s1 += t.w * t.c1;
-      s2 += t.w * t.c2;
+    float m[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int b = 0; b < nblk; ++b) {
+      const SampleTerms t = eval_block(c, b, carry);
+      const float wz = t.w * t.z, w0 = t.w * t.c0, w1 = t.w * t.c1, w2 = t.w * t.c2;
+      m[0] += t.w; m[1] += wz; m[2] += w0; m[3] += w1; m[4] += w2;
+      m[5] += wz * t.z; m[6] += w0 * t.c0; m[7] += w1 * t.c1; m[8] += w2 * t.c2;
       if (a.weights) {
-        int k = b * 32 + lane;
+        const int k = b * 32 + lane;
         if (k < S) a.weights[ray * S + k] = t.w;
       }
-    };
-    if (CACHE) {
-#pragma unroll
-      for (int b = 0; b < kCacheBlocks; ++b)
-        if (b < nblk) pass1(b);
-    } else {
-      for (int b = 0; b < nblk; ++b) pass1(b);
     }
-    const float P = warp_sum(sw), D = warp_sum(sz);
-    const float C0 = warp_sum(s0), C1 = warp_sum(s1), C2 = warp_sum(s2);
-
-    float vz = 0.f, v0 = 0.f, v1 = 0.f, v2 = 0.f;
-    if (a.color_var || a.depth_var) {
-      carry = 1.0f;
-      auto pass2 = [&](int b) {
-        SampleTerms t = CACHE ? cache[CACHE ? b : 0] : eval_block(c, b, carry, false);
-        float d;
-        d = D - t.z;  vz += t.w * (d * d);
-        d = C0 - t.c0; v0 += t.w * (d * d);
-        d = C1 - t.c1; v1 += t.w * (d * d);
-        d = C2 - t.c2; v2 += t.w * (d * d);
-      };
-      if (CACHE) {
 #pragma unroll
-        for (int b = 0; b < kCacheBlocks; ++b)
-          if (b < nblk) pass2(b);
-      } else {
-        for (int b = 0; b < nblk; ++b) pass2(b);
-      }
-      vz = warp_sum(vz); v0 = warp_sum(v0); v1 = warp_sum(v1); v2 = warp_sum(v2);
-    }
+    for (int i = 0; i < 9; ++i) m[i] = warp_sum(m[i]);
     if (lane == 0) {
+      const float P = m[0], D = m[1], C0 = m[2], C1 = m[3], C2 = m[4];
+      const float t2 = 2.0f - P;
       reinterpret_cast<float4*>(a.rgbd)[ray] = make_float4(C0, C1, C2, D);
       if (a.color_var) {
-        a.color_var[ray * 3 + 0] = v0;
-        a.color_var[ray * 3 + 1] = v1;
-        a.color_var[ray * 3 + 2] = v2;
+        a.color_var[ray * 3 + 0] = fmaxf(fmaf(-C0 * C0, t2, m[6]), 0.0f);
+        a.color_var[ray * 3 + 1] = fmaxf(fmaf(-C1 * C1, t2, m[7]), 0.0f);
+        a.color_var[ray * 3 + 2] = fmaxf(fmaf(-C2 * C2, t2, m[8]), 0.0f);
       }
-      if (a.depth_var) a.depth_var[ray] = vz;
+      if (a.depth_var) a.depth_var[ray] = fmaxf(fmaf(-D * D, t2, m[5]), 0.0f);
       // term prob = 1 - bg = 1 - (1 - sum w)  (run_mapping.py:774,796)
       if (a.term_prob) a.term_prob[ray] = 1.0f - (1.0f - P);
     }
@@ -210,10 +183,7 @@ int launch_composite(const NgmCompositeArgs& a, cudaStream_t stream) {
   long long blocks = (a.num_rays + kWarpsPerBlock - 1) / kWarpsPerBlock;
   const long long cap = (long long)num_sms() * 64;
   if (blocks > cap) blocks = cap;
-  if (a.num_samples <= 32 * kCacheBlocks)
-    composite_kernel<true><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, stream>>>(a);
-  else
-    composite_kernel<false><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, stream>>>(a);
+  composite_kernel<<<(unsigned)blocks, kWarpsPerBlock * 32, 0, stream>>>(a);
   return check_launch("composite_kernel");
 }
 
