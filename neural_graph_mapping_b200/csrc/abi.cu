@@ -221,7 +221,7 @@ int ngm_fieldset_knn_fwd(const NgmKnnFwdArgs* a, void* stream) {
 }
 
 int ngm_debug_tmem_bw(int warps, int iters, int mode, uint64_t* host_cycles) {
-  NGM_CHECK_ARG(warps >= 1 && warps <= 32 && iters > 0 && host_cycles, "bad args");
+  NGM_CHECK_ARG(warps >= 1 && warps <= 16 && iters > 0 && host_cycles, "bad args");
   return tmem_bw_bench(warps, iters, mode, reinterpret_cast<unsigned long long*>(host_cycles));
 }
 

@@ -5,7 +5,7 @@
 namespace ngm {
 namespace {
 
-__global__ void __launch_bounds__(1024, 1) tmem_bw_kernel(int iters, int mode, unsigned long long* out) {
+__global__ void __launch_bounds__(512, 1) tmem_bw_kernel(int iters, int mode, unsigned long long* out) {
   __shared__ uint32_t tmem_base_s;
   const int warp = threadIdx.x >> 5;
   if (warp == 0) ptx::tmem_alloc(&tmem_base_s, 512);
@@ -28,13 +28,15 @@ __global__ void __launch_bounds__(1024, 1) tmem_bw_kernel(int iters, int mode, u
     if (mode == 0) {  // load x32, wait each
       ptx::tmem_ld32(base, v);
       ptx::tc_wait_ld();
-      acc += v[it & 31];
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) acc ^= v[i];
     } else if (mode == 1) {  // two loads in flight
       uint32_t w[32];
       ptx::tmem_ld32(base, v);
       ptx::tmem_ld32(base + 32, w);
       ptx::tc_wait_ld();
-      acc += v[it & 31] + w[(it + 1) & 31];
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) acc ^= v[i] ^ w[i];
     } else if (mode == 2) {  // store x16 (half2 activations)
       ptx::tmem_st16(base, v);
       ptx::tc_wait_st();
@@ -42,7 +44,8 @@ __global__ void __launch_bounds__(1024, 1) tmem_bw_kernel(int iters, int mode, u
       uint32_t w[16];
       ptx::tmem_ld16(base, w);
       ptx::tc_wait_ld();
-      acc += w[it & 15];
+#pragma unroll
+      for (int i = 0; i < 16; i += 4) acc ^= w[i];
     }
   }
   const long long t1 = clock64();
