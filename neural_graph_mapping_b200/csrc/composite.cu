@@ -123,9 +123,12 @@ __device__ __forceinline__ SampleTerms eval_block(const RayCtx& c, int blk, floa
 // One pass per ray: per-lane partial moments over the ray's 32-sample blocks, then nine warp
 // reductions.  The variances use  Sum w (m - x)^2 = Sum w x^2 - m^2 (2 - Sum w)  (exact algebra;
 // the fp32 cancellation error is ~1e-7 of the colour / depth scale).
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) composite_kernel(NgmCompositeArgs a) {
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 5) composite_kernel(NgmCompositeArgs a) {
   const int lane = threadIdx.x & 31;
-  const long long warp0 = blockIdx.x * (long long)kWarpsPerBlock + (threadIdx.x >> 5);
+  // broadcast -> provably warp-uniform ray index, so the shuffles below are emitted without
+  // per-instruction WARPSYNC / ENDCOLLECTIVE convergence wrappers
+  const int warp_in_block = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const long long warp0 = blockIdx.x * (long long)kWarpsPerBlock + warp_in_block;
   const long long nwarps = (long long)gridDim.x * kWarpsPerBlock;
   const int S = a.num_samples;
   const bool drop_last = (a.geometry_mode == NGM_GEOM_DENSITY || a.geometry_mode == NGM_GEOM_NEUS);
