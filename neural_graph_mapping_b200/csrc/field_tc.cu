@@ -751,6 +751,16 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const TcParams p) {
 
 int nerf_octaves_supported(int o) { return o == 4 || o == 8; }
 
+// one persistent CTA per SM; NGM_TC_MAX_CTAS (tests) caps the grid so that small problems exercise the
+// multi-round / multi-segment paths of a CTA
+int tc_grid(long long total_tiles) {
+  static int cap = -1;
+  if (cap < 0) { const char* e = getenv("NGM_TC_MAX_CTAS"); cap = e ? atoi(e) : 0; }
+  long long g = num_sms();
+  if (cap > 0 && cap < g) g = cap;
+  return (int)(total_tiles < g ? total_tiles : g);
+}
+
 int tc_trace_enabled() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("NGM_TC_TRACE"); v = (e && e[0] == '1') ? 1 : 0; }
@@ -836,8 +846,7 @@ int launch_field_fwd_tc(const NgmFieldFwdArgs& a, cudaStream_t stream) {
   p.out = a.out;
   p.tiles_per_field = (a.points_per_field + 127) / 128;
   p.total_tiles = p.tiles_per_field * a.num_fields;
-  const int sms = num_sms();
-  const int grid = (int)(p.total_tiles < sms ? p.total_tiles : sms);
+  const int grid = tc_grid(p.total_tiles);
   return launch_tc<1>(p, a.field.nerf_num_octaves, tc_smem_bytes(p.im), grid, stream);
 }
 
@@ -853,8 +862,7 @@ int launch_tc_gemm_debug(const NgmFieldDesc& fd, const void* a_half, long long r
   p.out = out;
   p.tiles_per_field = (rows + 127) / 128;
   p.total_tiles = p.tiles_per_field;
-  const int sms = num_sms();
-  const int grid = (int)(p.total_tiles < sms ? p.total_tiles : sms);
+  const int grid = tc_grid(p.total_tiles);
   return launch_tc<1>(p, 8, tc_smem_bytes(p.im), grid, stream);
 }
 
@@ -909,8 +917,7 @@ int launch_render_fused_tc(const NgmRenderArgs& a, void* tc_ws, float* isd_ws, c
   p.freespace = a.freespace; p.freespace_mask = a.freespace_mask; p.tsdf = a.tsdf; p.tsdf_mask = a.tsdf_mask;
   p.tiles_per_field = (a.rays_per_field + p.rpt - 1) / p.rpt;
   p.total_tiles = p.tiles_per_field * a.num_fields;
-  const int sms = num_sms();
-  const int grid = (int)(p.total_tiles < sms ? p.total_tiles : sms);
+  const int grid = tc_grid(p.total_tiles);
   return launch_tc<0>(p, a.field.nerf_num_octaves, tc_smem_bytes(p.im), grid, stream);
 }
 

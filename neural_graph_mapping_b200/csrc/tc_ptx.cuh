@@ -81,12 +81,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // kernel's critical paths): a waiting warp costs ~4 issue slots per wake-up instead of ~13.
 __device__ __forceinline__ void mbar_wait_lean(uint64_t* bar, uint32_t parity) {
   uint32_t it = 0;
+  long long t0 = 0;
 #pragma unroll 1
   while (!mbar_try_hint(bar, parity, 0x989680u)) {
-    if (++it == 0x4000000u) {  // ~10^8 wake-ups: a protocol bug, not a slow tile
-      printf("ngm: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x,
-             smem_u32(bar), parity);
-      __trap();
+    if ((++it & 63u) == 0u) {  // a failed attempt may sleep for a long time when nothing happens: bound by the clock
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 8000000000ll) {
+        printf("ngm: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x,
+               smem_u32(bar), parity);
+        __trap();
+      }
     }
   }
 }

@@ -168,3 +168,30 @@ def test_render_fp16_vs_fp32_sizes(S, Sg):
     if Sg:
         assert p16.freespace_geometry.shape == p32.freespace_geometry.shape
         assert p16.tsdf_residuals.shape == p32.tsdf_residuals.shape
+
+
+def test_psnr_trained_field_within_0p1_db():
+    """north_star: PSNR within 0.1 dB of the reference.  Fixture: a field trained (by the oracle, CPU) on an
+    analytic sphere scene; PSNR of the reference-arithmetic render vs the analytic ground truth is stored."""
+    import neural_graph_mapping_b200 as ngm
+
+    meta, a = G.load("trained_sphere")
+    H, W = meta["image_hw"]
+    S = meta["num_samples"]
+    a = dict(a)
+    a["jitter"] = torch.rand(1, H * W, S, generator=torch.Generator().manual_seed(meta["jitter_seed"]))
+    gt = a["gt_rgb"][0].reshape(H, W, 3)
+    ref_img = a["out_rgbds"][0, :, :3].reshape(H, W, 3)
+    psnr_ref = R.psnr(ref_img, gt)
+    assert abs(psnr_ref - meta["psnr_reference_db"]) < 1e-3
+    out = {}
+    for prec in ("fp32", "fp16"):
+        p = run_vmap_case(meta, a, DEV, precision=prec)
+        img = p.rgbds[0, :, :3].cpu().reshape(H, W, 3)
+        out[prec] = (R.psnr(img, gt), R.psnr(img, ref_img), (p.rgbds[0, :, 3].cpu() - a["gt_depth"][0]).abs().mean().item())
+    print("PSNR vs gt: reference %.3f dB, fp32 %.3f dB, fp16 %.3f dB; fp16 vs reference image %.1f dB; depth L1 %s" % (
+        psnr_ref, out["fp32"][0], out["fp16"][0], out["fp16"][1], [round(out[k][2], 4) for k in out]))
+    assert abs(out["fp32"][0] - psnr_ref) < 0.01, out
+    assert abs(out["fp16"][0] - psnr_ref) < 0.1, out
+    assert out["fp16"][1] > 45.0, out
+    assert abs(out["fp16"][2] - meta["depth_l1_reference"]) < 5e-3
