@@ -263,6 +263,8 @@ int ngm_debug_tc_gemm(const float* weight, const float* bias, int n, int k, cons
 /* diagnostics: with NGM_TC_TRACE=1 in the environment, CTA 0 of every tcgen05 launch records (event, clock)
  * pairs; this copies them to HOST memory (synchronises the device); returns the event count. */
 int ngm_debug_tc_trace(uint64_t* host_out, int max_events);
+/* same without synchronising the device (reads the trace of a still-running kernel; deadlock diagnosis) */
+int ngm_debug_tc_trace_peek(uint64_t* host_out, int max_events);
 /* diagnostics: TMEM load/store micro-benchmark (the only entry point that allocates a scratch buffer itself):
  * `warps` warps per CTA issue `iters` tcgen05.ld/st (mode 0: ld.x32, 1: 2x ld.x32 in flight, 2: st.x16,
  * 3: ld.x16); writes the cycle count of CTA 0 to *host_cycles. */

@@ -111,7 +111,7 @@ class NgmKnnFwdArgs(C.Structure):
 STRUCTS = [NgmCamera, NgmFieldDesc, NgmSampleArgs, NgmFieldFwdArgs, NgmCompositeArgs, NgmRenderArgs, NgmKnnFwdArgs]
 EXPORTS = [
     "ngm_abi_version", "ngm_last_error", "ngm_struct_size", "ngm_launch_count", "ngm_sample_rays", "ngm_field_fwd", "ngm_composite",
-    "ngm_render_rays_fwd", "ngm_debug_tc_gemm", "ngm_debug_tc_trace", "ngm_debug_tmem_bw", "ngm_fieldset_knn_fwd", "ngm_fieldset_knn_workspace_bytes", "ngm_field_fwd_workspace_bytes", "ngm_render_workspace_bytes",
+    "ngm_render_rays_fwd", "ngm_debug_tc_gemm", "ngm_debug_tc_trace", "ngm_debug_tc_trace_peek", "ngm_debug_tmem_bw", "ngm_fieldset_knn_fwd", "ngm_fieldset_knn_workspace_bytes", "ngm_field_fwd_workspace_bytes", "ngm_render_workspace_bytes",
 ]
 
 if not os.path.exists(LIB_PATH):
@@ -135,6 +135,8 @@ lib.ngm_fieldset_knn_workspace_bytes.restype = C.c_int
 lib.ngm_fieldset_knn_workspace_bytes.argtypes = [C.POINTER(NgmKnnFwdArgs), C.POINTER(C.c_size_t)]
 lib.ngm_debug_tmem_bw.restype = C.c_int
 lib.ngm_debug_tmem_bw.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p]
+lib.ngm_debug_tc_trace_peek.restype = C.c_int
+lib.ngm_debug_tc_trace_peek.argtypes = [C.c_void_p, C.c_int]
 lib.ngm_debug_tc_trace.restype = C.c_int
 lib.ngm_debug_tc_trace.argtypes = [C.c_void_p, C.c_int]
 lib.ngm_debug_tc_gemm.restype = C.c_int

@@ -49,6 +49,7 @@ size_t knn_workspace_bytes(long long num_points, int num_knn, int num_fields);
 int launch_fieldset_knn(const NgmKnnFwdArgs& a, cudaStream_t stream);
 
 int tc_trace_read(unsigned long long* out, int max_events);
+int tc_trace_peek(unsigned long long* out, int max_events);
 int tmem_bw_bench(int warps, int iters, int mode, unsigned long long* host_cycles);
 
 static int validate_field(const NgmFieldDesc& fd) {
@@ -218,6 +219,11 @@ int ngm_fieldset_knn_fwd(const NgmKnnFwdArgs* a, void* stream) {
     return NGM_ERR_WORKSPACE;
   }
   return launch_fieldset_knn(*a, (cudaStream_t)stream);
+}
+
+int ngm_debug_tc_trace_peek(uint64_t* host_out, int max_events) {
+  NGM_CHECK_ARG(host_out && max_events > 0, "null args");
+  return tc_trace_peek(reinterpret_cast<unsigned long long*>(host_out), max_events);
 }
 
 int ngm_debug_tmem_bw(int warps, int iters, int mode, uint64_t* host_cycles) {

@@ -877,6 +877,26 @@ int tc_trace_read(unsigned long long* out, int max_events) {
   return (int)n;
 }
 
+// same, but WITHOUT synchronising the device: reads the trace of a kernel that is still running (or hung)
+// through a non-blocking stream -- the watchdog of tools/tc_trace.py uses it to diagnose deadlocks
+int tc_trace_peek(unsigned long long* out, int max_events) {
+  cudaStream_t st;
+  if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) return -1;
+  unsigned n = 0;
+  int rc = -1;
+  if (cudaMemcpyFromSymbolAsync(&n, g_trace_n, sizeof(n), 0, cudaMemcpyDeviceToHost, st) == cudaSuccess &&
+      cudaStreamSynchronize(st) == cudaSuccess) {
+    if (n > 16384u) n = 16384u;
+    if ((int)n > max_events) n = (unsigned)max_events;
+    if (n == 0 || (cudaMemcpyFromSymbolAsync(out, g_trace, n * sizeof(unsigned long long), 0, cudaMemcpyDeviceToHost, st) ==
+                       cudaSuccess &&
+                   cudaStreamSynchronize(st) == cudaSuccess))
+      rc = (int)n;
+  }
+  cudaStreamDestroy(st);
+  return rc;
+}
+
 int launch_neus_isd(const float* sd, const int64_t* slots, int num_fields, float* out, cudaStream_t stream);
 
 bool render_fused_tc_ok(const NgmRenderArgs& a) {
