@@ -167,7 +167,7 @@ constexpr int kMaxRaysPerTile = 16;  // Sp >= 8
 constexpr int kRayFloats = 12;       // o_local[3], dir_local[3], zscale, near, far, gt, valid, pad
 
 struct Smem {
-  uint64_t a0_ready[2];  // layer-0 A operand stored (front-end threads) + previous tile's last D read (compositor threads)
+  uint64_t a0_ready[2];  // layer-0 A operand stored (front-end group) + every slot thread past the previous tile's last layer
   uint64_t a_ready[2];   // hidden-layer A operand stored (all 256 threads of the slot)
   uint64_t d_ready[2];   // accumulator complete (tcgen05.commit)
   uint64_t w_ready;
@@ -462,7 +462,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const TcParams p) {
   if (warp == 0) ptx::tmem_alloc(&sm.tmem_base, kTmemCols);
   if (tid == 64) {
     for (int s = 0; s < 2; ++s) {
-      ptx::mbar_init(&sm.a0_ready[s], 256);
+      ptx::mbar_init(&sm.a0_ready[s], 640);  // 512 slot threads past the previous tile's last layer + 128 front-end stores
       ptx::mbar_init(&sm.a_ready[s], 512);
       ptx::mbar_init(&sm.d_ready[s], 1);
     }
@@ -657,7 +657,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const TcParams p) {
         const int step_b = real ? (L < 1 ? L : 1) : 0;         // fe_a after step 0, fe_b after step min(1, L)
         if (real && MODE == 0 && cg >= 2 && row < p.rpt && 2 * (r + 2) + fs < ntiles)  // two rounds ahead
           compute_ray_params(p, f, slot, (tile0_in_field + 2 * (r + 2) + fs) * p.rpt + row, sm.ray[fs][(r + 2) & 3][row]);
+        trace_ev(tr, ev_id(4 + cg, 0, 7, r & 15));
         if (real) ptx::named_bar_sync(kBarAll, 512);  // row data / ray parameters of round r visible to the compositors
+        trace_ev(tr, ev_id(4 + cg, 0, 8, r & 15));
         for (int l = 0; l < nsteps; ++l) {
 #pragma unroll 1
           for (int s = 0; s < 2; ++s) {
@@ -665,7 +667,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const TcParams p) {
             const bool has_next = 2 * (r + 1) + s < ntiles;
             const uint32_t d_addr = lane_base + s * kSlotCols;
             if (has_tile) {
+              trace_ev(tr, ev_id(4 + cg, s, 9, l));
               ptx::mbar_wait_lean(&sm.d_ready[s], (pd >> s) & 1u);
+              trace_ev(tr, ev_id(4 + cg, s, 10, l));
               pd ^= 1u << s;
               ptx::tc_fence_after();
               if (l < L) {
@@ -676,7 +680,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const TcParams p) {
                 ptx::tc_fence_before();
                 ptx::mbar_arrive(&sm.a_ready[s]);
                 trace_ev(tr, ev_id(2, s, 4, l));
-              } else if (cg == s) {
+              } else if (cg != s) {
+                // Every slot thread must have observed this (last-layer) phase of d_ready[s] before the next
+                // tile's layer 0 may complete, or a late thread would see the barrier two phases ahead
+                // (parity aliasing) and wait forever: all 512 threads arrive on a0_ready, not only the two
+                // duty groups.
+                if (has_next) ptx::mbar_arrive(&sm.a0_ready[s]);
+              } else {
                 // ---------- last layer of slot s: column group s owns the output / compositor ----------
                 trace_ev(tr, ev_id(2, s, 5, 0));
                 const long long tile_in_field = tile0_in_field + 2 * r + s;
@@ -727,8 +737,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const TcParams p) {
                 }
                 trace_ev(tr, ev_id(2, s, 6, 0));
               }
-            } else if (!real && cg == s) {
-              if (has_next) ptx::mbar_arrive(&sm.a0_ready[s]);  // first tile of the slot: no accumulator to drain
+            } else if (!real) {
+              if (has_next) ptx::mbar_arrive(&sm.a0_ready[s]);  // first tile of the slot: nothing to drain / observe
             }
             if (cg == 2 + s && has_next) {  // front end of slot s's tile of the next round
               if (l == 0) fe_a(s, r + 1, nring, npar);
