@@ -148,6 +148,7 @@ struct TcParams {
   RayJitter jit;
   float near_scalar, far_scalar, range_guided;
   int c2w_per_ray, S, G, St, Sp, sp_shift, rpt;
+  float inv_S;  // 1 / S (torch.linspace step)
   long long rays_per_field;
   int geometry_mode, overwrite;
   float geometry_factor, color_factor, truncation;
@@ -167,7 +168,7 @@ constexpr int kMaxRaysPerTile = 16;  // Sp >= 8
 constexpr int kRayFloats = 12;       // o_local[3], dir_local[3], zscale, near, far, gt, valid, pad
 
 struct Smem {
-  uint64_t a0_ready[2];  // layer-0 A operand stored (front-end group) + every slot thread past the previous tile's last layer
+  uint64_t a0_ready[2];  // layer-0 A operand stored (front-end half) + previous tile's last accumulator drained (compositor half)
   uint64_t a_ready[2];   // hidden-layer A operand stored (all 256 threads of the slot)
   uint64_t d_ready[2];   // accumulator complete (tcgen05.commit)
   uint64_t w_ready;
@@ -240,6 +241,19 @@ __device__ __forceinline__ void cvt16(const uint32_t* v, const uint32_t* bias2, 
 __device__ __forceinline__ void hidden_epilogue(uint32_t d_addr, uint32_t a_addr, const uint32_t* bias2, int c0, int n) {
   int c = c0;
   const int end = c0 + n;
+  for (; c + 64 <= end; c += 64) {  // two tcgen05.ld in flight: one TMEM latency instead of two
+    uint32_t v0[32], v1[32];
+    ptx::tmem_ld32(d_addr + c, v0);
+    ptx::tmem_ld32(d_addr + c + 32, v1);
+    ptx::tc_wait_ld();
+    uint32_t w[16];
+    cvt16(v0, bias2 + c / 2, w);
+    cvt16(v0 + 16, bias2 + c / 2 + 8, w + 8);
+    ptx::tmem_st16(a_addr + c / 2, w);
+    cvt16(v1, bias2 + c / 2 + 16, w);
+    cvt16(v1 + 16, bias2 + c / 2 + 24, w + 8);
+    ptx::tmem_st16(a_addr + c / 2 + 16, w);
+  }
   for (; c + 32 <= end; c += 32) {
     uint32_t v[32];
     ptx::tmem_ld32(d_addr + c, v);
@@ -299,7 +313,8 @@ __device__ __forceinline__ void compute_ray_params(const TcParams& p, long long 
   }
   out[0] = o[0]; out[1] = o[1]; out[2] = o[2];
   out[3] = dl[0]; out[4] = dl[1]; out[5] = dl[2];
-  out[6] = zs; out[7] = nr; out[8] = fr; out[9] = gt; out[10] = ok ? 1.0f : 0.0f; out[11] = 0.f;
+  out[6] = zs; out[7] = nr; out[8] = fr; out[9] = gt; out[10] = ok ? 1.0f : 0.0f;
+  out[11] = __fsub_rn(fr, nr) / (float)p.S;  // stratum width of the coarse set (camera.py:270), once per ray
 }
 
 template <int WSEG>
@@ -440,10 +455,13 @@ __device__ __forceinline__ void issue_layer(uint32_t d_addr, uint32_t a_addr, ui
 
 // Thread layout (576 threads, one CTA per SM):
 //   warp 0  : MMA issuer of slot 0 (+ weight-image loader)     warp 1 : MMA issuer of slot 1
-//   warps 2-17 : the 512 "slot threads": every hidden-layer epilogue of EITHER slot is spread over all of
-//                them (warp w: TMEM lane quadrant w % 4, column group (w-2)/4); column groups 0/1 also run
-//                the compositor of slot 0/1, column groups 2/3 the front end (sample, encode, layer-0 A
-//                operand) of slot 0/1's next tile.
+//   warps 2-9  : slot 0   (warp w: TMEM quadrant w % 4, half h = ((w-2) / 4) & 1)
+//   warps 10-17: slot 1
+// Within a slot both halves share the hidden-layer epilogues (h = 0: first column half, h = 1: second);
+// h = 1 threads additionally run the FRONT END of the slot's next tile (sample, encode, layer-0 A operand,
+// slotted into the waits for the current tile's MMAs), h = 0 threads the COMPOSITOR of the current tile.
+// (A lockstep variant in which all 16 warps share every epilogue job of both slots was measured slower --
+// 3.85 ms vs 2.83 ms per frame -- because each duty then stalls all 512 threads; profiles/README.md.)
 template <int MODE, int OCT>
 __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const TcParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -462,8 +480,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const TcParams p) {
   if (warp == 0) ptx::tmem_alloc(&sm.tmem_base, kTmemCols);
   if (tid == 64) {
     for (int s = 0; s < 2; ++s) {
-      ptx::mbar_init(&sm.a0_ready[s], 640);  // 512 slot threads past the previous tile's last layer + 128 front-end stores
-      ptx::mbar_init(&sm.a_ready[s], 512);
+      // 128 front-end stores + 128 compositor threads that drained the accumulator.  No parity aliasing on d_ready:
+      // the compositor threads arrive only after the slot-wide named barrier that follows the last-layer wait, so
+      // the next tile's layer 0 cannot complete before all 256 slot threads have observed the last-layer phase.
+      ptx::mbar_init(&sm.a0_ready[s], 256);
+      ptx::mbar_init(&sm.a_ready[s], 256);
       ptx::mbar_init(&sm.d_ready[s], 1);
     }
     ptx::mbar_init(&sm.w_ready, 1);
@@ -480,7 +501,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const TcParams p) {
 
   uint32_t w_phase = 0;
   uint32_t pa0 = 0, pa = 0;  // MMA issuer: parities of its slot's a0_ready / a_ready
-  uint32_t pd = 0;           // slot thread: parities of d_ready[0] (bit 0) and d_ready[1] (bit 1)
+  uint32_t pd = 0;           // slot thread: parity of its slot's d_ready
   const int L = p.L, W = p.W;
 
   long long t = t_begin;
@@ -529,35 +550,30 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const TcParams p) {
         }
       }
     } else {
-      // ===================== tile-slot threads (16 warps) =====================
-      // All 16 warps work on BOTH slots, in lockstep job order (slot 0 layer l, slot 1 layer l, ...):
-      // while they run slot 0's epilogue the tensor pipe runs slot 1's layer and vice versa, and an
-      // epilogue job is spread over 512 threads (32 columns each), which halves its latency.
-      //   warp w: TMEM lane quadrant q = w % 4, column group cg = (w - 2) / 4 (0..3)
-      //   extra duties: cg 0 / 1 = compositor of slot 0 / 1;  cg 2 / 3 = front end of slot 0 / 1
-      const int eg = warp - 2;
-      const int cg = eg >> 2;
-      const int qwarp = warp & 3;
+      // ===================== tile-slot threads =====================
+      const int s = (warp - 2) >> 3;
+      const int h = ((warp - 2) >> 2) & 1;  // 0: compositor half, 1: front-end half
+      const int qwarp = warp & 3;           // TMEM lane quadrant this warp may access
       const int row = qwarp * 32 + lane;
-      const uint32_t lane_base = tmem_base + ((uint32_t)(qwarp * 32) << 16);
+      const uint32_t d_addr = tmem_base + ((uint32_t)(qwarp * 32) << 16) + s * kSlotCols;
+      const uint32_t a_addr = d_addr + kACol;
       const uint32_t* bias2 = reinterpret_cast<const uint32_t*>(wsm + p.im.bias_h2_off);
       const float* bias_last = reinterpret_cast<const float*>(wsm + p.im.bias_last_off);
       const long long slot = p.field_slots ? p.field_slots[f] : f;
-      constexpr int kBarAll = 1;          // the 512 slot threads
-      const int bar_duty = 2 + cg;        // the 128 threads of this column group (its compositor / front-end duty)
-      // column split of the hidden epilogues in 16-column chunks, balanced over the four groups
-      const int nchunk = W / 16;
-      const int my_c0 = (nchunk * cg / 4) * 16, my_n = (nchunk * (cg + 1) / 4) * 16 - my_c0;
-      const int fs = cg - 2;              // slot whose front end this thread runs (cg >= 2)
-      const int tr = p.trace && lane == 0 && qwarp == 2;  // one leader thread per column group
-      const int R = (ntiles + 1) / 2;     // rounds: round r = tiles 2r (slot 0) and 2r + 1 (slot 1)
+      const int bar_slot = 1 + s;  // 256 threads of the slot
+      const int bar_half = 3 + 2 * s + h;  // the 128 threads of this half (compositor or front end)
+      // column split of the hidden epilogues: multiples of 16, h = 0 takes the (larger) first part
+      const int w0 = ((W / 16 + 1) / 2) * 16;
+      const int my_c0 = h ? w0 : 0, my_n = h ? W - w0 : w0;
+      const int tr = p.trace && lane == 0 && qwarp == 2;  // one leader thread per half
 
-      float3 fx = make_float3(0.f, 0.f, 0.f);  // sample point of this row for the next tile (fe_a -> fe_b)
+      const uint32_t a0_addr = d_addr + kStageCol;  // staging columns: layer-0 A operand of the NEXT tile
+      float3 fx = make_float3(0.f, 0.f, 0.f);        // sample point of this row for the next tile (fe_a -> fe_b)
 
-      // Front end of tile 2r + s (column group 2 + s), in two parts slotted between the epilogue jobs:
-      //   fe_a = sample point + row data,  fe_b = encoding -> staging columns -> arrive
-      auto fe_a = [&](int s, int r, int ring, int par) {
-        const long long tile_in_field = tile0_in_field + 2 * r + s;
+      // Front end of tile `ti` (h == 1 threads), in two parts that are slotted into the waits for
+      // the CURRENT tile's MMAs:  fe_a = sample point + row data,  fe_b = encoding -> staging -> arrive.
+      auto fe_a = [&](int ti, int ring, int par) {
+        const long long tile_in_field = tile0_in_field + ti;
         trace_ev(tr, ev_id(1, s, 0, 0));
         fx = make_float3(0.f, 0.f, 0.f);
         if (MODE == 1) {
@@ -600,11 +616,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const TcParams p) {
               }
               sm.sm_x[s][rit * p.Sp + pos] = dk;
             }
-            ptx::named_bar_sync(bar_duty, 128);
+            ptx::named_bar_sync(bar_half, 128);
             d = sm.sm_x[s][row];
-            ptx::named_bar_sync(bar_duty, 128);
+            ptx::named_bar_sync(bar_half, 128);
           } else if (valid) {
-            d = stratified_distance(nr, fr, k, S, p.jit.coarse(ray, k, S, St));
+            // (delta * u + linspace(0,1,S+1)[k] * (far - near)) + near with the per-ray division hoisted
+            const float lin = k < (S + 1) / 2 ? __fmul_rn(p.inv_S, (float)k)
+                                              : __fsub_rn(1.0f, __fmul_rn(p.inv_S, (float)(S - k)));
+            d = __fadd_rn(__fadd_rn(__fmul_rn(rp[11], p.jit.coarse(ray, k, S, St)), __fmul_rn(lin, __fsub_rn(fr, nr))), nr);
           }
           float z = 0.f;
           if (valid) {
@@ -615,10 +634,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const TcParams p) {
         }
         trace_ev(tr, ev_id(1, s, 1, 0));
       };
-      auto fe_b = [&](int s, int r) {
-        const uint32_t a0_addr = lane_base + s * kSlotCols + kStageCol;
+      auto fe_b = [&](int ti) {
         if (MODE == 1 && p.raw_a) {
-          const long long gp = (tile0_in_field + 2 * r + s) * 128 + row;
+          const long long gp = (tile0_in_field + ti) * 128 + row;
           const bool valid = gp < p.points_per_field;
           const long long rr = valid ? f * p.points_per_field + gp : 0;
           const uint32_t* src = reinterpret_cast<const uint32_t*>(p.raw_a + rr * p.EP);
@@ -637,59 +655,49 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const TcParams p) {
         trace_ev(tr, ev_id(1, s, 2, 0));
       };
 
-      if (MODE == 0 && cg >= 2) {  // ray parameters of the front-end slot's first two tiles (later ones two rounds ahead)
+      if (MODE == 0 && h == 1) {  // ray parameters of this slot's first two tiles (later ones two tiles ahead)
         if (row < p.rpt) {
-          if (fs < ntiles) compute_ray_params(p, f, slot, (tile0_in_field + fs) * p.rpt + row, sm.ray[fs][0][row]);
-          if (fs + 2 < ntiles) compute_ray_params(p, f, slot, (tile0_in_field + fs + 2) * p.rpt + row, sm.ray[fs][1][row]);
+          if (s < ntiles) compute_ray_params(p, f, slot, (tile0_in_field + s) * p.rpt + row, sm.ray[s][0][row]);
+          if (s + 2 < ntiles) compute_ray_params(p, f, slot, (tile0_in_field + s + 2) * p.rpt + row, sm.ray[s][1][row]);
         }
-        ptx::named_bar_sync(bar_duty, 128);
+        ptx::named_bar_sync(bar_half, 128);
       }
       ptx::mbar_wait(&sm.w_ready, w_phase);  // biases live in the image
 
-      // Round r: MLP layers of tiles 2r (slot 0) and 2r + 1 (slot 1), job by job; the front ends of round
-      // r + 1 and the compositors of round r are duties of single column groups, slotted between the jobs.
-      // Round -1 is virtual: it only runs the front ends of the first two tiles.
-      for (int r = -1; r < R; ++r) {
-        const bool real = r >= 0;
-        const int ring = r & 3, nring = (r + 1) & 3;           // ray-parameter ring slot of round r / r + 1
-        const int par = (r + 3) % 3, npar = (r + 4) % 3;       // row-data ring slot of round r / r + 1
+      // Software-pipelined tile loop.  Iteration `ti` runs the MLP layers of tile ti; the front end of the
+      // slot's next tile (ti + 2) is slotted into the waits for tile ti's MMAs (h == 1 threads: fe_a after
+      // the first epilogue, fe_b after the second), and the compositor of tile ti (h == 0 threads) runs
+      // after the last layer while the next tile's layer 0 is already on the tensor pipe.
+      // The first iteration (ti = s - 2) is virtual: it only runs the front end of the first tile.
+      int ring = 3, par = 2;  // ring slot (of 4) of the ray parameters / ring slot (of 3) of the row data of tile ti
+      for (int ti = s - 2; ti < ntiles; ti += 2) {
+        const bool real = ti >= 0;
+        const bool has_next = ti + 2 < ntiles;
+        const int nring = (ring + 1) & 3, npar = par == 2 ? 0 : par + 1;
+        const long long tile_in_field = tile0_in_field + ti;
         const int nsteps = real ? L + 1 : 1;
-        const int step_b = real ? (L < 1 ? L : 1) : 0;         // fe_a after step 0, fe_b after step min(1, L)
-        if (real && MODE == 0 && cg >= 2 && row < p.rpt && 2 * (r + 2) + fs < ntiles)  // two rounds ahead
-          compute_ray_params(p, f, slot, (tile0_in_field + 2 * (r + 2) + fs) * p.rpt + row, sm.ray[fs][(r + 2) & 3][row]);
-        trace_ev(tr, ev_id(4 + cg, 0, 7, r & 15));
-        if (real) ptx::named_bar_sync(kBarAll, 512);  // row data / ray parameters of round r visible to the compositors
-        trace_ev(tr, ev_id(4 + cg, 0, 8, r & 15));
+        const int step_b = real ? (L < 1 ? L : 1) : 0;  // fe_a at step 0, fe_b at step min(1, L)
+        if (real && MODE == 0 && h == 1 && row < p.rpt && ti + 4 < ntiles)  // off the critical path: layer 0's MMA runs now
+          compute_ray_params(p, f, slot, (tile_in_field + 4) * p.rpt + row, sm.ray[s][(ring + 2) & 3][row]);
         for (int l = 0; l < nsteps; ++l) {
-#pragma unroll 1
-          for (int s = 0; s < 2; ++s) {
-            const bool has_tile = real && 2 * r + s < ntiles;
-            const bool has_next = 2 * (r + 1) + s < ntiles;
-            const uint32_t d_addr = lane_base + s * kSlotCols;
-            if (has_tile) {
-              trace_ev(tr, ev_id(4 + cg, s, 9, l));
-              ptx::mbar_wait_lean(&sm.d_ready[s], (pd >> s) & 1u);
-              trace_ev(tr, ev_id(4 + cg, s, 10, l));
-              pd ^= 1u << s;
-              ptx::tc_fence_after();
-              if (l < L) {
-                // ---------- hidden layer l of slot s: this thread's column group ----------
-                trace_ev(tr, ev_id(2, s, 3, l));
-                if (my_n > 0) hidden_epilogue(d_addr, d_addr + kACol, bias2 + l * (W / 2), my_c0, my_n);
-                ptx::tc_wait_st();
-                ptx::tc_fence_before();
-                ptx::mbar_arrive(&sm.a_ready[s]);
-                trace_ev(tr, ev_id(2, s, 4, l));
-              } else if (cg != s) {
-                // Every slot thread must have observed this (last-layer) phase of d_ready[s] before the next
-                // tile's layer 0 may complete, or a late thread would see the barrier two phases ahead
-                // (parity aliasing) and wait forever: all 512 threads arrive on a0_ready, not only the two
-                // duty groups.
-                if (has_next) ptx::mbar_arrive(&sm.a0_ready[s]);
-              } else {
-                // ---------- last layer of slot s: column group s owns the output / compositor ----------
-                trace_ev(tr, ev_id(2, s, 5, 0));
-                const long long tile_in_field = tile0_in_field + 2 * r + s;
+          if (real) {
+            ptx::mbar_wait_lean(&sm.d_ready[s], pd);
+            pd ^= 1;
+            ptx::tc_fence_after();
+            if (l < L) {
+              // ---------- hidden layer l (both halves) ----------
+              trace_ev(tr, ev_id(1 + (h == 0), s, 3, l));
+              if (my_n > 0) hidden_epilogue(d_addr, a_addr, bias2 + l * (W / 2), my_c0, my_n);
+              ptx::tc_wait_st();
+              ptx::tc_fence_before();
+              ptx::mbar_arrive(&sm.a_ready[s]);
+              trace_ev(tr, ev_id(1 + (h == 0), s, 4, l));
+            } else {
+              // ---------- last layer ----------
+              trace_ev(tr, ev_id(1 + (h == 0), s, 5, 0));
+              // row data / ray parameters written by the front-end half are visible to the compositor half
+              ptx::named_bar_sync(bar_slot, 256);
+              if (h == 0) {
                 if (MODE == 1) {
                   const long long gp = tile_in_field * 128 + row;
                   const bool valid = gp < p.points_per_field;
@@ -726,26 +734,28 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const TcParams p) {
                   const float g = __uint_as_float(v[3]) + bias_last[3];
                   const float isd_gamma = p.neus_isd ? __ldg(p.neus_isd + f) * p.geometry_factor : 0.0f;
                   if (p.Sp >= 32)
-                    composite_rows<32>(p, sm, s, row, qwarp, lane, bar_duty, ray_global, k, valid, c0, c1, c2, g, dz.x, dz.y,
+                    composite_rows<32>(p, sm, s, row, qwarp, lane, bar_half, ray_global, k, valid, c0, c1, c2, g, dz.x, dz.y,
                                        gt, p.gt != nullptr, isd_gamma);
                   else if (p.Sp == 16)
-                    composite_rows<16>(p, sm, s, row, qwarp, lane, bar_duty, ray_global, k, valid, c0, c1, c2, g, dz.x, dz.y,
+                    composite_rows<16>(p, sm, s, row, qwarp, lane, bar_half, ray_global, k, valid, c0, c1, c2, g, dz.x, dz.y,
                                        gt, p.gt != nullptr, isd_gamma);
                   else
-                    composite_rows<8>(p, sm, s, row, qwarp, lane, bar_duty, ray_global, k, valid, c0, c1, c2, g, dz.x, dz.y,
+                    composite_rows<8>(p, sm, s, row, qwarp, lane, bar_half, ray_global, k, valid, c0, c1, c2, g, dz.x, dz.y,
                                       gt, p.gt != nullptr, isd_gamma);
                 }
                 trace_ev(tr, ev_id(2, s, 6, 0));
               }
-            } else if (!real) {
-              if (has_next) ptx::mbar_arrive(&sm.a0_ready[s]);  // first tile of the slot: nothing to drain / observe
             }
-            if (cg == 2 + s && has_next) {  // front end of slot s's tile of the next round
-              if (l == 0) fe_a(s, r + 1, nring, npar);
-              if (l == step_b) fe_b(s, r + 1);
-            }
+          } else if (h == 0) {
+            if (has_next) ptx::mbar_arrive(&sm.a0_ready[s]);  // first tile: no accumulator to drain
+          }
+          if (h == 1 && has_next) {
+            if (l == 0) fe_a(ti + 2, nring, npar);
+            if (l == step_b) fe_b(ti + 2);
           }
         }
+        ring = nring;
+        par = npar;
       }
     }
     w_phase ^= 1;
@@ -928,6 +938,7 @@ int launch_render_fused_tc(const NgmRenderArgs& a, void* tc_ws, float* isd_ws, c
   p.near_scalar = a.near_scalar; p.far_scalar = a.far_scalar; p.range_guided = a.range_guided;
   p.c2w_per_ray = a.c2w_per_ray;
   p.S = a.num_samples;
+  p.inv_S = 1.0f / (float)a.num_samples;
   p.G = a.gt ? a.num_samples_guided : 0;
   p.St = p.S + p.G;
   int Sp = 8, shift = 3;  // ray stride in rows: power of two >= max(St, 8)
