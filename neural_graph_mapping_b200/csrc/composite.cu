@@ -70,40 +70,57 @@ struct RayCtx {
   }
 };
 
-// One 32-sample block: loads, aux outputs, occupancy, scan.  `carry` = transmittance entering
-// the block, updated on exit.
-__device__ __forceinline__ SampleTerms eval_block(const RayCtx& c, int blk, float& carry) {
+struct RawSample {
+  float c0, c1, c2, g, dist, z;
+};
+
+// global loads of one 32-sample block (issued one block ahead of their use)
+template <bool PACKED>
+__device__ __forceinline__ RawSample load_block(const RayCtx& c, int blk) {
+  const NgmCompositeArgs& a = c.a;
+  const int k = blk * 32 + c.lane;
+  RawSample r{0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (k < c.S) {
+    const long long idx = c.ray * c.S + k;
+    r.dist = __ldg(a.distances + idx);
+    r.z = __ldg(a.depths + idx);
+    if (PACKED) {  // rgb + geometry of the MLP output in one 16-byte load
+      const float4 v = __ldg(reinterpret_cast<const float4*>(a.colors) + idx);
+      r.c0 = v.x; r.c1 = v.y; r.c2 = v.z; r.g = v.w;
+    } else {
+      const float* col = a.colors + idx * a.color_stride;
+      r.c0 = __ldg(col); r.c1 = __ldg(col + 1); r.c2 = __ldg(col + 2);
+      r.g = __ldg(a.geometries + idx * a.geometry_stride);
+    }
+    if (a.overwrite_behind_camera && r.z < 0.0f)
+      r.g = (a.geometry_mode == NGM_GEOM_OCCUPANCY || a.geometry_mode == NGM_GEOM_DENSITY) ? -100.0f : 1.0f;
+  }
+  return r;
+}
+
+// One 32-sample block: aux outputs, occupancy, scan.  `carry` = transmittance entering the block,
+// updated on exit.
+__device__ __forceinline__ SampleTerms eval_block(const RayCtx& c, int blk, const RawSample& r, float& carry) {
   const NgmCompositeArgs& a = c.a;
   const int k = blk * 32 + c.lane;
   SampleTerms t{0.f, 0.f, 0.f, 0.f, 0.f};
   float occ = 0.0f;
   if (k < c.S) {
     const long long idx = c.ray * c.S + k;
-    const float dist = __ldg(a.distances + idx);
-    const float z = __ldg(a.depths + idx);
-    const float g = c.geometry(k, z);
     if (a.freespace) {  // run_mapping.py:624-630
       float thr = c.has_gt ? (c.gt - a.truncation) * (c.gt != 0.0f ? 1.0f : 0.0f) : 0.0f;
-      a.freespace[idx] = g * a.truncation;
-      a.freespace_mask[idx] = (c.has_gt && dist < thr) ? 1 : 0;
+      a.freespace[idx] = r.g * a.truncation;
+      a.freespace_mask[idx] = (c.has_gt && r.dist < thr) ? 1 : 0;
     }
     if (a.tsdf) {  // run_mapping.py:632-639
-      float delta = c.gt - dist;
-      a.tsdf[idx] = g * a.truncation - delta;
+      float delta = c.gt - r.dist;
+      a.tsdf[idx] = r.g * a.truncation - delta;
       a.tsdf_mask[idx] = (c.has_gt && fabsf(delta) < a.truncation && c.gt != 0.0f) ? 1 : 0;
     }
     if (k < c.Se) {
-      occ = c.occupancy(k, g, dist);
-      t.z = z;
-      const float* col = a.colors + idx * a.color_stride;
-      if (a.color_stride == 4) {  // packed MLP output: one 16-byte load
-        const float4 v = __ldg(reinterpret_cast<const float4*>(col));
-        t.c0 = a.color_factor * v.x; t.c1 = a.color_factor * v.y; t.c2 = a.color_factor * v.z;
-      } else {
-        t.c0 = a.color_factor * __ldg(col + 0);
-        t.c1 = a.color_factor * __ldg(col + 1);
-        t.c2 = a.color_factor * __ldg(col + 2);
-      }
+      occ = c.occupancy(k, r.g, r.dist);
+      t.z = r.z;
+      t.c0 = a.color_factor * r.c0; t.c1 = a.color_factor * r.c1; t.c2 = a.color_factor * r.c2;
     }
   }
   // exclusive product scan of (1 - occ) across the warp, times carry (run_mapping.py:764-771)
@@ -120,9 +137,10 @@ __device__ __forceinline__ SampleTerms eval_block(const RayCtx& c, int blk, floa
   return t;
 }
 
-// One pass per ray: per-lane partial moments over the ray's 32-sample blocks, then nine warp
-// reductions.  The variances use  Sum w (m - x)^2 = Sum w x^2 - m^2 (2 - Sum w)  (exact algebra;
-// the fp32 cancellation error is ~1e-7 of the colour / depth scale).
+// One pass per ray: per-lane partial moments over the ray's 32-sample blocks (loads issued one block
+// ahead), then nine warp reductions.  The variances use  Sum w (m - x)^2 = Sum w x^2 - m^2 (2 - Sum w)
+// (exact algebra; the fp32 cancellation error is ~1e-7 of the colour / depth scale).
+template <bool PACKED>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, 5) composite_kernel(NgmCompositeArgs a) {
   const int lane = threadIdx.x & 31;
   // broadcast -> provably warp-uniform ray index, so the shuffles below are emitted without
@@ -141,8 +159,12 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 5) composite_kernel(NgmCo
     if (c.has_gt) c.gt = __ldg(a.gt + ray);
     float carry = 1.0f;
     float m[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    RawSample cur = load_block<PACKED>(c, 0);
     for (int b = 0; b < nblk; ++b) {
-      const SampleTerms t = eval_block(c, b, carry);
+      RawSample nxt = cur;
+      if (b + 1 < nblk) nxt = load_block<PACKED>(c, b + 1);
+      const SampleTerms t = eval_block(c, b, cur, carry);
+      cur = nxt;
       const float wz = t.w * t.z, w0 = t.w * t.c0, w1 = t.w * t.c1, w2 = t.w * t.c2;
       m[0] += t.w; m[1] += wz; m[2] += w0; m[3] += w1; m[4] += w2;
       m[5] += wz * t.z; m[6] += w0 * t.c0; m[7] += w1 * t.c1; m[8] += w2 * t.c2;
@@ -189,7 +211,10 @@ int launch_composite(const NgmCompositeArgs& a, cudaStream_t stream) {
   long long blocks = (a.num_rays + kWarpsPerBlock - 1) / kWarpsPerBlock;
   const long long cap = (long long)num_sms() * 64;
   if (blocks > cap) blocks = cap;
-  composite_kernel<<<(unsigned)blocks, kWarpsPerBlock * 32, 0, stream>>>(a);
+  const bool packed = a.color_stride == 4 && a.geometry_stride == 4 && a.geometries == a.colors + 3 &&
+                      (reinterpret_cast<uintptr_t>(a.colors) & 15) == 0;
+  if (packed) composite_kernel<true><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, stream>>>(a);
+  else composite_kernel<false><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, stream>>>(a);
   return check_launch("composite_kernel");
 }
 

@@ -241,19 +241,6 @@ __device__ __forceinline__ void cvt16(const uint32_t* v, const uint32_t* bias2, 
 __device__ __forceinline__ void hidden_epilogue(uint32_t d_addr, uint32_t a_addr, const uint32_t* bias2, int c0, int n) {
   int c = c0;
   const int end = c0 + n;
-  for (; c + 64 <= end; c += 64) {  // two tcgen05.ld in flight: one TMEM latency instead of two
-    uint32_t v0[32], v1[32];
-    ptx::tmem_ld32(d_addr + c, v0);
-    ptx::tmem_ld32(d_addr + c + 32, v1);
-    ptx::tc_wait_ld();
-    uint32_t w[16];
-    cvt16(v0, bias2 + c / 2, w);
-    cvt16(v0 + 16, bias2 + c / 2 + 8, w + 8);
-    ptx::tmem_st16(a_addr + c / 2, w);
-    cvt16(v1, bias2 + c / 2 + 16, w);
-    cvt16(v1 + 16, bias2 + c / 2 + 24, w + 8);
-    ptx::tmem_st16(a_addr + c / 2 + 16, w);
-  }
   for (; c + 32 <= end; c += 32) {
     uint32_t v[32];
     ptx::tmem_ld32(d_addr + c, v);
