@@ -414,7 +414,13 @@ __device__ __forceinline__ void composite_rows(const TcParams& p, Smem& sm, int 
   }
 }
 
-// ---- optional phase trace (diagnostics; enabled by NGM_TC_TRACE=1, block 0 only) ----------------
+// ---- optional phase trace (diagnostics, block 0 only) --------------------------------------------
+// NGM_TC_TRACE=1: low-overhead trace -- each role leader appends (event, clock) to its own ring in
+//   shared memory (one STS.64, no atomics) and block 0 dumps the rings to g_trace when it finishes.
+// NGM_TC_TRACE=2: every event goes straight to global memory with an atomic (perturbs the timing by
+//   ~1k cycles per event, but survives a hang: tools/tc_watchdog.py reads it while the kernel runs).
+constexpr int kTraceRoles = 6;   // issuer 0/1, slot 0 {compositor, front-end} half, slot 1 {...}
+constexpr int kTraceN = 1024;    // events per role (shared-memory ring: 6 x 1024 x 8 B = 48 KB)
 __device__ unsigned long long g_trace[16384];
 __device__ unsigned int g_trace_n;
 __device__ __forceinline__ void trace_ev(int on, unsigned ev) {
@@ -423,6 +429,26 @@ __device__ __forceinline__ void trace_ev(int on, unsigned ev) {
     if (i < 16384u) g_trace[i] = ((unsigned long long)ev << 48) | ((unsigned long long)clock64() & 0xFFFFFFFFFFFFull);
   }
 }
+template <bool ON>
+struct Tracer {
+  uint2* ring;  // this role's ring in shared memory, or nullptr
+  int n, slow;
+  __device__ __forceinline__ void operator()(unsigned ev) {
+    if constexpr (!ON) return;
+    if (ring) {
+      if (n < kTraceN) ring[n++] = make_uint2(ev, (unsigned)clock());
+    } else if (slow) {
+      trace_ev(1, ev);
+    }
+  }
+  __device__ __forceinline__ void dump() {
+    if constexpr (!ON) return;
+    if (!ring) return;
+    const unsigned base = atomicAdd(&g_trace_n, (unsigned)n);
+    for (int i = 0; i < n && base + i < 16384u; ++i)
+      g_trace[base + i] = ((unsigned long long)ring[i].x << 48) | (unsigned long long)ring[i].y;
+  }
+};
 // event id = role(4b: 0 issuer, 1 front-end thread, 2 compositor thread) | slot(1b) | phase(4b) | layer(4b)
 __device__ __forceinline__ unsigned ev_id(int role, int slot, int phase, int layer) {
   return (unsigned)((role << 12) | (slot << 8) | (phase << 4) | layer);
@@ -449,7 +475,7 @@ __device__ __forceinline__ void issue_layer(uint32_t d_addr, uint32_t a_addr, ui
 // slotted into the waits for the current tile's MMAs), h = 0 threads the COMPOSITOR of the current tile.
 // (A lockstep variant in which all 16 warps share every epilogue job of both slots was measured slower --
 // 3.85 ms vs 2.83 ms per frame -- because each duty then stalls all 512 threads; profiles/README.md.)
-template <int MODE, int OCT>
+template <int MODE, int OCT, bool TRACE>
 __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const TcParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   // weights image first (1024-B aligned for SWIZZLE_128B), bookkeeping after it; plain pointer
@@ -458,6 +484,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const TcParams p) {
   uint8_t* wsm = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
   Smem& sm = *reinterpret_cast<Smem*>(wsm + (p.im.total_bytes + 127) / 128 * 128);
   const uint32_t wsm_addr = ptx::smem_u32(wsm);
+  uint2* const trace_rings = reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(&sm) + (sizeof(Smem) + 15) / 16 * 16);
 
   // warp index via broadcast: provably warp-uniform, so role branches and the shuffles inside them are
   // compiled as uniform control flow (no WARPSYNC / ENDCOLLECTIVE wrappers)
@@ -491,6 +518,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const TcParams p) {
   uint32_t pd = 0;           // slot thread: parity of its slot's d_ready
   const int L = p.L, W = p.W;
 
+  Tracer<TRACE> tev{nullptr, 0, 0};
+  auto tev_role = [&](int role, bool leader) {  // called once per field segment; keeps the ring position
+    if constexpr (!TRACE) return;
+    if (p.trace == 1 && blockIdx.x == 0 && leader) tev.ring = trace_rings + role * kTraceN;
+    tev.slow = p.trace == 2 && blockIdx.x == 0 && leader;
+  };
+
   long long t = t_begin;
   while (t < t_end) {
     const long long f = t / p.tiles_per_field;
@@ -512,6 +546,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const TcParams p) {
     if (warp < 2) {
       // ===================== MMA issuer of slot `warp` =====================
       const int s = warp;
+      tev_role(s, lane == 0);
       ptx::mbar_wait(&sm.w_ready, w_phase);
       const int my_tiles = s == 0 ? (ntiles + 1) / 2 : ntiles / 2;
       // broadcast -> provably warp-uniform operands (uniform registers, no per-lane waterfall)
@@ -524,7 +559,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const TcParams p) {
           if (l == 0) { ptx::mbar_wait_lean(&sm.a0_ready[s], pa0); pa0 ^= 1; }
           else        { ptx::mbar_wait_lean(&sm.a_ready[s], pa);   pa ^= 1; }
           ptx::tc_fence_after();
-          trace_ev(p.trace && lane == 0, ev_id(0, s, 0, l));
+          tev(ev_id(0, s, 0, l));
           const TcLayer y = p.im.layer[l];
           const uint64_t desc0 = ptx::make_smem_desc_sw128(wsm_u + y.off);
           const uint32_t idesc = ptx::make_idesc_f16(y.n_pad);
@@ -533,7 +568,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const TcParams p) {
             ptx::mma_commit(&sm.d_ready[s]);
           }
           __syncwarp();
-          trace_ev(p.trace && lane == 0, ev_id(0, s, 1, l));
+          tev(ev_id(0, s, 1, l));
         }
       }
     } else {
@@ -552,7 +587,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const TcParams p) {
       // column split of the hidden epilogues: multiples of 16, h = 0 takes the (larger) first part
       const int w0 = ((W / 16 + 1) / 2) * 16;
       const int my_c0 = h ? w0 : 0, my_n = h ? W - w0 : w0;
-      const int tr = p.trace && lane == 0 && qwarp == 2;  // one leader thread per half
+      tev_role(2 + 2 * s + h, lane == 0 && qwarp == 2);  // one leader thread per half
 
       const uint32_t a0_addr = d_addr + kStageCol;  // staging columns: layer-0 A operand of the NEXT tile
       float3 fx = make_float3(0.f, 0.f, 0.f);        // sample point of this row for the next tile (fe_a -> fe_b)
@@ -561,7 +596,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const TcParams p) {
       // the CURRENT tile's MMAs:  fe_a = sample point + row data,  fe_b = encoding -> staging -> arrive.
       auto fe_a = [&](int ti, int ring, int par) {
         const long long tile_in_field = tile0_in_field + ti;
-        trace_ev(tr, ev_id(1, s, 0, 0));
+        tev(ev_id(1, s, 0, 0));
         fx = make_float3(0.f, 0.f, 0.f);
         if (MODE == 1) {
           const long long gp = tile_in_field * 128 + row;
@@ -619,7 +654,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const TcParams p) {
           }
           *reinterpret_cast<float2*>(sm.rowdata[s][par][row]) = make_float2(d, z);
         }
-        trace_ev(tr, ev_id(1, s, 1, 0));
+        tev(ev_id(1, s, 1, 0));
       };
       auto fe_b = [&](int ti) {
         if (MODE == 1 && p.raw_a) {
@@ -639,7 +674,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const TcParams p) {
         ptx::tc_wait_st();
         ptx::tc_fence_before();
         ptx::mbar_arrive(&sm.a0_ready[s]);
-        trace_ev(tr, ev_id(1, s, 2, 0));
+        tev(ev_id(1, s, 2, 0));
       };
 
       if (MODE == 0 && h == 1) {  // ray parameters of this slot's first two tiles (later ones two tiles ahead)
@@ -673,15 +708,15 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const TcParams p) {
             ptx::tc_fence_after();
             if (l < L) {
               // ---------- hidden layer l (both halves) ----------
-              trace_ev(tr, ev_id(1 + (h == 0), s, 3, l));
+              tev(ev_id(1 + (h == 0), s, 3, l));
               if (my_n > 0) hidden_epilogue(d_addr, a_addr, bias2 + l * (W / 2), my_c0, my_n);
               ptx::tc_wait_st();
               ptx::tc_fence_before();
               ptx::mbar_arrive(&sm.a_ready[s]);
-              trace_ev(tr, ev_id(1 + (h == 0), s, 4, l));
+              tev(ev_id(1 + (h == 0), s, 4, l));
             } else {
               // ---------- last layer ----------
-              trace_ev(tr, ev_id(1 + (h == 0), s, 5, 0));
+              tev(ev_id(1 + (h == 0), s, 5, 0));
               // row data / ray parameters written by the front-end half are visible to the compositor half
               ptx::named_bar_sync(bar_slot, 256);
               if (h == 0) {
@@ -730,7 +765,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const TcParams p) {
                     composite_rows<8>(p, sm, s, row, qwarp, lane, bar_half, ray_global, k, valid, c0, c1, c2, g, dz.x, dz.y,
                                       gt, p.gt != nullptr, isd_gamma);
                 }
-                trace_ev(tr, ev_id(2, s, 6, 0));
+                tev(ev_id(2, s, 6, 0));
               }
             }
           } else if (h == 0) {
@@ -754,6 +789,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const TcParams p) {
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 0) ptx::tmem_dealloc(tmem_base, kTmemCols);
+  tev.dump();
 }
 
 int nerf_octaves_supported(int o) { return o == 4 || o == 8; }
@@ -787,9 +823,11 @@ int launch_tc(const TcParams& p_in, int octaves, size_t smem, int grid, cudaStre
     kernel<<<grid, kThreads, smem, stream>>>(p);
     return check_launch("tc_kernel");
   };
-  switch (octaves) {
-    case 4: return go(tc_kernel<MODE, 4>);
-    case 8: return go(tc_kernel<MODE, 8>);
+  switch (octaves * 2 + (p.trace ? 1 : 0)) {
+    case 8: return go(tc_kernel<MODE, 4, false>);
+    case 9: return go(tc_kernel<MODE, 4, true>);
+    case 16: return go(tc_kernel<MODE, 8, false>);
+    case 17: return go(tc_kernel<MODE, 8, true>);
     default: set_error("tcgen05 path: unsupported num_octaves %d", octaves); return NGM_ERR_UNSUPPORTED;
   }
 }
@@ -819,7 +857,8 @@ int fill_common(TcParams& p, const NgmFieldDesc& fd, int num_fields, const float
 
 // >= 120 KB so that exactly one CTA (one 512-column TMEM allocation) is resident per SM
 size_t tc_smem_bytes(const TcImage& im) {
-  const size_t need = 1024 + (im.total_bytes + 127) / 128 * 128 + sizeof(Smem) + 128;
+  const size_t need = 1024 + (im.total_bytes + 127) / 128 * 128 + sizeof(Smem) + 128 +
+                      (tc_trace_enabled() == 1 ? (size_t)kTraceRoles * kTraceN * sizeof(uint2) : 0);
   return need < 120 * 1024 ? 120 * 1024 : need;
 }
 

@@ -127,6 +127,42 @@ def test_quadrature_sizes_vs_oracle(S):
             _close(o, r, 1e-5, 5e-5, f"S={S} {mode}/{nm}")
 
 
+@pytest.mark.parametrize("S", [4, 8, 12, 64, 100])
+@pytest.mark.parametrize("overwrite", [False, True])
+def test_composite_staged_kernel(S, overwrite, monkeypatch):
+    """Packed (N,S,4) MLP output takes the thread-per-ray staged kernel: against the oracle's _quadrature
+    (behind-camera overwrite applied on the host, run_mapping.py:614-622) and against the general kernel."""
+    from neural_graph_mapping_b200 import renderer
+
+    g = torch.Generator().manual_seed(100 + S)
+    N = 1000 + S  # not a multiple of 32: partial last tile
+    packed = torch.cat([torch.rand(N, S, 3, generator=g), torch.randn(N, S, 1, generator=g) * 0.2], -1)
+    dist, _ = torch.sort(torch.rand(N, S, generator=g) * 4, dim=-1)
+    depth = dist * 0.9
+    if overwrite:
+        depth = depth - 0.5  # some samples behind the camera
+    isd = torch.rand(4, generator=g) + 0.5
+    pk, dd, zz = packed.to(DEV), dist.to(DEV), depth.to(DEV)
+    for mode, gf in [("nrgbd", 20.0), ("occupancy", 2.0), ("density", 4.0), ("neus", 3.0)]:
+        geom = packed[..., 3].clone()
+        if overwrite:
+            geom[depth < 0] = -100.0 if mode in ("occupancy", "density") else 1.0
+        rays_per = (N + 3) // 4
+        isds = isd.repeat_interleave(rays_per)[:N, None] if mode == "neus" else None
+        ref = R.quadrature(packed[..., :3], geom, dist, depth, isds, mode, gf)
+        kw = dict(color_stride=4, geometry_stride=4, overwrite_behind_camera=overwrite,
+                  neus_isd=isd.to(DEV) if mode == "neus" else None, rays_per_isd=rays_per)
+        out = renderer.composite(pk, pk[..., 3], dd, zz, mode, gf, **kw)
+        monkeypatch.setenv("NGM_COMPOSITE_STAGED", "0")
+        gen = renderer.composite(pk, pk[..., 3], dd, zz, mode, gf, **kw)
+        monkeypatch.delenv("NGM_COMPOSITE_STAGED")
+        got = (out[0][:, :3], out[0][:, 3], out[1], out[2], out[3])
+        old = (gen[0][:, :3], gen[0][:, 3], gen[1], gen[2], gen[3])
+        for nm, o, r, q in zip(["colors", "depths", "color_vars", "depth_vars", "term"], got, ref, old):
+            _close(o, r, 1e-5, 5e-5, f"staged S={S} {mode}/{nm}")
+            _close(o, q.cpu(), 1e-5, 5e-5, f"staged vs general S={S} {mode}/{nm}")
+
+
 # ---------------------------------------------------------------- field evaluation (a6, a8-a11, a16)
 def test_fields_forward_golden():
     """NeuralField.forward for every in-tree encoding and skip mode vs the reference's outputs."""

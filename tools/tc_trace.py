@@ -61,3 +61,11 @@ for k in sorted(dur):
 t0, t1 = ev[0][0], ev[-1][0]
 tiles = sum(1 for _, e in ev if (e >> 12) == 2 and ((e >> 4) & 15) == 6)
 print(f"CTA 0: {tiles} tiles in {t1 - t0} cycles -> {(t1 - t0) / max(tiles, 1):.0f} cycles/tile (both slots)")
+# raw timeline of a window in the middle of the trace (relative cycles), for reading the overlap by eye
+mid = len(ev) // 2
+base = ev[mid][0] if ev else 0
+print("-- timeline (cycle, role/slot, phase, layer)")
+for clk, e in ev[mid:mid + 260]:
+    role, slot, phase, layer = e >> 12, (e >> 8) & 1, (e >> 4) & 15, e & 15
+    print(f"{clk - base:8d}  {'  ' * (2 * slot + (role != 0) + (role == 1))}{'I' if role == 0 else ('F' if role == 1 else 'C')}{slot} "
+          f"{names[(role, phase)].split(': ')[-1]} L{layer}")
