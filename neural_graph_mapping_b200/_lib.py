@@ -12,7 +12,8 @@ import os
 import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libngm_b200.so")
+# NGM_B200_LIB: load another build of the same library (A/B timing of kernel variants on one GPU box)
+LIB_PATH = os.environ.get("NGM_B200_LIB") or os.path.join(_PKG, "libngm_b200.so")
 
 NGM_ABI_VERSION = 1
 NGM_MAX_LINEARS = 9

@@ -179,7 +179,8 @@ struct Smem {
   float sm_x[2][128];      // per slot: front end, depth-guided merge exchange
   float sm_d[2][128];      // per slot: compositor, sample distance (density deltas)
   float sm_g[2][128];      // per slot: geometry after the behind-camera overwrite (neus neighbour)
-  float sm_part[2][2][4][12];  // per slot, per exchange step, per quadrant: scan tails / partial sums
+  float sm_part[2][16][12];  // per slot, per segment (128 / wseg <= 16): 9 partial moments + transmittance leaving the segment
+  float comp[2][8][128];     // per slot: deferred compositor inputs of the previous tile {c0,c1,c2,g,d,z,gt,ray_ok} per row
 };
 
 __device__ __forceinline__ float fast_sigmoid(float x) { return __frcp_rn(1.0f + __expf(-x)); }
@@ -260,11 +261,6 @@ __device__ __forceinline__ void hidden_epilogue(uint32_t d_addr, uint32_t a_addr
   }
 }
 
-__device__ __forceinline__ float seg_sum(float v, int width) {
-  for (int o = width >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-
 // Per-ray quantities of the fused renderer, computed once per ray (two tiles ahead) instead of per
 // sample: the sample point in scaled field-local coordinates is o + d * dir (algebraically the
 // reference's  scale(q^-1 (R (dir d) + t - c)), run_mapping.py:547 + models.py:331-339).
@@ -304,28 +300,35 @@ __device__ __forceinline__ void compute_ray_params(const TcParams& p, long long 
   out[11] = __fsub_rn(fr, nr) / (float)p.S;  // stratum width of the coarse set (camera.py:270), once per ray
 }
 
-template <int WSEG>
-__device__ __forceinline__ float seg_sum(float v) {
-#pragma unroll
-  for (int o = WSEG >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-
-// ---- compositor on one tile slot (the 128 h == 0 threads, rows with ray stride Sp) ----------------
-// ngm/run_mapping.py:610-639, 709-799.  `valid` = this row is a real sample of a real ray.
-// WSEG = min(Sp, 32): lanes of one ray inside a warp.  Rays of 64 / 128 rows span 2 / 4 warps and
-// exchange the scan tail and the partial moments through shared memory (two named barriers).
-// The variances use Sum w (m - x)^2 = Sum w x^2 - m^2 (2 - Sum w), so one reduction pass suffices.
-template <int WSEG>
-__device__ __forceinline__ void composite_rows(const TcParams& p, Smem& sm, int s, int row, int qwarp, int lane, int barrier_id,
-                                               long long ray_global, int k, bool valid, float c0, float c1, float c2, float g,
-                                               float d, float z, float gt, bool has_gt, float isd_gamma) {
-  const int Sp = p.Sp, St = p.St;
+// ---- compositor of one tile slot (the 128 h == 0 threads, one row each, rows of a ray Sp apart) ----
+// ngm/run_mapping.py:610-639, 709-799.  The compositor of tile t is DEFERRED: when the last layer of
+// tile t completes, the h == 0 threads only pull their row's four outputs out of TMEM into shared
+// memory (Smem::comp) and go straight on to the next tile's hidden-layer epilogues; the arithmetic runs
+// in two stages slotted into the waits for the next tile's MMAs (stage 1 after the first hidden
+// epilogue, stage 2 after the second), exactly like the front end on the other half of the slot.
+//   stage 1: occupancy, segmented product scan (transmittance relative to the segment start), the nine
+//            weighted moments, a transposed segmented reduction (8 values in 4+2+1(+log) shuffles
+//            instead of 8 x log), partial results -> shared memory
+//   stage 2: one named barrier, the k == 0 thread of every ray chains its ray's segments
+//            (moments are linear in the transmittance entering a segment) and stores the ray.
+// wseg = min(Sp, 32) = lanes of one ray inside a warp; rays of 64 / 128 rows span 2 / 4 segments.
+// The variances use Sum w (m - x)^2 = Sum w x^2 - m^2 (2 - Sum w): one reduction pass suffices.
+__device__ __forceinline__ void comp_stage1(const TcParams& p, Smem& sm, int s, int row, int lane, int barrier_id, int wseg,
+                                            long long f, long long tile_in_field) {
+  const int St = p.St;
   const int mode = p.geometry_mode;
   const bool drop_last = (mode == NGM_GEOM_DENSITY || mode == NGM_GEOM_NEUS);
   const int Se = drop_last ? St - 1 : St;
+  const int k = row & (p.Sp - 1);
+  const float c0 = sm.comp[s][0][row], c1 = sm.comp[s][1][row], c2 = sm.comp[s][2][row];
+  float g = sm.comp[s][3][row];
+  const float d = sm.comp[s][4][row], z = sm.comp[s][5][row], gt = sm.comp[s][6][row];
+  const bool ray_ok = sm.comp[s][7][row] != 0.0f;
+  const bool valid = ray_ok && k < St;
+  const bool has_gt = p.gt != nullptr;
   if (p.overwrite && z < 0.0f) g = (mode == NGM_GEOM_OCCUPANCY || mode == NGM_GEOM_DENSITY) ? -100.0f : 1.0f;
   if (valid && (p.freespace || p.tsdf)) {
+    const long long ray_global = f * p.rays_per_field + tile_in_field * p.rpt + (row >> p.sp_shift);
     const long long idx = ray_global * St + k;
     if (p.freespace) {
       const float thr = has_gt ? (gt - p.truncation) * (gt != 0.0f ? 1.0f : 0.0f) : 0.0f;
@@ -348,6 +351,7 @@ __device__ __forceinline__ void composite_rows(const TcParams& p, Smem& sm, int 
         const float delta = sm.sm_d[s][row + 1] - d;
         occ = 1.0f - __expf(-delta * fmaxf(g, 0.0f));
       } else {
+        const float isd_gamma = __ldg(p.neus_isd + f) * p.geometry_factor;
         const float t0 = fast_sigmoid(isd_gamma * g), t1 = fast_sigmoid(isd_gamma * sm.sm_g[s][row + 1]);
         occ = fmaxf(__fdividef(t0 - t1, t0 + 1e-5f), 0.0f);
       }
@@ -361,48 +365,67 @@ __device__ __forceinline__ void composite_rows(const TcParams& p, Smem& sm, int 
       occ = fast_sigmoid(p.geometry_factor * g);
     }
   }
-  // exclusive product scan of (1 - occ) along the ray
+  // inclusive product scan of (1 - occ) inside the segment
+  const int ls = lane & (wseg - 1);
   float incl = 1.0f - occ;
-#pragma unroll
-  for (int o = 1; o < WSEG; o <<= 1) {
-    const float n = __shfl_up_sync(0xffffffffu, incl, o, WSEG);
-    if ((lane & (WSEG - 1)) >= o) incl *= n;
+  for (int o = 1; o < wseg; o <<= 1) {
+    const float n = __shfl_up_sync(0xffffffffu, incl, o, wseg);
+    if (ls >= o) incl *= n;
   }
-  float excl = __shfl_up_sync(0xffffffffu, incl, 1, WSEG);
-  if ((lane & (WSEG - 1)) == 0) excl = 1.0f;
-  const int wpr = Sp >> 5;  // warps per ray (0 or 1: the ray lives inside one warp)
-  const int first = wpr > 1 ? (qwarp & ~(wpr - 1)) : qwarp;
-  if (WSEG == 32 && wpr > 1) {
-    if (lane == 31) sm.sm_part[s][0][qwarp][0] = incl;
-    ptx::named_bar_sync(barrier_id, 128);
+  float excl = __shfl_up_sync(0xffffffffu, incl, 1, wseg);
+  if (ls == 0) excl = 1.0f;
+  const float wgt = occ * excl;  // weight relative to the transmittance entering this segment
+  // transposed reduction of the 8 moments: halve the value set while folding the three top lane bits
+  const int h1 = wseg >> 1, h2 = wseg >> 2, h3 = wseg >> 3;
+  const bool b1 = (lane & h1) != 0, b2 = (lane & h2) != 0, b3 = (lane & h3) != 0;
+  float v[8];
+  v[0] = wgt * z; v[1] = wgt * c0; v[2] = wgt * c1; v[3] = wgt * c2;
+  v[4] = v[0] * z; v[5] = v[1] * c0; v[6] = v[2] * c1; v[7] = v[3] * c2;
+  float a4[4], a2[2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float send = b1 ? v[i] : v[i + 4], keep = b1 ? v[i + 4] : v[i];
+    a4[i] = keep + __shfl_xor_sync(0xffffffffu, send, h1);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float send = b2 ? a4[i] : a4[i + 2], keep = b2 ? a4[i + 2] : a4[i];
+    a2[i] = keep + __shfl_xor_sync(0xffffffffu, send, h2);
+  }
+  float r8 = (b3 ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, b3 ? a2[0] : a2[1], h3);
+  float w0 = wgt;
+  w0 += __shfl_xor_sync(0xffffffffu, w0, h1);
+  w0 += __shfl_xor_sync(0xffffffffu, w0, h2);
+  w0 += __shfl_xor_sync(0xffffffffu, w0, h3);
+  for (int o = wseg >> 4; o > 0; o >>= 1) {
+    r8 += __shfl_xor_sync(0xffffffffu, r8, o);
+    w0 += __shfl_xor_sync(0xffffffffu, w0, o);
+  }
+  // partials of this segment: [0] Sum w, [1] Sum w z, [2..4] Sum w c, [5] Sum w z^2, [6..8] Sum w c^2, [9] transmittance out
+  float* part = sm.sm_part[s][row >> (p.sp_shift < 5 ? p.sp_shift : 5)];
+  if ((lane & (h3 - 1)) == 0) part[1 + (b1 ? 4 : 0) + (b2 ? 2 : 0) + (b3 ? 1 : 0)] = r8;
+  if (ls == 0) part[0] = w0;
+  if (ls == wseg - 1) part[9] = incl;
+}
+
+__device__ __forceinline__ void comp_stage2(const TcParams& p, Smem& sm, int s, int row, int barrier_id, long long f,
+                                            long long tile_in_field) {
+  ptx::named_bar_sync(barrier_id, 128);
+  const int k = row & (p.Sp - 1);
+  if (k == 0 && sm.comp[s][7][row] != 0.0f) {
+    const int nseg = p.Sp > 32 ? p.Sp >> 5 : 1;
+    const int sg0 = row >> (p.sp_shift < 5 ? p.sp_shift : 5);
+    float m[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     float carry = 1.0f;
-    for (int w = first; w < qwarp; ++w) carry *= sm.sm_part[s][0][w][0];
-    excl *= carry;
-  }
-  const float wgt = occ * excl;
-  float m[9];
-  m[0] = wgt;        m[1] = wgt * z;    m[2] = wgt * c0;   m[3] = wgt * c1;   m[4] = wgt * c2;
-  m[5] = m[1] * z;   m[6] = m[2] * c0;  m[7] = m[3] * c1;  m[8] = m[4] * c2;
+    for (int w = 0; w < nseg; ++w) {
+      const float* q = sm.sm_part[s][sg0 + w];
 #pragma unroll
-  for (int i = 0; i < 9; ++i) m[i] = seg_sum<WSEG>(m[i]);
-  if (WSEG == 32 && wpr > 1) {
-    if (lane == 0) {
-      float* q = sm.sm_part[s][1][qwarp];
-#pragma unroll
-      for (int i = 0; i < 9; ++i) q[i] = m[i];
+      for (int i = 0; i < 9; ++i) m[i] = fmaf(carry, q[i], m[i]);
+      carry *= q[9];
     }
-    ptx::named_bar_sync(barrier_id, 128);
-#pragma unroll
-    for (int i = 0; i < 9; ++i) m[i] = 0.0f;
-    for (int w = first; w < first + wpr; ++w) {
-      const float* q = sm.sm_part[s][1][w];
-#pragma unroll
-      for (int i = 0; i < 9; ++i) m[i] += q[i];
-    }
-  }
-  if (k == 0 && ray_global >= 0) {
     const float P = m[0], D = m[1], C0 = m[2], C1 = m[3], C2 = m[4];
     const float t2 = 2.0f - P;
+    const long long ray_global = f * p.rays_per_field + tile_in_field * p.rpt + (row >> p.sp_shift);
     reinterpret_cast<float4*>(p.rgbd)[ray_global] = make_float4(C0, C1, C2, D);
     if (p.color_var) {
       p.color_var[ray_global * 3 + 0] = fmaxf(fmaf(-C0 * C0, t2, m[6]), 0.0f);
@@ -692,8 +715,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const TcParams p) {
       // after the last layer while the next tile's layer 0 is already on the tensor pipe.
       // The first iteration (ti = s - 2) is virtual: it only runs the front end of the first tile.
       int ring = 3, par = 2;  // ring slot (of 4) of the ray parameters / ring slot (of 3) of the row data of tile ti
-      for (int ti = s - 2; ti < ntiles; ti += 2) {
-        const bool real = ti >= 0;
+      int comp_pending = 0;   // h == 0: 1 = inputs of the previous tile parked in sm.comp, 2 = its stage 1 done
+      long long comp_tile = 0;
+      const int wseg = p.Sp >= 32 ? 32 : p.Sp;
+      // one trailing virtual iteration per slot drains the compositor of the slot's last tile
+      for (int ti = s - 2; ti < ntiles || comp_pending; ti += 2) {
+        const bool real = ti >= 0 && ti < ntiles;
         const bool has_next = ti + 2 < ntiles;
         const int nring = (ring + 1) & 3, npar = par == 2 ? 0 : par + 1;
         const long long tile_in_field = tile0_in_field + ti;
@@ -740,32 +767,23 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const TcParams p) {
                   uint32_t v[4];
                   ptx::tmem_ld4(d_addr, v);
                   const int rit = row >> p.sp_shift;
-                  const int k = row & (p.Sp - 1);
                   const float* rp = sm.ray[s][ring][rit];
-                  const bool ray_ok = rp[10] != 0.0f;
-                  const float gt = rp[9];
                   const float2 dz = *reinterpret_cast<const float2*>(sm.rowdata[s][par][row]);
+                  sm.comp[s][4][row] = dz.x;
+                  sm.comp[s][5][row] = dz.y;
+                  sm.comp[s][6][row] = rp[9];
+                  sm.comp[s][7][row] = rp[10];
                   ptx::tc_wait_ld();
                   ptx::tc_fence_before();
                   if (has_next) ptx::mbar_arrive(&sm.a0_ready[s]);  // the next layer-0 MMA may overwrite the accumulator
-                  const long long ray_global = ray_ok ? f * p.rays_per_field + tile_in_field * p.rpt + rit : -1;
-                  const bool valid = ray_ok && k < p.St;
-                  const float c0 = p.color_factor * (__uint_as_float(v[0]) + bias_last[0]);
-                  const float c1 = p.color_factor * (__uint_as_float(v[1]) + bias_last[1]);
-                  const float c2 = p.color_factor * (__uint_as_float(v[2]) + bias_last[2]);
-                  const float g = __uint_as_float(v[3]) + bias_last[3];
-                  const float isd_gamma = p.neus_isd ? __ldg(p.neus_isd + f) * p.geometry_factor : 0.0f;
-                  if (p.Sp >= 32)
-                    composite_rows<32>(p, sm, s, row, qwarp, lane, bar_half, ray_global, k, valid, c0, c1, c2, g, dz.x, dz.y,
-                                       gt, p.gt != nullptr, isd_gamma);
-                  else if (p.Sp == 16)
-                    composite_rows<16>(p, sm, s, row, qwarp, lane, bar_half, ray_global, k, valid, c0, c1, c2, g, dz.x, dz.y,
-                                       gt, p.gt != nullptr, isd_gamma);
-                  else
-                    composite_rows<8>(p, sm, s, row, qwarp, lane, bar_half, ray_global, k, valid, c0, c1, c2, g, dz.x, dz.y,
-                                      gt, p.gt != nullptr, isd_gamma);
+                  sm.comp[s][0][row] = p.color_factor * (__uint_as_float(v[0]) + bias_last[0]);
+                  sm.comp[s][1][row] = p.color_factor * (__uint_as_float(v[1]) + bias_last[1]);
+                  sm.comp[s][2][row] = p.color_factor * (__uint_as_float(v[2]) + bias_last[2]);
+                  sm.comp[s][3][row] = __uint_as_float(v[3]) + bias_last[3];
+                  comp_pending = 1;
+                  comp_tile = tile_in_field;
                 }
-                tev(ev_id(2, s, 6, 0));
+                tev(ev_id(2, s, 7, 0));
               }
             }
           } else if (h == 0) {
@@ -774,6 +792,18 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const TcParams p) {
           if (h == 1 && has_next) {
             if (l == 0) fe_a(ti + 2, nring, npar);
             if (l == step_b) fe_b(ti + 2);
+          }
+          // deferred compositor of the slot's previous tile, in the wait for this tile's next MMA
+          if (MODE == 0 && h == 0 && comp_pending && l < 2 && (l < L || !real)) {
+            if (l == 0) {
+              comp_stage1(p, sm, s, row, lane, bar_half, wseg, f, comp_tile);
+              comp_pending = 2;
+            }
+            if (l == 1 || L == 1 || !real) {
+              comp_stage2(p, sm, s, row, bar_half, f, comp_tile);
+              comp_pending = 0;
+              tev(ev_id(2, s, 6, 0));
+            }
           }
         }
         ring = nring;
@@ -948,7 +978,9 @@ int launch_neus_isd(const float* sd, const int64_t* slots, int num_fields, float
 bool render_fused_tc_ok(const NgmRenderArgs& a) {
   const int St = a.num_samples + (a.gt ? a.num_samples_guided : 0);
   const char* why;
-  return a.precision == NGM_PREC_FP16 && St <= 128 && a.field.dim_out == 4 && field_tc_supported(a.field, &why);
+  // num_layers >= 1: the deferred compositor runs in the waits of the hidden layers
+  return a.precision == NGM_PREC_FP16 && St <= 128 && a.field.dim_out == 4 && a.field.num_layers >= 1 &&
+         field_tc_supported(a.field, &why);
 }
 
 int launch_render_fused_tc(const NgmRenderArgs& a, void* tc_ws, float* isd_ws, cudaStream_t stream) {

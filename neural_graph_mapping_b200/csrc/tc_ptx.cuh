@@ -96,6 +96,25 @@ __device__ __forceinline__ void mbar_wait_lean(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Pure spin on test_wait (no hardware suspend): lowest wake-up latency, burns issue slots -- only for
+// the two MMA-issuer warps, whose wake-up sits on the kernel's critical path.
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+  uint32_t it = 0;
+  long long t0 = 0;
+#pragma unroll 1
+  while (!mbar_test(bar, parity)) {
+    if ((++it & 0xFFFFu) == 0u) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 8000000000ll) {
+        printf("ngm: mbarrier spin wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x,
+               smem_u32(bar), parity);
+        __trap();
+      }
+    }
+  }
+}
+
 // one lane of the (converged) warp
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;

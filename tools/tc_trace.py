@@ -30,7 +30,7 @@ n = _lib.lib.ngm_debug_tc_trace(buf, 16384)
 ev = sorted(((buf[i] & 0xFFFFFFFFFFFF), buf[i] >> 48) for i in range(n))
 print("events", n)
 PH = {0: "FE start", 1: "sample ready (pre-encode)", 2: "A0 stored+arrived", 3: "d_ready (hidden)",
-      4: "hidden epilogue done", 5: "d_ready (last)", 6: "compositor done"}
+      4: "hidden epilogue done", 5: "d_ready (last)", 6: "compositor done", 7: "accumulator drained"}
 ROLE = {0: "issuer", 1: "front-end half", 2: "compositor half"}
 
 
