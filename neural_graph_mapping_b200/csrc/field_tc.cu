@@ -31,7 +31,7 @@ namespace ngm {
 
 namespace {
 
-constexpr int kThreads = 576;
+constexpr int kThreads = 608;  // 2 MMA issuers + 2 x 8 slot warps + 1 ray-parameter producer
 constexpr int kTmemCols = 512;
 constexpr int kSlotCols = 256;
 constexpr int kACol = 128;
@@ -172,6 +172,8 @@ struct Smem {
   uint64_t a_ready[2];   // hidden-layer A operand stored (all 256 threads of the slot)
   uint64_t d_ready[2];   // accumulator complete (tcgen05.commit)
   uint64_t w_ready;
+  uint64_t ray_full[2][4];   // ray parameters of a tile written (producer warp, 32 arrivals)
+  uint64_t ray_empty[2][4];  // ... consumed (the 128 compositor-half threads of the slot)
   uint32_t tmem_base;
   uint32_t pad_;
   float ray[2][4][kMaxRaysPerTile][kRayFloats];  // [slot][ring of 4 tiles][ray in tile][param]
@@ -525,6 +527,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const TcParams p) {
       ptx::mbar_init(&sm.d_ready[s], 1);
     }
     ptx::mbar_init(&sm.w_ready, 1);
+    for (int i = 0; i < 8; ++i) {
+      ptx::mbar_init(&sm.ray_full[i >> 2][i & 3], 32);
+      ptx::mbar_init(&sm.ray_empty[i >> 2][i & 3], 128);
+    }
     ptx::fence_mbar_init();
   }
   ptx::tc_fence_before();
@@ -537,6 +543,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const TcParams p) {
   const long long t_end = p.total_tiles * (blockIdx.x + 1) / gridDim.x;
 
   uint32_t w_phase = 0;
+  int ray_n0 = 0, ray_n1 = 0;  // tiles of slot 0 / 1 started by this CTA so far (ray-parameter ring position = n & 3)
   uint32_t pa0 = 0, pa = 0;  // MMA issuer: parities of its slot's a0_ready / a_ready
   uint32_t pd = 0;           // slot thread: parity of its slot's d_ready
   const int L = p.L, W = p.W;
@@ -566,7 +573,27 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const TcParams p) {
       }
     }
 
-    if (warp < 2) {
+    if (warp == 18) {
+      // ===================== ray-parameter producer (fused render only) =====================
+      // Per-ray quantities of every tile (12 floats per ray; dependent global loads, ~1.5k cycles of
+      // latency) are produced up to four tiles ahead of each slot by this otherwise idle warp, so no
+      // slot warp ever waits on HBM.  Lanes 0-15 serve slot 0's tile, lanes 16-31 slot 1's.
+      if (MODE == 0) {
+        const long long slot = p.field_slots ? p.field_slots[f] : f;
+        const int sl = lane >> 4, r = lane & 15;
+        for (int tp = 0; tp < ntiles; tp += 2) {
+          const int n0 = ray_n0 + (tp >> 1), n1 = ray_n1 + (tp >> 1);
+          const bool have1 = tp + 1 < ntiles;
+          if (n0 >= 4) ptx::mbar_wait(&sm.ray_empty[0][n0 & 3], ((n0 >> 2) + 1) & 1);
+          if (have1 && n1 >= 4) ptx::mbar_wait(&sm.ray_empty[1][n1 & 3], ((n1 >> 2) + 1) & 1);
+          const int n = sl ? n1 : n0;
+          if (r < p.rpt && (sl == 0 || have1))
+            compute_ray_params(p, f, slot, (tile0_in_field + tp + sl) * p.rpt + r, sm.ray[sl][n & 3][r]);
+          ptx::mbar_arrive(&sm.ray_full[0][n0 & 3]);
+          if (have1) ptx::mbar_arrive(&sm.ray_full[1][n1 & 3]);
+        }
+      }
+    } else if (warp < 2) {
       // ===================== MMA issuer of slot `warp` =====================
       const int s = warp;
       tev_role(s, lane == 0);
@@ -617,7 +644,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const TcParams p) {
 
       // Front end of tile `ti` (h == 1 threads), in two parts that are slotted into the waits for
       // the CURRENT tile's MMAs:  fe_a = sample point + row data,  fe_b = encoding -> staging -> arrive.
-      auto fe_a = [&](int ti, int ring, int par) {
+      auto fe_a = [&](int ti, int rn, int par) {  // rn: slot-tile count of tile ti
         const long long tile_in_field = tile0_in_field + ti;
         tev(ev_id(1, s, 0, 0));
         fx = make_float3(0.f, 0.f, 0.f);
@@ -637,7 +664,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const TcParams p) {
         } else {
           const int rit = row >> p.sp_shift;
           const int k = row & (p.Sp - 1);
-          const float* rp = sm.ray[s][ring][rit];
+          ptx::mbar_wait(&sm.ray_full[s][rn & 3], (rn >> 2) & 1);  // produced (normally long ago)
+          const float* rp = sm.ray[s][rn & 3][rit];
           const bool ray_ok = rp[10] != 0.0f;
           const long long ray = f * p.rays_per_field + tile_in_field * p.rpt + rit;
           const bool valid = ray_ok && k < p.St;
@@ -700,13 +728,6 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const TcParams p) {
         tev(ev_id(1, s, 2, 0));
       };
 
-      if (MODE == 0 && h == 1) {  // ray parameters of this slot's first two tiles (later ones two tiles ahead)
-        if (row < p.rpt) {
-          if (s < ntiles) compute_ray_params(p, f, slot, (tile0_in_field + s) * p.rpt + row, sm.ray[s][0][row]);
-          if (s + 2 < ntiles) compute_ray_params(p, f, slot, (tile0_in_field + s + 2) * p.rpt + row, sm.ray[s][1][row]);
-        }
-        ptx::named_bar_sync(bar_half, 128);
-      }
       ptx::mbar_wait(&sm.w_ready, w_phase);  // biases live in the image
 
       // Software-pipelined tile loop.  Iteration `ti` runs the MLP layers of tile ti; the front end of the
@@ -714,7 +735,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const TcParams p) {
       // the first epilogue, fe_b after the second), and the compositor of tile ti (h == 0 threads) runs
       // after the last layer while the next tile's layer 0 is already on the tensor pipe.
       // The first iteration (ti = s - 2) is virtual: it only runs the front end of the first tile.
-      int ring = 3, par = 2;  // ring slot (of 4) of the ray parameters / ring slot (of 3) of the row data of tile ti
+      int ray_n = (s ? ray_n1 : ray_n0) - 1;  // slot-tile count of tile ti (ray-parameter ring position = ray_n & 3)
+      int par = 2;                            // ring slot (of 3) of the row data of tile ti
       int comp_pending = 0;   // h == 0: 1 = inputs of the previous tile parked in sm.comp, 2 = its stage 1 done
       long long comp_tile = 0;
       const int wseg = p.Sp >= 32 ? 32 : p.Sp;
@@ -722,12 +744,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const TcParams p) {
       for (int ti = s - 2; ti < ntiles || comp_pending; ti += 2) {
         const bool real = ti >= 0 && ti < ntiles;
         const bool has_next = ti + 2 < ntiles;
-        const int nring = (ring + 1) & 3, npar = par == 2 ? 0 : par + 1;
+        const int ring = ray_n & 3, npar = par == 2 ? 0 : par + 1;
         const long long tile_in_field = tile0_in_field + ti;
         const int nsteps = real ? L + 1 : 1;
         const int step_b = real ? (L < 1 ? L : 1) : 0;  // fe_a at step 0, fe_b at step min(1, L)
-        if (real && MODE == 0 && h == 1 && row < p.rpt && ti + 4 < ntiles)  // off the critical path: layer 0's MMA runs now
-          compute_ray_params(p, f, slot, (tile_in_field + 4) * p.rpt + row, sm.ray[s][(ring + 2) & 3][row]);
         for (int l = 0; l < nsteps; ++l) {
           if (real) {
             ptx::mbar_wait_lean(&sm.d_ready[s], pd);
@@ -767,12 +787,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const TcParams p) {
                   uint32_t v[4];
                   ptx::tmem_ld4(d_addr, v);
                   const int rit = row >> p.sp_shift;
+                  ptx::mbar_wait(&sm.ray_full[s][ring], (ray_n >> 2) & 1);  // acquire (completed long ago)
                   const float* rp = sm.ray[s][ring][rit];
                   const float2 dz = *reinterpret_cast<const float2*>(sm.rowdata[s][par][row]);
                   sm.comp[s][4][row] = dz.x;
                   sm.comp[s][5][row] = dz.y;
                   sm.comp[s][6][row] = rp[9];
                   sm.comp[s][7][row] = rp[10];
+                  ptx::mbar_arrive(&sm.ray_empty[s][ring]);  // the producer may refill this ring entry
                   ptx::tc_wait_ld();
                   ptx::tc_fence_before();
                   if (has_next) ptx::mbar_arrive(&sm.a0_ready[s]);  // the next layer-0 MMA may overwrite the accumulator
@@ -790,7 +812,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const TcParams p) {
             if (has_next) ptx::mbar_arrive(&sm.a0_ready[s]);  // first tile: no accumulator to drain
           }
           if (h == 1 && has_next) {
-            if (l == 0) fe_a(ti + 2, nring, npar);
+            if (l == 0) fe_a(ti + 2, ray_n + 1, npar);
             if (l == step_b) fe_b(ti + 2);
           }
           // deferred compositor of the slot's previous tile, in the wait for this tile's next MMA
@@ -806,11 +828,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const TcParams p) {
             }
           }
         }
-        ring = nring;
+        ++ray_n;
         par = npar;
       }
     }
     w_phase ^= 1;
+    ray_n0 += (ntiles + 1) / 2;
+    ray_n1 += ntiles / 2;
     t = seg_end;
     ptx::fence_proxy_async();  // generic-proxy reads of the image before the next bulk copy overwrites it
     __syncthreads();
