@@ -105,31 +105,45 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.t0 = self.t1 = None
 
     def start(self):
+        """Start nvidia-smi early (it needs ~0.5 s to produce its first line); mark() brackets the timed region."""
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index),
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        ok = [(t, r) for t, r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        # a line printed at time t reports the clocks of the preceding sampling period
+        inside = [r for t, r in ok if self.t0 is not None and self.t0 <= t <= self.t1 + 0.03]
+        window = "timed region"
+        if not inside:  # region shorter than the sampling period: the samples of the whole GPU-busy run (warm-up included)
+            inside, window = [r for _, r in ok], "whole run (timed region shorter than one nvidia-smi period)"
+        sm = [float(r[0]) for r in inside]
+        mx = [float(r[1]) for r in inside if r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        reasons = sorted({n for r in inside for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "window": window}
 
 
 def measured_peaks():
@@ -243,8 +257,8 @@ def run_reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="auto", choices=["auto", "fp16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -264,6 +278,8 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = f"cuda:{local_rank}"
+    clocks = ClockSampler(local_rank)
+    clocks.start()
     if world > 1:
         import torch.distributed as dist
 
@@ -322,11 +338,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup):
+    def timed(fn, steps, warmup, clk=None):
         for _ in range(warmup):
             fn()
             flush.fill_(1)
         barrier()
+        if clk:
+            clk.mark_begin()
         evs = []
         for _ in range(steps):
             flush.fill_(1)  # L2 flush between timed iterations (outside the per-step events)
@@ -336,6 +354,8 @@ def main():
             e1.record()
             evs.append((e0, e1))
         barrier()
+        if clk:
+            clk.mark_end()
         total_ms = sum(a.elapsed_time(b) for a, b in evs)
         if world > 1:
             import torch.distributed as dist
@@ -345,10 +365,8 @@ def main():
             total_ms = float(t.item())
         return total_ms
 
-    clocks = ClockSampler(local_rank)
     launches0 = _lib.lib.ngm_launch_count()
-    clocks.start()
-    total_ms = timed(step_resident, args.steps, args.warmup)
+    total_ms = timed(step_resident, args.steps, args.warmup, clocks)
     clock_info = clocks.stop()
     launches = (_lib.lib.ngm_launch_count() - launches0) * args.steps // (args.steps + args.warmup)
     ms_per_step = total_ms / args.steps
@@ -473,8 +491,21 @@ def stage_breakdown(st, dz, cam, precision, steps, flush):
     else:
         dom = dict(stages["field_mlp"])
         dom["kernel"] = "field_fwd_simt_kernel (encode + MLP, fp32 FFMA)"
-    dom["traffic"] = None
+    dom["traffic"] = ncu_traffic("tc_kernel<0" if precision == "fp16" else "field_fwd_simt_kernel")
+    dom["traffic_source"] = "profiles/r1_ncu_summary.json (committed ncu --set full capture of this kernel on this workload; not live)"
     return {"stages": stages, "dominant": dom}
+
+
+def ncu_traffic(kernel_substr):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture (or None)."""
+    path = os.path.join(ROOT, "profiles", "r1_ncu_summary.json")
+    try:
+        for k in json.load(open(path))["kernels"]:
+            if kernel_substr in k["kernel"]:
+                return k.get("dram_read_bytes", 0.0) + k.get("dram_write_bytes", 0.0)
+    except (OSError, ValueError, KeyError):
+        pass
+    return None
 
 
 if __name__ == "__main__":

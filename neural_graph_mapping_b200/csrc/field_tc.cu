@@ -31,7 +31,8 @@ namespace ngm {
 
 namespace {
 
-constexpr int kThreads = 608;  // 2 MMA issuers + 2 x 8 slot warps + 1 ray-parameter producer
+// 2 MMA issuers + 2 x 8 slot warps (+ 1 ray-parameter producer in the fused renderer)
+constexpr int threads_of(int mode) { return mode == 0 ? 608 : 576; }
 constexpr int kTmemCols = 512;
 constexpr int kSlotCols = 256;
 constexpr int kACol = 128;
@@ -501,7 +502,7 @@ __device__ __forceinline__ void issue_layer(uint32_t d_addr, uint32_t a_addr, ui
 // (A lockstep variant in which all 16 warps share every epilogue job of both slots was measured slower --
 // 3.85 ms vs 2.83 ms per frame -- because each duty then stalls all 512 threads; profiles/README.md.)
 template <int MODE, int OCT, bool TRACE>
-__global__ void __launch_bounds__(kThreads, 1) tc_kernel(const TcParams p) {
+__global__ void __launch_bounds__(threads_of(MODE), 1) tc_kernel(const TcParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   // weights image first (1024-B aligned for SWIZZLE_128B), bookkeeping after it; plain pointer
   // arithmetic on smem_raw keeps the shared address space (LDS/STS, not generic LD/ST)
@@ -573,7 +574,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const TcParams p) {
       }
     }
 
-    if (warp == 18) {
+    if (MODE == 0 && warp == 18) {
       // ===================== ray-parameter producer (fused render only) =====================
       // Per-ray quantities of every tile (12 floats per ray; dependent global loads, ~1.5k cycles of
       // latency) are produced up to four tiles ahead of each slot by this otherwise idle warp, so no
@@ -874,7 +875,7 @@ int launch_tc(const TcParams& p_in, int octaves, size_t smem, int grid, cudaStre
   }
   auto go = [&](auto kernel) -> int {
     NGM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kernel<<<grid, kThreads, smem, stream>>>(p);
+    kernel<<<grid, threads_of(MODE), smem, stream>>>(p);
     return check_launch("tc_kernel");
   };
   switch (octaves * 2 + (p.trace ? 1 : 0)) {
