@@ -177,6 +177,45 @@ typedef struct NgmCompositeArgs {
   uint8_t* tsdf_mask;      /* (num_rays, S) */
 } NgmCompositeArgs;
 
+/* ---- stage: positional encoding on its own ------------------------------------------------
+ * ngm/positional_encodings.py (NeRF :245-272, Fourier :197-212, Triplane :132-161, permutohedral
+ * wrapper :19-66) as a stand-alone operator, and the permutohedral table gradient -- the two
+ * pieces of NeuralField.forward (ngm/models.py:143-145) the training path needs as kernels. */
+typedef struct NgmEncodeArgs {
+  NgmFieldDesc field;          /* only the encoding members are read */
+  int64_t points_per_field;
+  const float* points;         /* (num_fields, points_per_field, 3) field-local, scaled coordinates */
+  const int64_t* field_slots;  /* row of each field in the encoding tables; NULL = identity */
+  float* out;                  /* fwd: (num_fields, points_per_field, dim_encoding) */
+  const float* d_out;          /* bwd: upstream gradient, same shape as out */
+  float* d_param0;             /* bwd: gradient of field.enc_param0, same layout and per-field stride;
+                                  accumulated with atomics -- the caller zeroes it */
+  int32_t num_fields;
+  int32_t _pad;
+} NgmEncodeArgs;
+
+/* ---- stage: compositor backward ---------------------------------------------------------
+ * Gradient of the compositor above with respect to the sample colours and geometries (and, in neus
+ * mode, the inverse sd): what torch.autograd derives from NeuralGraphMap._quadrature and the
+ * post-MLP split (ngm/run_mapping.py:610-639, 709-799) when the training step calls
+ * loss.backward() (ngm/run_mapping.py:1186).  Distances / depths carry no gradient (they depend on
+ * the camera ray only). */
+typedef struct NgmCompositeBwdArgs {
+  NgmCompositeArgs fwd;     /* the forward call's inputs (its output pointers are ignored) */
+  /* upstream gradients; NULL = zero */
+  const float* g_rgbd;      /* (num_rays, 4) */
+  const float* g_color_var; /* (num_rays, 3) */
+  const float* g_depth_var; /* (num_rays) */
+  const float* g_term_prob; /* (num_rays) */
+  const float* g_freespace; /* (num_rays, S) dense: zero where the forward's freespace_mask is false */
+  const float* g_tsdf;      /* (num_rays, S) dense */
+  /* outputs */
+  float* d_colors;          /* element (r,s,c) at d_colors[(r*S+s)*color_stride + c] (same layout as fwd.colors) */
+  float* d_geometries;      /* element (r,s) at d_geometries[(r*S+s)*geometry_stride] */
+  float* d_neus_isd;        /* (num_rays) per-ray gradient of the inverse sd (neus mode; caller sums per field), or NULL */
+  float* workspace;         /* >= 2 * num_rays * S floats */
+} NgmCompositeBwdArgs;
+
 /* ---- fused render --------------------------------------------------------------------
  * Replaces NeuralGraphMap._render_ijs with use_vmap=True (ngm/run_mapping.py:440-666):
  * sampler -> world->local -> encoding -> per-field MLP -> compositor for
@@ -242,7 +281,7 @@ int ngm_abi_version(void);
 const char* ngm_last_error(void);
 /* sizeof() of the structs above as compiled, so a binding can verify its mirror:
  * which = 0 NgmCamera, 1 NgmFieldDesc, 2 NgmSampleArgs, 3 NgmFieldFwdArgs, 4 NgmCompositeArgs, 5 NgmRenderArgs,
- * 6 NgmKnnFwdArgs */
+ * 6 NgmKnnFwdArgs, 7 NgmCompositeBwdArgs, 8 NgmEncodeArgs */
 size_t ngm_struct_size(int which);
 /* number of CUDA kernels this library has launched in this process (bench.py's gpu_launches) */
 uint64_t ngm_launch_count(void);
@@ -250,6 +289,9 @@ uint64_t ngm_launch_count(void);
 int ngm_sample_rays(const NgmSampleArgs* args, void* stream);   /* camera.py:215-292, run_mapping.py:521-547 */
 int ngm_field_fwd(const NgmFieldFwdArgs* args, void* stream);   /* models.py:143-182, 329-345 */
 int ngm_composite(const NgmCompositeArgs* args, void* stream);  /* run_mapping.py:610-639, 709-799 */
+int ngm_composite_bwd(const NgmCompositeBwdArgs* args, void* stream); /* autograd of run_mapping.py:610-639, 709-799 */
+int ngm_encode_fwd(const NgmEncodeArgs* args, void* stream);    /* positional_encodings.py forward()s */
+int ngm_encode_bwd(const NgmEncodeArgs* args, void* stream);    /* d lattice_values of the permutohedral encoding */
 int ngm_render_rays_fwd(const NgmRenderArgs* args, void* stream); /* run_mapping.py:440-666 (use_vmap=True) */
 int ngm_fieldset_knn_fwd(const NgmKnnFwdArgs* args, void* stream); /* models.py:347-405 (use_vmap=False) */
 int ngm_fieldset_knn_workspace_bytes(const NgmKnnFwdArgs* args, size_t* out);

@@ -83,6 +83,21 @@ class NgmCompositeArgs(C.Structure):
     ]
 
 
+class NgmCompositeBwdArgs(C.Structure):
+    _fields_ = [
+        ("fwd", NgmCompositeArgs), ("g_rgbd", _fp), ("g_color_var", _fp), ("g_depth_var", _fp), ("g_term_prob", _fp),
+        ("g_freespace", _fp), ("g_tsdf", _fp), ("d_colors", _fp), ("d_geometries", _fp), ("d_neus_isd", _fp),
+        ("workspace", _fp),
+    ]
+
+
+class NgmEncodeArgs(C.Structure):
+    _fields_ = [
+        ("field", NgmFieldDesc), ("points_per_field", C.c_int64), ("points", _fp), ("field_slots", _fp), ("out", _fp),
+        ("d_out", _fp), ("d_param0", _fp), ("num_fields", C.c_int32), ("_pad", C.c_int32),
+    ]
+
+
 class NgmRenderArgs(C.Structure):
     _fields_ = [
         ("field", NgmFieldDesc), ("cam", NgmCamera), ("rays_per_field", C.c_int64), ("ijs", _fp), ("c2ws", _fp),
@@ -109,9 +124,10 @@ class NgmKnnFwdArgs(C.Structure):
     ]
 
 
-STRUCTS = [NgmCamera, NgmFieldDesc, NgmSampleArgs, NgmFieldFwdArgs, NgmCompositeArgs, NgmRenderArgs, NgmKnnFwdArgs]
+STRUCTS = [NgmCamera, NgmFieldDesc, NgmSampleArgs, NgmFieldFwdArgs, NgmCompositeArgs, NgmRenderArgs, NgmKnnFwdArgs,
+           NgmCompositeBwdArgs, NgmEncodeArgs]
 EXPORTS = [
-    "ngm_abi_version", "ngm_last_error", "ngm_struct_size", "ngm_launch_count", "ngm_sample_rays", "ngm_field_fwd", "ngm_composite",
+    "ngm_abi_version", "ngm_last_error", "ngm_struct_size", "ngm_launch_count", "ngm_sample_rays", "ngm_field_fwd", "ngm_composite", "ngm_composite_bwd", "ngm_encode_fwd", "ngm_encode_bwd",
     "ngm_render_rays_fwd", "ngm_debug_tc_gemm", "ngm_debug_tc_trace", "ngm_debug_tc_trace_peek", "ngm_debug_tmem_bw", "ngm_fieldset_knn_fwd", "ngm_fieldset_knn_workspace_bytes", "ngm_field_fwd_workspace_bytes", "ngm_render_workspace_bytes",
 ]
 
@@ -129,7 +145,8 @@ lib.ngm_struct_size.argtypes = [C.c_int]
 lib.ngm_launch_count.restype = C.c_uint64
 for _name, _arg in [("ngm_sample_rays", NgmSampleArgs), ("ngm_field_fwd", NgmFieldFwdArgs),
                     ("ngm_composite", NgmCompositeArgs), ("ngm_render_rays_fwd", NgmRenderArgs),
-                    ("ngm_fieldset_knn_fwd", NgmKnnFwdArgs)]:
+                    ("ngm_fieldset_knn_fwd", NgmKnnFwdArgs), ("ngm_composite_bwd", NgmCompositeBwdArgs),
+                    ("ngm_encode_fwd", NgmEncodeArgs), ("ngm_encode_bwd", NgmEncodeArgs)]:
     getattr(lib, _name).restype = C.c_int
     getattr(lib, _name).argtypes = [C.POINTER(_arg), C.c_void_p]
 lib.ngm_fieldset_knn_workspace_bytes.restype = C.c_int

@@ -48,6 +48,9 @@ int launch_tc_gemm_debug(const NgmFieldDesc& fd, const void* a_half, long long r
 size_t knn_workspace_bytes(long long num_points, int num_knn, int num_fields);
 int launch_fieldset_knn(const NgmKnnFwdArgs& a, cudaStream_t stream);
 
+int launch_composite_bwd(const NgmCompositeBwdArgs& b, cudaStream_t stream);
+int launch_encode_fwd(const NgmEncodeArgs& a, cudaStream_t stream);
+int launch_encode_bwd(const NgmEncodeArgs& a, cudaStream_t stream);
 int tc_trace_read(unsigned long long* out, int max_events);
 int tc_trace_peek(unsigned long long* out, int max_events);
 int tmem_bw_bench(int warps, int iters, int mode, unsigned long long* host_cycles);
@@ -133,6 +136,8 @@ size_t ngm_struct_size(int which) {
     case 4: return sizeof(NgmCompositeArgs);
     case 5: return sizeof(NgmRenderArgs);
     case 6: return sizeof(NgmKnnFwdArgs);
+    case 7: return sizeof(NgmCompositeBwdArgs);
+    case 8: return sizeof(NgmEncodeArgs);
     default: return 0;
   }
 }
@@ -190,6 +195,64 @@ int ngm_composite(const NgmCompositeArgs* a, void* stream) {
   NGM_CHECK_ARG((a->tsdf == nullptr) == (a->tsdf_mask == nullptr), "tsdf and its mask go together");
   NGM_CHECK_ARG(((uintptr_t)a->rgbd & 15) == 0, "rgbd must be 16-byte aligned");
   return launch_composite(*a, (cudaStream_t)stream);
+}
+
+int ngm_composite_bwd(const NgmCompositeBwdArgs* b, void* stream) {
+  NGM_CHECK_ARG(b != nullptr, "null args");
+  const NgmCompositeArgs* a = &b->fwd;
+  NGM_CHECK_ARG(a->num_rays >= 0 && a->num_samples > 0, "bad ray/sample counts");
+  if (a->num_rays == 0) return NGM_OK;
+  NGM_CHECK_ARG(a->colors && a->geometries && a->distances && a->depths, "missing forward input");
+  NGM_CHECK_ARG(b->d_colors && b->d_geometries && b->workspace, "missing output / workspace");
+  NGM_CHECK_ARG(a->geometry_mode >= NGM_GEOM_DENSITY && a->geometry_mode <= NGM_GEOM_NRGBD, "unknown geometry_mode %d",
+                a->geometry_mode);
+  if (a->geometry_mode == NGM_GEOM_NEUS)
+    NGM_CHECK_ARG(a->neus_isd && a->rays_per_isd > 0, "neus mode needs neus_isd");
+  return launch_composite_bwd(*b, (cudaStream_t)stream);
+}
+
+static int validate_encoding(const NgmFieldDesc& fd) {
+  NGM_CHECK_ARG(fd.encoding >= NGM_ENC_NERF && fd.encoding <= NGM_ENC_PERMUTO, "unknown encoding %d", fd.encoding);
+  NGM_CHECK_ARG(fd.dim_encoding > 0, "non-positive encoding width");
+  switch (fd.encoding) {
+    case NGM_ENC_NERF:
+      NGM_CHECK_ARG(fd.dim_encoding == 6 * fd.nerf_num_octaves, "nerf: dim_encoding != 2*3*num_octaves");
+      break;
+    case NGM_ENC_FOURIER:
+      NGM_CHECK_ARG(fd.enc_param0 && fd.dim_encoding == fd.fourier_num_features + (fd.fourier_raw_coords ? 3 : 0),
+                    "fourier: bad dims or missing weight");
+      break;
+    case NGM_ENC_TRIPLANE:
+      NGM_CHECK_ARG(fd.enc_param0 && fd.triplane_resolution >= 2 &&
+                        fd.dim_encoding == fd.triplane_components * (fd.triplane_mode == NGM_TRIPLANE_CONCAT ? 3 : 1),
+                    "triplane: bad dims or missing plane_coef");
+      break;
+    default:
+      NGM_CHECK_ARG(fd.enc_param0 && fd.enc_param1 && fd.permuto_scale, "permuto: missing table/shift/scale");
+      NGM_CHECK_ARG(fd.permuto_feats >= 1 && fd.permuto_feats <= 8 && fd.permuto_log2_capacity >= 1 &&
+                        fd.permuto_log2_capacity <= 30 &&
+                        fd.dim_encoding == fd.permuto_levels * fd.permuto_feats + (fd.permuto_concat_points ? 3 : 0),
+                    "permuto: unsupported dims");
+  }
+  return NGM_OK;
+}
+
+int ngm_encode_fwd(const NgmEncodeArgs* a, void* stream) {
+  NGM_CHECK_ARG(a != nullptr, "null args");
+  if (int rc = validate_encoding(a->field)) return rc;
+  NGM_CHECK_ARG(a->num_fields >= 0 && a->points_per_field >= 0, "negative sizes");
+  if (a->num_fields == 0 || a->points_per_field == 0) return NGM_OK;
+  NGM_CHECK_ARG(a->points && a->out, "points / out missing");
+  return launch_encode_fwd(*a, (cudaStream_t)stream);
+}
+
+int ngm_encode_bwd(const NgmEncodeArgs* a, void* stream) {
+  NGM_CHECK_ARG(a != nullptr, "null args");
+  if (int rc = validate_encoding(a->field)) return rc;
+  NGM_CHECK_ARG(a->num_fields >= 0 && a->points_per_field >= 0, "negative sizes");
+  if (a->num_fields == 0 || a->points_per_field == 0) return NGM_OK;
+  NGM_CHECK_ARG(a->points && a->d_out && a->d_param0, "points / d_out / d_param0 missing");
+  return launch_encode_bwd(*a, (cudaStream_t)stream);
 }
 
 int ngm_fieldset_knn_workspace_bytes(const NgmKnnFwdArgs* a, size_t* out) {

@@ -1,0 +1,110 @@
+// Stage kernels: positional encodings on their own (field-local, scaled points -> features), and the
+// permutohedral table gradient.  ngm/positional_encodings.py: NeRF :245-272, Fourier :197-212,
+// Triplane :132-161, permutohedral wrapper :19-66.  The training path (autograd.py) evaluates the MLP
+// with library GEMMs around these; the render kernels encode in-line with the same device functions.
+#include "common.cuh"
+#include "encodings.cuh"
+
+namespace ngm {
+
+namespace {
+
+__global__ void __launch_bounds__(256) encode_fwd_kernel(NgmEncodeArgs a) {
+  const NgmFieldDesc& fd = a.field;
+  const int E = fd.dim_encoding;
+  const long long n = a.points_per_field;
+  if (fd.encoding == NGM_ENC_PERMUTO) {
+    const int L = fd.permuto_levels, F = fd.permuto_feats;
+    const long long total = (long long)a.num_fields * n * (L + 1);  // L lattice levels + 1 "concat points" item
+    const size_t level_elems = ((size_t)1 << fd.permuto_log2_capacity) * F;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+      const int l = (int)(idx % (L + 1));
+      const long long pt = idx / (L + 1);
+      const long long f = pt / n;
+      const long long slot = a.field_slots ? a.field_slots[f] : f;
+      const float* src = a.points + pt * 3;
+      const float x[3] = {__ldg(src), __ldg(src + 1), __ldg(src + 2)};
+      float* dst = a.out + pt * E;
+      if (l < L) {
+        permuto_level<8>(x, fd.enc_param0 + slot * fd.enc_param0_stride + l * level_elems,
+                         fd.enc_param1 + slot * fd.enc_param1_stride + l * 3, fd.permuto_scale + l * 3,
+                         fd.permuto_log2_capacity, F, dst + l * F);
+      } else if (fd.permuto_concat_points) {
+        for (int c = 0; c < 3; ++c) dst[L * F + c] = x[c] * fd.permuto_concat_scaling;
+      }
+    }
+    return;
+  }
+  const long long total = (long long)a.num_fields * n * E;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % E);
+    const long long pt = idx / E;
+    const long long f = pt / n;
+    const long long slot = a.field_slots ? a.field_slots[f] : f;
+    const float* src = a.points + pt * 3;
+    const float x[3] = {__ldg(src), __ldg(src + 1), __ldg(src + 2)};
+    const float* ep = fd.enc_param0 ? fd.enc_param0 + slot * fd.enc_param0_stride : nullptr;
+    float v;
+    if (fd.encoding == NGM_ENC_NERF) v = nerf_feature(x, c, fd.nerf_num_octaves, fd.nerf_start_octave);
+    else if (fd.encoding == NGM_ENC_FOURIER) v = fourier_feature(x, c, ep, fd.fourier_raw_coords);
+    else v = triplane_feature(x, c, ep, fd.triplane_resolution, fd.triplane_components, fd.triplane_mode);
+    a.out[idx] = v;
+  }
+}
+
+// permutohedral: d lattice_values; one thread per (field, point, level)
+__global__ void __launch_bounds__(256) permuto_bwd_kernel(NgmEncodeArgs a) {
+  const NgmFieldDesc& fd = a.field;
+  const int E = fd.dim_encoding, L = fd.permuto_levels, F = fd.permuto_feats;
+  const long long n = a.points_per_field;
+  const long long total = (long long)a.num_fields * n * L;
+  const size_t level_elems = ((size_t)1 << fd.permuto_log2_capacity) * F;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int l = (int)(idx % L);
+    const long long pt = idx / L;
+    const long long f = pt / n;
+    const long long slot = a.field_slots ? a.field_slots[f] : f;
+    const float* src = a.points + pt * 3;
+    const float x[3] = {__ldg(src), __ldg(src + 1), __ldg(src + 2)};
+    float g[8];
+    bool any = false;
+    for (int i = 0; i < F; ++i) {
+      g[i] = __ldg(a.d_out + pt * E + l * F + i);
+      any |= g[i] != 0.0f;
+    }
+    if (!any) continue;
+    permuto_level_bwd<8>(x, a.d_param0 + slot * fd.enc_param0_stride + l * level_elems,
+                         fd.enc_param1 + slot * fd.enc_param1_stride + l * 3, fd.permuto_scale + l * 3,
+                         fd.permuto_log2_capacity, F, g);
+  }
+}
+
+unsigned grid_for(long long items) {
+  long long blocks = (items + 255) / 256;
+  const long long cap = (long long)num_sms() * 16;
+  return (unsigned)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
+}
+
+}  // namespace
+
+int launch_encode_fwd(const NgmEncodeArgs& a, cudaStream_t stream) {
+  const NgmFieldDesc& fd = a.field;
+  const long long per_point = fd.encoding == NGM_ENC_PERMUTO ? fd.permuto_levels + 1 : fd.dim_encoding;
+  encode_fwd_kernel<<<grid_for((long long)a.num_fields * a.points_per_field * per_point), 256, 0, stream>>>(a);
+  return check_launch("encode_fwd_kernel");
+}
+
+int launch_encode_bwd(const NgmEncodeArgs& a, cudaStream_t stream) {
+  if (a.field.encoding != NGM_ENC_PERMUTO) {
+    set_error("ngm_encode_bwd: only the permutohedral table gradient is a CUDA kernel (nerf has no parameters; "
+              "fourier / triplane gradients come from the PyTorch expressions in autograd.py)");
+    return NGM_ERR_UNSUPPORTED;
+  }
+  permuto_bwd_kernel<<<grid_for((long long)a.num_fields * a.points_per_field * a.field.permuto_levels), 256, 0, stream>>>(a);
+  return check_launch("permuto_bwd_kernel");
+}
+
+}  // namespace ngm

@@ -65,12 +65,11 @@ __device__ __forceinline__ float triplane_feature(const float* x, int c, const f
   return mode == NGM_TRIPLANE_PRODUCT ? (a * b) * d : (a + b) + d;
 }
 
-// One level of the permutohedral-lattice hash encoding for a 3-D point: writes `feats` values.
-//   table = (capacity, feats) of this level; shift/scale = 3 floats of this level.
-template <int MAXF>
-__device__ __forceinline__ void permuto_level(const float* x, const float* __restrict__ table,
-                                              const float* __restrict__ shift, const float* __restrict__ scale,
-                                              int log2_capacity, int feats, float* out) {
+// Enclosing simplex of a 3-D point on one level of the permutohedral lattice: the hashed table rows of
+// its four vertices and their barycentric weights.  shift/scale = 3 floats of this level.
+__device__ __forceinline__ void permuto_simplex(const float* x, const float* __restrict__ shift,
+                                                const float* __restrict__ scale, int log2_capacity, uint32_t (&row)[4],
+                                                float (&weight)[4]) {
   constexpr int D = 3, D1 = 4;
   float cf[D];
 #pragma unroll
@@ -121,9 +120,6 @@ __device__ __forceinline__ void permuto_level(const float* x, const float* __res
     }
   }
   bary[0] = __fadd_rn(bary[0], __fadd_rn(1.0f, bary[D + 1]));
-  float acc[MAXF];
-#pragma unroll
-  for (int f = 0; f < MAXF; ++f) acc[f] = 0.0f;
   const uint32_t mask = (1u << log2_capacity) - 1u;
 #pragma unroll
   for (int r = 0; r < D1; ++r) {
@@ -134,14 +130,51 @@ __device__ __forceinline__ void permuto_level(const float* x, const float* __res
       if (rank[i] > D - r) key -= D1;
       h = (h + (uint32_t)key) * 2531011u;
     }
-    const float* fv = table + (size_t)(h & mask) * feats;
+    row[r] = h & mask;
+    weight[r] = bary[r];
+  }
+}
+
+// One level of the permutohedral-lattice hash encoding for a 3-D point: writes `feats` values.
+//   table = (capacity, feats) of this level.
+template <int MAXF>
+__device__ __forceinline__ void permuto_level(const float* x, const float* __restrict__ table,
+                                              const float* __restrict__ shift, const float* __restrict__ scale,
+                                              int log2_capacity, int feats, float* out) {
+  uint32_t row[4];
+  float weight[4];
+  permuto_simplex(x, shift, scale, log2_capacity, row, weight);
+  float acc[MAXF];
+#pragma unroll
+  for (int f = 0; f < MAXF; ++f) acc[f] = 0.0f;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const float* fv = table + (size_t)row[r] * feats;
 #pragma unroll
     for (int f = 0; f < MAXF; ++f)
-      if (f < feats) acc[f] = __fadd_rn(acc[f], __fmul_rn(bary[r], __ldg(fv + f)));
+      if (f < feats) acc[f] = __fadd_rn(acc[f], __fmul_rn(weight[r], __ldg(fv + f)));
   }
 #pragma unroll
   for (int f = 0; f < MAXF; ++f)
     if (f < feats) out[f] = acc[f];
+}
+
+// Gradient of one level with respect to its table: d_table[row_r] += weight_r * d_out  (atomics: many points
+// share a vertex).  The point itself carries no gradient (sample positions do not depend on parameters).
+template <int MAXF>
+__device__ __forceinline__ void permuto_level_bwd(const float* x, float* __restrict__ d_table,
+                                                  const float* __restrict__ shift, const float* __restrict__ scale,
+                                                  int log2_capacity, int feats, const float* d_out) {
+  uint32_t row[4];
+  float weight[4];
+  permuto_simplex(x, shift, scale, log2_capacity, row, weight);
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    float* dv = d_table + (size_t)row[r] * feats;
+#pragma unroll
+    for (int f = 0; f < MAXF; ++f)
+      if (f < feats) atomicAdd(dv + f, weight[r] * d_out[f]);
+  }
 }
 
 }  // namespace ngm

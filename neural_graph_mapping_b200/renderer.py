@@ -90,17 +90,27 @@ def render_rays(
         # the reference driver: keep its side effects (gather copy + optimizer remap, :500,668-707)
         driver._set_vmap_fields(field_ids)
         params = model.vmap_fields_params
-        models._no_autograd(*params.values())
         positions = driver._global_map_dict["positions"][field_ids]
         orientations = driver._global_map_dict["orientations"][field_ids]
         slots = None
     else:
         # stand-alone: read the stacked tables in place through field_slots (no gather copy)
         params = model.all_fields_params
-        models._no_autograd(*params.values())
         positions = driver._global_map_dict["positions"]
         orientations = driver._global_map_dict["orientations"]
         slots = field_ids.to(device=dev, dtype=torch.int64).contiguous()
+    if torch.is_grad_enabled() and any(t.requires_grad for t in params.values()):
+        # training (run_mapping.py:1164-1186): autograd must reach the field parameters
+        from . import autograd as ag
+
+        if slots is not None:  # gather the active fields (differentiable; what set_vmap_fields does, models.py:274-276)
+            params = {k: v[slots] for k, v in params.items()}
+            positions, orientations = positions[slots], orientations[slots]
+        if out is not None:
+            raise ValueError("out= is not supported on the differentiable path")
+        return Prediction(*ag.render_rays_vmap(
+            driver, camera, ijs, c2ws, params, positions, orientations, near_distances, far_distances, gt_distances,
+            overwrite, jitter, jitter_guided, 0 if jitter is not None else _next_seed()))
     with torch.no_grad(), torch.cuda.device(dev):
         a.field, k2 = proto.field_desc(params, True)
         keep += k2
