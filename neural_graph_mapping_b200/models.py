@@ -35,8 +35,8 @@ def get_default_precision() -> str:
 def _no_autograd(*tensors) -> None:
     if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors):
         raise NotImplementedError(
-            "libngm_b200 implements the forward pass only (SURVEY.md 8f #2: backward is the next "
-            "row); call under torch.no_grad() or detach the parameters"
+            "this entry point is forward-only: gradients flow through render_rays(use_vmap=True) "
+            "(neural_graph_mapping_b200.autograd); call under torch.no_grad() or detach the parameters"
         )
 
 
