@@ -25,6 +25,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "encodings.cuh"
 #include "tc_ptx.cuh"
 
 namespace ngm {
@@ -126,6 +127,13 @@ struct TcParams {
   int num_fields;
   int E, EP, W, L, dim_out;
   int nerf_start;
+  // permutohedral encoding (OCT == 0): per-field table (levels, capacity, 2) fp32, read through L2
+  const float* pm_table;
+  const float* pm_shift;
+  const float* pm_scale;
+  long long pm_table_stride, pm_shift_stride;
+  int pm_levels, pm_log2cap, pm_concat;
+  float pm_concat_scale;
   // field poses
   const float* positions;
   const float* orientations;
@@ -229,6 +237,46 @@ __device__ __forceinline__ void encode_nerf_to_tmem(uint32_t a_addr, float3 x, i
 #pragma unroll
   for (int j = 0; j < EP / 2; ++j) w[j] = ptx::pack_half2(fe[2 * j], fe[2 * j + 1]);
   ptx::tmem_store_n<EP / 2>(a_addr, w);
+}
+
+// Permutohedral features (2 per level) of lattice levels [l0, l1) of one row -> fp16 -> TMEM A-operand words
+// [l0, l1) (one word per level).  The table stays in global memory (L2-resident: 512 KB per field).
+__device__ __forceinline__ void encode_permuto_levels(const TcParams& p, uint32_t a_addr, float3 x, long long slot, int l0,
+                                                      int l1) {
+  const float xs[3] = {x.x, x.y, x.z};
+  const size_t level_elems = ((size_t)1 << p.pm_log2cap) * 2;
+  const float* table = p.pm_table + slot * p.pm_table_stride;
+  const float* shift = p.pm_shift + slot * p.pm_shift_stride;
+  for (int l = l0; l < l1; l += 4) {
+    if (l + 4 <= l1) {
+      uint32_t w[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float f2[2];
+        permuto_level<2>(xs, table + (size_t)(l + i) * level_elems, shift + (l + i) * 3, p.pm_scale + (l + i) * 3,
+                         p.pm_log2cap, 2, f2);
+        w[i] = ptx::pack_half2(f2[0], f2[1]);
+      }
+      ptx::tmem_st4(a_addr + l, w);
+    } else {
+      for (int i = l; i < l1; ++i) {
+        float f2[2];
+        permuto_level<2>(xs, table + (size_t)i * level_elems, shift + i * 3, p.pm_scale + i * 3, p.pm_log2cap, 2, f2);
+        uint32_t w1[1] = {ptx::pack_half2(f2[0], f2[1])};
+        ptx::tmem_st1(a_addr + i, w1);
+      }
+    }
+  }
+}
+// words [levels, EP/2): the optional raw points (concat_points) and the zero padding up to the K multiple of 16
+__device__ __forceinline__ void encode_permuto_tail(const TcParams& p, uint32_t a_addr, float3 x) {
+  const float cs = p.pm_concat_scale;
+  for (int w = p.pm_levels; w < p.EP / 2; ++w) {
+    uint32_t v[1] = {0u};
+    if (p.pm_concat && w == p.pm_levels) v[0] = ptx::pack_half2(x.x * cs, x.y * cs);
+    if (p.pm_concat && w == p.pm_levels + 1) v[0] = ptx::pack_half2(x.z * cs, 0.0f);
+    ptx::tmem_st1(a_addr + w, v);
+  }
 }
 
 // 16 accumulator columns -> relu(x + b) as 8 packed half2 words
@@ -720,13 +768,28 @@ __global__ void __launch_bounds__(threads_of(MODE), 1) tc_kernel(const TcParams 
             for (int i = 0; i < 8; ++i) w[i] = valid ? __ldg(src + c + i) : 0u;
             ptx::tmem_st8(a0_addr + c, w);
           }
-        } else {
+        } else if constexpr (OCT > 0) {
           encode_nerf_to_tmem<OCT>(a0_addr, fx, p.nerf_start);
         }
         ptx::tc_wait_st();
         ptx::tc_fence_before();
         ptx::mbar_arrive(&sm.a0_ready[s]);
         tev(ev_id(1, s, 2, 0));
+      };
+      // permutohedral front end: the 16 x 4 table gathers of a row are spread over the waits of up to four
+      // hidden layers (gap g handles a quarter of the levels and stores them straight into the staging columns)
+      auto fe_permuto = [&](int l, int ngaps) {
+        if (l >= ngaps) return;
+        const int Lv = p.pm_levels;
+        const int g0 = (Lv + 3) / 4 * l / ngaps * 4, g1 = l + 1 == ngaps ? Lv : (Lv + 3) / 4 * (l + 1) / ngaps * 4;
+        encode_permuto_levels(p, a0_addr, fx, slot, g0 < Lv ? g0 : Lv, g1 < Lv ? g1 : Lv);
+        if (l + 1 == ngaps) {
+          encode_permuto_tail(p, a0_addr, fx);
+          ptx::tc_wait_st();
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(&sm.a0_ready[s]);
+          tev(ev_id(1, s, 2, 0));
+        }
       };
 
       ptx::mbar_wait(&sm.w_ready, w_phase);  // biases live in the image
@@ -814,7 +877,11 @@ __global__ void __launch_bounds__(threads_of(MODE), 1) tc_kernel(const TcParams 
           }
           if (h == 1 && has_next) {
             if (l == 0) fe_a(ti + 2, ray_n + 1, npar);
-            if (l == step_b) fe_b(ti + 2);
+            if (OCT > 0 || (MODE == 1 && p.raw_a)) {
+              if (l == step_b) fe_b(ti + 2);
+            } else {
+              fe_permuto(l, real ? (L < 4 ? (L < 1 ? 1 : L) : 4) : 1);
+            }
           }
           // deferred compositor of the slot's previous tile, in the wait for this tile's next MMA
           if (MODE == 0 && h == 0 && comp_pending && l < 2 && (l < L || !real)) {
@@ -878,7 +945,9 @@ int launch_tc(const TcParams& p_in, int octaves, size_t smem, int grid, cudaStre
     kernel<<<grid, threads_of(MODE), smem, stream>>>(p);
     return check_launch("tc_kernel");
   };
-  switch (octaves * 2 + (p.trace ? 1 : 0)) {
+  switch (octaves * 2 + (p.trace ? 1 : 0)) {  // octaves == 0: permutohedral
+    case 0: return go(tc_kernel<MODE, 0, false>);
+    case 1: return go(tc_kernel<MODE, 0, true>);
     case 8: return go(tc_kernel<MODE, 4, false>);
     case 9: return go(tc_kernel<MODE, 4, true>);
     case 16: return go(tc_kernel<MODE, 8, false>);
@@ -897,6 +966,13 @@ int fill_common(TcParams& p, const NgmFieldDesc& fd, int num_fields, const float
   p.L = fd.num_layers;
   p.dim_out = fd.dim_out;
   p.nerf_start = fd.nerf_start_octave;
+  if (fd.encoding == NGM_ENC_PERMUTO) {
+    p.pm_table = fd.enc_param0; p.pm_table_stride = fd.enc_param0_stride;
+    p.pm_shift = fd.enc_param1; p.pm_shift_stride = fd.enc_param1_stride;
+    p.pm_scale = fd.permuto_scale;
+    p.pm_levels = fd.permuto_levels; p.pm_log2cap = fd.permuto_log2_capacity;
+    p.pm_concat = fd.permuto_concat_points; p.pm_concat_scale = fd.permuto_concat_scaling;
+  }
   p.im = make_image(fd, p.EP);
   p.images = static_cast<const uint8_t*>(workspace);
   p.num_fields = num_fields;
@@ -921,8 +997,11 @@ size_t tc_smem_bytes(const TcImage& im) {
 
 bool field_tc_supported(const NgmFieldDesc& fd, const char** why) {
   const char* w = nullptr;
-  if (fd.encoding != NGM_ENC_NERF) w = "only the NeRF encoding is on the tcgen05 path in this revision";
-  else if (!nerf_octaves_supported(fd.nerf_num_octaves)) w = "num_octaves must be 4 or 8";
+  if (fd.encoding != NGM_ENC_NERF && fd.encoding != NGM_ENC_PERMUTO)
+    w = "only the NeRF and permutohedral encodings are on the tcgen05 path in this revision";
+  else if (fd.encoding == NGM_ENC_NERF && !nerf_octaves_supported(fd.nerf_num_octaves)) w = "num_octaves must be 4 or 8";
+  else if (fd.encoding == NGM_ENC_PERMUTO && fd.permuto_feats != 2) w = "permutohedral: nr_feat_per_level must be 2 on the tcgen05 path";
+  else if (fd.encoding == NGM_ENC_PERMUTO && ep_of(fd) > 64) w = "permutohedral: encoding wider than 64 features";
   else if (fd.skip_mode != NGM_SKIP_NO) w = "skip connections are only on the fp32 path";
   else if (fd.dim_mlp_out % 16 != 0 || fd.dim_mlp_out < 16 || fd.dim_mlp_out > 128) w = "dim_mlp_out must be a multiple of 16 in [16,128]";
   else if (fd.dim_out > 128) w = "dim_out > 128";
@@ -948,7 +1027,7 @@ int launch_field_fwd_tc(const NgmFieldFwdArgs& a, cudaStream_t stream) {
   p.tiles_per_field = (a.points_per_field + 127) / 128;
   p.total_tiles = p.tiles_per_field * a.num_fields;
   const int grid = tc_grid(p.total_tiles);
-  return launch_tc<1>(p, a.field.nerf_num_octaves, tc_smem_bytes(p.im), grid, stream);
+  return launch_tc<1>(p, a.field.encoding == NGM_ENC_PERMUTO ? 0 : a.field.nerf_num_octaves, tc_smem_bytes(p.im), grid, stream);
 }
 
 // debug / unit-test entry: D = A (fp16, given) x W^T with the production weight packing, smem
@@ -1042,7 +1121,7 @@ int launch_render_fused_tc(const NgmRenderArgs& a, void* tc_ws, float* isd_ws, c
   p.tiles_per_field = (a.rays_per_field + p.rpt - 1) / p.rpt;
   p.total_tiles = p.tiles_per_field * a.num_fields;
   const int grid = tc_grid(p.total_tiles);
-  return launch_tc<0>(p, a.field.nerf_num_octaves, tc_smem_bytes(p.im), grid, stream);
+  return launch_tc<0>(p, a.field.encoding == NGM_ENC_PERMUTO ? 0 : a.field.nerf_num_octaves, tc_smem_bytes(p.im), grid, stream);
 }
 
 }  // namespace ngm

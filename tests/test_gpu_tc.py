@@ -195,3 +195,77 @@ def test_psnr_trained_field_within_0p1_db():
     assert abs(out["fp16"][0] - psnr_ref) < 0.1, out
     assert out["fp16"][1] > 45.0, out
     assert abs(out["fp16"][2] - meta["depth_l1_reference"]) < 5e-3
+
+
+_PERMUTO_KW = dict(pos_dim=3, log2_hashmap_size=12, nr_levels=16, nr_feat_per_level=2, coarsest_scale=1.0,
+                   finest_scale=1e-4, init_scale=0.5)
+
+
+@pytest.mark.parametrize("W,L,levels,concat,n", [(128, 4, 16, False, 4096), (32, 1, 16, False, 1000), (64, 2, 6, True, 333),
+                                               (48, 3, 10, False, 129)])
+def test_fieldset_permuto_fp16_vs_oracle(W, L, levels, concat, n):
+    """Permutohedral front end of the tcgen05 kernel (field stage): several fields, level counts that are not a
+    multiple of four, concat_points, tile tails; against oracle/permuto.py + the oracle MLP."""
+    import neural_graph_mapping_b200 as ngm
+
+    g = torch.Generator().manual_seed(W + L + levels)
+    F = 4
+    ekw = dict(_PERMUTO_KW, nr_levels=levels, concat_points=concat, concat_points_scaling=0.5)
+    spec = R.FieldSpec("permuto", ekw, L, 4, W, "no")
+    params = R.stack_params([R.init_field_params(spec, g) for _ in range(F)])
+    pos = torch.randn(F, 3, generator=g)
+    q = torch.randn(F, 4, generator=g)
+    ori = q / q.norm(dim=-1, keepdim=True)
+    pts = pos[:, None] + torch.rand(F, n, 3, generator=g) * 1.6 - 0.8
+    rs = R.RenderSpec(field_radius=1.0, scale_mode="unit_cube")
+    ref = R.fieldset_forward_vmap(pts, pos, ori, spec, params, rs)
+    model = ngm.NeuralFieldSet(3, "neural_graph_mapping_b200.models.NeuralField",
+                               {"encoding_type": "neural_graph_mapping_b200.positional_encodings.PermutohedralEncoding",
+                                "encoding_kwargs": ekw, "num_layers": L, "dim_out": 4, "dim_mlp_out": W}, 2, 10.0, 1.0,
+                               field_radius=1.0, scale_mode="unit_cube", precision="fp16").to(DEV)
+    model.all_fields_params = {k: v.to(DEV) for k, v in params.items()}
+    model.set_vmap_fields(None)
+    with torch.no_grad():
+        y = model(pts.to(DEV), pos.to(DEV), ori.to(DEV), None, True)
+    scale = ref.abs().max().item()
+    e = (y.cpu() - ref).abs()
+    assert e.max().item() < 2e-2 * scale and e.mean().item() < 3e-3 * scale, (e.max().item(), e.mean().item(), scale)
+
+
+@pytest.mark.parametrize("L,W,S", [(4, 128, 64), (1, 32, 24), (2, 64, 16)])
+def test_render_fused_permuto_fp16_vs_fp32(L, W, S):
+    """Fused tcgen05 render with the permutohedral encoding (the reference's default encoding; 1 hidden layer x 32
+    is its default MLP, neural_graph_map.yaml:6-17) against the fp32 kernels on identical rays and jitter."""
+    import neural_graph_mapping_b200 as ngm
+
+    meta, a = G.load("vmap_guided_nrgbd")
+    g = torch.Generator().manual_seed(L * 100 + W)
+    F, Rr = 3, 300
+    spec = R.FieldSpec("permuto", dict(_PERMUTO_KW), L, 4, W, "no")
+    params = R.stack_params([R.init_field_params(spec, g) for _ in range(F)])
+    params[f"_linears.{L}.weight"][:, 3] *= 10.0  # spread the geometry (x20 geometry_factor, nrgbd bump) so that
+    params[f"_linears.{L}.bias"][:, 3] += 0.3      # rays neither all terminate at the first sample nor never
+    fk = {"encoding_type": "neural_graph_mapping.positional_encodings.PermutohedralEncoding", "encoding_kwargs": dict(_PERMUTO_KW),
+          "num_layers": L, "dim_out": 4, "dim_mlp_out": W, "skip_mode": "no", "initial_geometry_bias": 0.0,
+          "neus_initial_sd": 1.0}
+    meta = dict(meta, num_samples=S, num_samples_depth_guided=0, field_kwargs=fk)
+    arrays = {f"param:{k}": v for k, v in params.items()}
+    arrays["positions"], arrays["orientations"] = a["positions"][:F], a["orientations"][:F]
+    ijs = torch.stack([torch.randint(0, 480, (F, Rr), generator=g), torch.randint(0, 640, (F, Rr), generator=g)], -1)
+    near = torch.rand(F, Rr, generator=g) * 0.5 + 0.3
+    far = near + 1.5
+    jit = torch.rand(F, Rr, S, generator=g)
+    cam = ngm.Camera(**meta["camera"])
+    outs = {}
+    for prec in ("fp32", "fp16"):
+        st = make_state(meta, arrays, DEV, prec)
+        with torch.no_grad():
+            outs[prec] = st._render_ijs(ijs.to(DEV), a["c2ws"][:F, :1].expand(F, Rr, 4, 4).to(DEV), cam,
+                                        torch.arange(F, device=DEV), True, near.to(DEV), far.to(DEV), None,
+                                        jitter=jit.to(DEV))
+    p32, p16 = outs["fp32"], outs["fp16"]
+    assert torch.isfinite(p16.rgbds).all()
+    assert (p16.rgbds[..., :3] - p32.rgbds[..., :3]).abs().mean().item() < 2e-3
+    assert (p16.rgbds[..., 3] - p32.rgbds[..., 3]).abs().mean().item() < 5e-3
+    assert (p16.term_probs - p32.term_probs).abs().mean().item() < 3e-3
+    assert p32.term_probs.std().item() > 1e-3, "degenerate scene: the comparison would be vacuous"
