@@ -41,7 +41,10 @@ bool field_tc_supported(const NgmFieldDesc& fd, const char** why);
 size_t field_tc_workspace_bytes(const NgmFieldDesc& fd, int num_fields);
 int launch_field_fwd_tc(const NgmFieldFwdArgs& a, cudaStream_t stream);
 bool render_fused_tc_ok(const NgmRenderArgs& a);
-int launch_render_fused_tc(const NgmRenderArgs& a, void* tc_ws, float* isd_ws, cudaStream_t stream);
+int launch_render_fused_tc(const NgmRenderArgs& a, void* tc_ws, float* isd_ws, const void* rows_half, const float* dist,
+                           const float* depth, cudaStream_t stream);
+bool render_tc_precoded(const NgmRenderArgs& a);
+int launch_permuto_rows_half(const PermutoRowsArgs& a, cudaStream_t stream);
 int launch_tc_gemm_debug(const NgmFieldDesc& fd, const void* a_half, long long rows, float* out, void* workspace,
                          cudaStream_t stream);
 
@@ -94,7 +97,7 @@ static int validate_field(const NgmFieldDesc& fd) {
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct RenderWorkspace {
-  size_t points_world, distances, depths, outs, isd, tc, total;
+  size_t points_world, distances, depths, outs, rows_half, isd, tc, total;
 };
 
 static RenderWorkspace render_workspace(const NgmRenderArgs& a) {
@@ -102,11 +105,17 @@ static RenderWorkspace render_workspace(const NgmRenderArgs& a) {
   const int St = a.num_samples + (a.gt ? a.num_samples_guided : 0);
   const size_t n = (size_t)a.num_fields * (size_t)a.rays_per_field * (size_t)St;
   size_t off = 0;
-  if (!render_fused_tc_ok(a)) {  // the fused kernel keeps every per-sample intermediate on chip
+  const bool fused = render_fused_tc_ok(a);
+  const bool precoded = fused && render_tc_precoded(a);
+  if (!fused || precoded) {  // the fused NeRF kernel keeps every per-sample intermediate on chip
     w.points_world = off; off = align_up(off + n * 3 * sizeof(float), 256);
     w.distances = off;    off = align_up(off + n * sizeof(float), 256);
     w.depths = off;       off = align_up(off + n * sizeof(float), 256);
-    w.outs = off;         off = align_up(off + n * 4 * sizeof(float), 256);
+  }
+  if (!fused) { w.outs = off; off = align_up(off + n * 4 * sizeof(float), 256); }
+  if (precoded) {  // fp16 A-operand rows of the permutohedral encoding
+    const size_t ep = (size_t)(a.field.dim_encoding + 15) / 16 * 16;
+    w.rows_half = off; off = align_up(off + n * ep * 2, 256);
   }
   w.isd = off;         off = align_up(off + (size_t)a.num_fields * sizeof(float), 256);
   w.tc = off;
@@ -346,11 +355,14 @@ int ngm_render_rays_fwd(const NgmRenderArgs* a, void* stream_) {
     NGM_CHECK_ARG(a->precision == NGM_PREC_FP32, "unknown precision %d", a->precision);
   }
   char* ws = static_cast<char*>(a->workspace);
-  if (render_fused_tc_ok(*a))  // one fused tcgen05 kernel per render batch
-    return launch_render_fused_tc(*a, ws + w.tc, reinterpret_cast<float*>(ws + w.isd), stream);
+  const bool fused = render_fused_tc_ok(*a);
+  const bool precoded = fused && render_tc_precoded(*a);
+  if (fused && !precoded)  // one fused tcgen05 kernel per render batch
+    return launch_render_fused_tc(*a, ws + w.tc, reinterpret_cast<float*>(ws + w.isd), nullptr, nullptr, nullptr, stream);
 
-  // staged path: the three stage kernels over workspace intermediates (fp32 reference arithmetic,
-  // or fp16 tensor-core field evaluation when a ray has more than 128 samples).
+  // staged path: the stage kernels over workspace intermediates (fp32 reference arithmetic, fp16 tensor-core
+  // field evaluation when a ray has more than 128 samples, or sampler + row encoder ahead of the fused kernel
+  // for the permutohedral encoding).
   const int St = a->num_samples + (a->gt ? a->num_samples_guided : 0);
   NgmSampleArgs s{};
   s.cam = a->cam;
@@ -366,6 +378,23 @@ int ngm_render_rays_fwd(const NgmRenderArgs* a, void* stream_) {
   s.distances = reinterpret_cast<float*>(ws + w.distances);
   s.depths = reinterpret_cast<float*>(ws + w.depths);
   if (int rc = launch_sample_rays(s, stream)) return rc;
+
+  if (precoded) {
+    PermutoRowsArgs e{};
+    e.field = a->field;
+    e.points_world = s.points_world;
+    e.positions = a->positions; e.orientations = a->orientations;
+    e.field_slots = reinterpret_cast<const long long*>(a->field_slots);
+    e.out = reinterpret_cast<uint32_t*>(ws + w.rows_half);
+    e.num_points = num_rays * St;
+    e.points_per_field = a->rays_per_field * St;
+    e.field_radius = a->field_radius;
+    e.scale_mode = a->scale_mode;
+    e.EP = (a->field.dim_encoding + 15) / 16 * 16;
+    if (int rc = launch_permuto_rows_half(e, stream)) return rc;
+    return launch_render_fused_tc(*a, ws + w.tc, reinterpret_cast<float*>(ws + w.isd), ws + w.rows_half, s.distances,
+                                  s.depths, stream);
+  }
 
   NgmFieldFwdArgs f{};
   f.field = a->field;

@@ -50,6 +50,19 @@ inline int check_launch(const char* what) {
 
 int num_sms();
 
+// internal: fp16 A-operand rows of the permutohedral encoding for the tcgen05 renderer (encode.cu)
+struct PermutoRowsArgs {
+  NgmFieldDesc field;
+  const float* points_world;   // (num_points, 3)
+  const float* positions;      // field table
+  const float* orientations;
+  const long long* field_slots;
+  uint32_t* out;               // (num_points, EP / 2) half2 words
+  long long num_points, points_per_field;
+  float field_radius;
+  int scale_mode, EP;
+};
+
 // ---- Philox4x32-10 counter RNG (in-kernel sampling jitter when no jitter tensor is given) ----
 __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
   const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;

@@ -2,6 +2,8 @@
 // permutohedral table gradient.  ngm/positional_encodings.py: NeRF :245-272, Fourier :197-212,
 // Triplane :132-161, permutohedral wrapper :19-66.  The training path (autograd.py) evaluates the MLP
 // with library GEMMs around these; the render kernels encode in-line with the same device functions.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "encodings.cuh"
 
@@ -82,6 +84,61 @@ __global__ void __launch_bounds__(256) permuto_bwd_kernel(NgmEncodeArgs a) {
   }
 }
 
+// Permutohedral A-operand rows for the tcgen05 renderer: world point -> field-local -> 2 features per level -> fp16,
+// one thread per (point, group of four levels), so that the 4 x 4 table gathers of a thread are independent and the
+// whole GPU's warps hide the L2 latency (inside the persistent MMA kernel only 8 warps per SM could).
+// Row layout = the kernel's A operand: EP halves per point (levels, optional raw points, zero padding).
+__global__ void __launch_bounds__(256) permuto_rows_half_kernel(PermutoRowsArgs a) {
+  const NgmFieldDesc& fd = a.field;
+  const int L = fd.permuto_levels, groups = (L + 3) / 4, words = a.EP / 2;
+  const size_t level_elems = ((size_t)1 << fd.permuto_log2_capacity) * 2;
+  const long long total = a.num_points * groups;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(idx % groups);
+    const long long pt = idx / groups;
+    const long long f = pt / a.points_per_field;
+    const long long slot = a.field_slots ? a.field_slots[f] : f;
+    const float* src = a.points_world + pt * 3;
+    float3 x = make_float3(__ldg(src), __ldg(src + 1), __ldg(src + 2));
+    const float* c = a.positions + slot * 3;
+    const float* q = a.orientations + slot * 4;
+    x = make_float3(x.x - __ldg(c), x.y - __ldg(c + 1), x.z - __ldg(c + 2));
+    x = quat_inv_rotate(__ldg(q), __ldg(q + 1), __ldg(q + 2), __ldg(q + 3), x);
+    x = scale_local(x, a.scale_mode, a.field_radius);
+    const float xs[3] = {x.x, x.y, x.z};
+    const float* table = fd.enc_param0 + slot * fd.enc_param0_stride;
+    const float* shift = fd.enc_param1 + slot * fd.enc_param1_stride;
+    uint32_t* row = a.out + pt * words;
+    uint32_t w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int l = 4 * g + i;
+      if (l < L) {
+        float f2[2];
+        permuto_level<2>(xs, table + (size_t)l * level_elems, shift + l * 3, fd.permuto_scale + l * 3,
+                         fd.permuto_log2_capacity, 2, f2);
+        const __half2 h = __floats2half2_rn(f2[0], f2[1]);
+        w[i] = *reinterpret_cast<const uint32_t*>(&h);
+      }
+    }
+    if (4 * g + 4 <= L && (words & 3) == 0) {
+      *reinterpret_cast<uint4*>(row + 4 * g) = make_uint4(w[0], w[1], w[2], w[3]);
+    } else {
+      for (int i = 0; i < 4 && 4 * g + i < L; ++i) row[4 * g + i] = w[i];
+    }
+    if (g == groups - 1) {  // raw points (concat_points) and the zero padding up to the K multiple of 16
+      const float cs = fd.permuto_concat_scaling;
+      for (int k = L; k < words; ++k) {
+        __half2 h = __floats2half2_rn(0.f, 0.f);
+        if (fd.permuto_concat_points && k == L) h = __floats2half2_rn(x.x * cs, x.y * cs);
+        if (fd.permuto_concat_points && k == L + 1) h = __floats2half2_rn(x.z * cs, 0.f);
+        row[k] = *reinterpret_cast<const uint32_t*>(&h);
+      }
+    }
+  }
+}
+
 unsigned grid_for(long long items) {
   long long blocks = (items + 255) / 256;
   const long long cap = (long long)num_sms() * 16;
@@ -95,6 +152,15 @@ int launch_encode_fwd(const NgmEncodeArgs& a, cudaStream_t stream) {
   const long long per_point = fd.encoding == NGM_ENC_PERMUTO ? fd.permuto_levels + 1 : fd.dim_encoding;
   encode_fwd_kernel<<<grid_for((long long)a.num_fields * a.points_per_field * per_point), 256, 0, stream>>>(a);
   return check_launch("encode_fwd_kernel");
+}
+
+int launch_permuto_rows_half(const PermutoRowsArgs& a, cudaStream_t stream) {
+  if (a.num_points == 0) return NGM_OK;
+  const long long items = a.num_points * ((a.field.permuto_levels + 3) / 4);
+  long long blocks = (items + 255) / 256;
+  const long long cap = (long long)num_sms() * 64;  // 8 resident CTAs per SM x 8 rounds, then grid-stride
+  permuto_rows_half_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, stream>>>(a);
+  return check_launch("permuto_rows_half_kernel");
 }
 
 int launch_encode_bwd(const NgmEncodeArgs& a, cudaStream_t stream) {

@@ -146,7 +146,10 @@ struct TcParams {
   const float* points;
   long long points_per_field;
   float* out;
-  const __half* raw_a;  // debug: A operand given directly, (num_fields*points_per_field, EP)
+  const __half* raw_a;  // layer-0 A operand given directly, (num_fields*points_per_field, EP): debug GEMM, and the
+                        // pre-encoded permutohedral rows of the renderer (then raw_dist / raw_depth come with it)
+  const float* raw_dist;   // MODE 0 with raw_a: sample distances / depths (num_rays, St) of the sampler kernel
+  const float* raw_depth;
   // MODE 0 (fused render)
   NgmCamera cam;
   const long long* ijs;
@@ -689,6 +692,8 @@ __global__ void __launch_bounds__(threads_of(MODE), 1) tc_kernel(const TcParams 
       tev_role(2 + 2 * s + h, lane == 0 && qwarp == 2);  // one leader thread per half
 
       const uint32_t a0_addr = d_addr + kStageCol;  // staging columns: layer-0 A operand of the NEXT tile
+      // layer-0 A operand read from HBM (pre-encoded rows): compiled out of the fused NeRF renderer
+      const bool raw = (MODE == 1 || OCT == 0) && p.raw_a != nullptr;
       float3 fx = make_float3(0.f, 0.f, 0.f);        // sample point of this row for the next tile (fe_a -> fe_b)
 
       // Front end of tile `ti` (h == 1 threads), in two parts that are slotted into the waits for
@@ -699,7 +704,7 @@ __global__ void __launch_bounds__(threads_of(MODE), 1) tc_kernel(const TcParams 
         fx = make_float3(0.f, 0.f, 0.f);
         if (MODE == 1) {
           const long long gp = tile_in_field * 128 + row;
-          if (!p.raw_a && gp < p.points_per_field) {
+          if (!raw && gp < p.points_per_field) {
             const float* src = p.points + (f * p.points_per_field + gp) * 3;
             float3 x = make_float3(__ldg(src), __ldg(src + 1), __ldg(src + 2));
             if (p.positions) {
@@ -721,7 +726,12 @@ __global__ void __launch_bounds__(threads_of(MODE), 1) tc_kernel(const TcParams 
           const float nr = rp[7], fr = rp[8], gt = rp[9];
           const int S = p.S, G = p.G, St = p.St;
           float d = 0.f;
-          if (G > 0) {
+          float z = 0.f;
+          if (raw) {  // samples and their encodings were produced by the sampler + encode kernels
+            const long long sample = ray * St + k;
+            if (valid) { d = __ldg(p.raw_dist + sample); z = __ldg(p.raw_depth + sample); }
+            fx.x = __int_as_float(valid ? (int)sample : -1);  // row of the pre-encoded A operand, for fe_b
+          } else if (G > 0) {
             // depth-guided merge (run_mapping.py:521-545): own distance + rank, then exchange by rank
             if (valid) {
               float glo, ghi;
@@ -747,8 +757,7 @@ __global__ void __launch_bounds__(threads_of(MODE), 1) tc_kernel(const TcParams 
                                               : __fsub_rn(1.0f, __fmul_rn(p.inv_S, (float)(S - k)));
             d = __fadd_rn(__fadd_rn(__fmul_rn(rp[11], p.jit.coarse(ray, k, S, St)), __fmul_rn(lin, __fsub_rn(fr, nr))), nr);
           }
-          float z = 0.f;
-          if (valid) {
+          if (valid && !raw) {
             fx = make_float3(fmaf(d, rp[3], rp[0]), fmaf(d, rp[4], rp[1]), fmaf(d, rp[5], rp[2]));
             z = d * rp[6];
           }
@@ -757,10 +766,18 @@ __global__ void __launch_bounds__(threads_of(MODE), 1) tc_kernel(const TcParams 
         tev(ev_id(1, s, 1, 0));
       };
       auto fe_b = [&](int ti) {
-        if (MODE == 1 && p.raw_a) {
-          const long long gp = (tile0_in_field + ti) * 128 + row;
-          const bool valid = gp < p.points_per_field;
-          const long long rr = valid ? f * p.points_per_field + gp : 0;
+        if (raw) {
+          bool valid;
+          long long rr;
+          if (MODE == 1) {
+            const long long gp = (tile0_in_field + ti) * 128 + row;
+            valid = gp < p.points_per_field;
+            rr = valid ? f * p.points_per_field + gp : 0;
+          } else {
+            const int sample = __float_as_int(fx.x);
+            valid = sample >= 0;
+            rr = valid ? sample : 0;
+          }
           const uint32_t* src = reinterpret_cast<const uint32_t*>(p.raw_a + rr * p.EP);
           for (int c = 0; c < p.EP / 2; c += 8) {
             uint32_t w[8];
@@ -877,7 +894,7 @@ __global__ void __launch_bounds__(threads_of(MODE), 1) tc_kernel(const TcParams 
           }
           if (h == 1 && has_next) {
             if (l == 0) fe_a(ti + 2, ray_n + 1, npar);
-            if (OCT > 0 || (MODE == 1 && p.raw_a)) {
+            if (OCT > 0 || raw) {
               if (l == step_b) fe_b(ti + 2);
             } else {
               fe_permuto(l, real ? (L < 4 ? (L < 1 ? 1 : L) : 4) : 1);
@@ -1087,8 +1104,23 @@ bool render_fused_tc_ok(const NgmRenderArgs& a) {
          field_tc_supported(a.field, &why);
 }
 
-int launch_render_fused_tc(const NgmRenderArgs& a, void* tc_ws, float* isd_ws, cudaStream_t stream) {
+// The permutohedral renderer runs as sampler kernel -> row encoder (encode.cu, whole-GPU occupancy for the L2
+// table gathers) -> this kernel with the A operand, distances and depths read back (1.3 GB of HBM traffic per
+// 640x480x64 frame, 0.4 ms, against 17 ms saved); NGM_TC_PERMUTO_INKERNEL=1 keeps the in-kernel front end.
+bool render_tc_precoded(const NgmRenderArgs& a) {
+  const char* e = getenv("NGM_TC_PERMUTO_INKERNEL");  // read per call: tests compare both front ends
+  const bool inkernel = e && e[0] == '1';
+  const long long St = a.num_samples + (a.gt ? a.num_samples_guided : 0);
+  return a.field.encoding == NGM_ENC_PERMUTO && !inkernel &&
+         (long long)a.num_fields * a.rays_per_field * St < (1ll << 31);
+}
+
+int launch_render_fused_tc(const NgmRenderArgs& a, void* tc_ws, float* isd_ws, const void* rows_half, const float* dist,
+                           const float* depth, cudaStream_t stream) {
   TcParams p{};
+  p.raw_a = static_cast<const __half*>(rows_half);
+  p.raw_dist = dist;
+  p.raw_depth = depth;
   if (int rc = fill_common(p, a.field, a.num_fields, a.positions, a.orientations, a.field_slots, a.scale_mode,
                            a.field_radius, tc_ws, stream))
     return rc;

@@ -232,12 +232,16 @@ def test_fieldset_permuto_fp16_vs_oracle(W, L, levels, concat, n):
     assert e.max().item() < 2e-2 * scale and e.mean().item() < 3e-3 * scale, (e.max().item(), e.mean().item(), scale)
 
 
+@pytest.mark.parametrize("inkernel", [False, True])
 @pytest.mark.parametrize("L,W,S", [(4, 128, 64), (1, 32, 24), (2, 64, 16)])
-def test_render_fused_permuto_fp16_vs_fp32(L, W, S):
+def test_render_fused_permuto_fp16_vs_fp32(L, W, S, inkernel, monkeypatch):
     """Fused tcgen05 render with the permutohedral encoding (the reference's default encoding; 1 hidden layer x 32
     is its default MLP, neural_graph_map.yaml:6-17) against the fp32 kernels on identical rays and jitter."""
     import neural_graph_mapping_b200 as ngm
 
+    # default: sampler kernel -> row encoder -> fused kernel reading the A operand; the env var keeps the
+    # in-kernel front end (table gathers in the MMA waits)
+    monkeypatch.setenv("NGM_TC_PERMUTO_INKERNEL", "1" if inkernel else "0")
     meta, a = G.load("vmap_guided_nrgbd")
     g = torch.Generator().manual_seed(L * 100 + W)
     F, Rr = 3, 300
