@@ -48,7 +48,7 @@ int launch_permuto_rows_half(const PermutoRowsArgs& a, cudaStream_t stream);
 int launch_tc_gemm_debug(const NgmFieldDesc& fd, const void* a_half, long long rows, float* out, void* workspace,
                          cudaStream_t stream);
 
-size_t knn_workspace_bytes(long long num_points, int num_knn, int num_fields);
+size_t knn_workspace_bytes(const NgmKnnFwdArgs& a);
 int launch_fieldset_knn(const NgmKnnFwdArgs& a, cudaStream_t stream);
 
 int launch_composite_bwd(const NgmCompositeBwdArgs& b, cudaStream_t stream);
@@ -267,7 +267,7 @@ int ngm_encode_bwd(const NgmEncodeArgs* a, void* stream) {
 int ngm_fieldset_knn_workspace_bytes(const NgmKnnFwdArgs* a, size_t* out) {
   NGM_CHECK_ARG(a && out, "null args");
   NGM_CHECK_ARG(a->num_points >= 0 && a->num_fields >= 1 && a->num_knn >= 1, "bad sizes");
-  *out = knn_workspace_bytes(a->num_points, a->num_knn, a->num_fields);
+  *out = knn_workspace_bytes(*a);
   return NGM_OK;
 }
 
@@ -284,8 +284,13 @@ int ngm_fieldset_knn_fwd(const NgmKnnFwdArgs* a, void* stream) {
   NGM_CHECK_ARG(a->scale_mode >= NGM_SCALE_NO && a->scale_mode <= NGM_SCALE_UNIT_CUBE, "scale_mode=%d is not available.",
                 a->scale_mode);
   NGM_CHECK_ARG(((uintptr_t)a->out & 15) == 0, "out must be 16-byte aligned");
-  NGM_UNSUPPORTED(a->precision != NGM_PREC_FP32, "the kNN path evaluates the fields in fp32 in this revision");
-  const size_t need = knn_workspace_bytes(a->num_points, a->num_knn, a->num_fields);
+  if (a->precision == NGM_PREC_FP16) {
+    const char* why = nullptr;
+    NGM_UNSUPPORTED(!field_tc_supported(a->field, &why), "fp16 tensor-core path unsupported: %s", why);
+  } else {
+    NGM_CHECK_ARG(a->precision == NGM_PREC_FP32, "unknown precision %d", a->precision);
+  }
+  const size_t need = knn_workspace_bytes(*a);
   if (need > a->workspace_bytes || !a->workspace) {
     set_error("workspace too small: need %zu B, have %zu B", need, a->workspace_bytes);
     return NGM_ERR_WORKSPACE;

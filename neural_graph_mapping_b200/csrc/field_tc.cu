@@ -148,6 +148,12 @@ struct TcParams {
   float* out;
   const __half* raw_a;  // layer-0 A operand given directly, (num_fields*points_per_field, EP): debug GEMM, and the
                         // pre-encoded permutohedral rows of the renderer (then raw_dist / raw_depth come with it)
+  // MODE 1 gather mode (kNN path, ngm/models.py:386-396): rows are (point, neighbour) entries bucketed by field;
+  // the tile count per field is data dependent and stays on the device (knn.cu)
+  const int* entries;        // [sum counts]  entry = point * K + k  (also the output row)
+  const int* entry_offsets;  // [F + 1]
+  const int* tile_offsets;   // [F + 1]  tiles of 128 entries per field
+  int knn_k;
   const float* raw_dist;   // MODE 0 with raw_a: sample distances / depths (num_rays, St) of the sampler kernel
   const float* raw_depth;
   // MODE 0 (fused render)
@@ -591,8 +597,10 @@ __global__ void __launch_bounds__(threads_of(MODE), 1) tc_kernel(const TcParams 
   const uint32_t tmem_base = sm.tmem_base;
 
   // contiguous, balanced tile range of this CTA
-  const long long t_begin = p.total_tiles * blockIdx.x / gridDim.x;
-  const long long t_end = p.total_tiles * (blockIdx.x + 1) / gridDim.x;
+  const bool gather = MODE == 1 && p.entries != nullptr;
+  const long long total_tiles = gather ? (long long)__ldg(p.tile_offsets + p.num_fields) : p.total_tiles;
+  const long long t_begin = total_tiles * blockIdx.x / gridDim.x;
+  const long long t_end = total_tiles * (blockIdx.x + 1) / gridDim.x;
 
   uint32_t w_phase = 0;
   int ray_n0 = 0, ray_n1 = 0;  // tiles of slot 0 / 1 started by this CTA so far (ray-parameter ring position = n & 3)
@@ -609,11 +617,24 @@ __global__ void __launch_bounds__(threads_of(MODE), 1) tc_kernel(const TcParams 
 
   long long t = t_begin;
   while (t < t_end) {
-    const long long f = t / p.tiles_per_field;
-    long long seg_end = (f + 1) * p.tiles_per_field;
+    long long f, seg_end, seg_begin;
+    if (gather) {  // largest f with tile_offsets[f] <= t (skips fields without entries)
+      int lo = 0, hi = p.num_fields;
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(p.tile_offsets + mid) <= t) lo = mid; else hi = mid;
+      }
+      f = lo;
+      seg_begin = __ldg(p.tile_offsets + lo);
+      seg_end = __ldg(p.tile_offsets + lo + 1);
+    } else {
+      f = t / p.tiles_per_field;
+      seg_begin = f * p.tiles_per_field;
+      seg_end = seg_begin + p.tiles_per_field;
+    }
     if (seg_end > t_end) seg_end = t_end;
     const int ntiles = (int)(seg_end - t);
-    const long long tile0_in_field = t - f * p.tiles_per_field;
+    const long long tile0_in_field = t - seg_begin;
 
     // ---- stage this field's weight image (TMA engine) ----
     if (tid == 0) {
@@ -704,12 +725,19 @@ __global__ void __launch_bounds__(threads_of(MODE), 1) tc_kernel(const TcParams 
         fx = make_float3(0.f, 0.f, 0.f);
         if (MODE == 1) {
           const long long gp = tile_in_field * 128 + row;
-          if (!raw && gp < p.points_per_field) {
-            const float* src = p.points + (f * p.points_per_field + gp) * 3;
+          bool ok = !raw && gp < p.points_per_field;
+          const float* src = p.points + (f * p.points_per_field + gp) * 3;
+          if (gather) {
+            const int e = __ldg(p.entry_offsets + f) + (int)gp;
+            ok = e < __ldg(p.entry_offsets + f + 1);
+            if (ok) src = p.points + (long long)(__ldg(p.entries + e) / p.knn_k) * 3;
+          }
+          if (ok) {
             float3 x = make_float3(__ldg(src), __ldg(src + 1), __ldg(src + 2));
             if (p.positions) {
-              const float* c = p.positions + slot * 3;
-              const float* q = p.orientations + slot * 4;
+              const long long pose = gather ? f : slot;  // gather mode: poses are already those of the F fields
+              const float* c = p.positions + pose * 3;
+              const float* q = p.orientations + pose * 4;
               x = make_float3(x.x - __ldg(c), x.y - __ldg(c + 1), x.z - __ldg(c + 2));
               x = quat_inv_rotate(__ldg(q), __ldg(q + 1), __ldg(q + 2), __ldg(q + 3), x);
             }
@@ -850,8 +878,13 @@ __global__ void __launch_bounds__(threads_of(MODE), 1) tc_kernel(const TcParams 
               if (h == 0) {
                 if (MODE == 1) {
                   const long long gp = tile_in_field * 128 + row;
-                  const bool valid = gp < p.points_per_field;
+                  bool valid = gp < p.points_per_field;
                   float* o = p.out + (f * p.points_per_field + gp) * p.dim_out;
+                  if (gather) {
+                    const int e = __ldg(p.entry_offsets + f) + (int)gp;
+                    valid = e < __ldg(p.entry_offsets + f + 1);
+                    if (valid) o = p.out + (long long)__ldg(p.entries + e) * p.dim_out;
+                  }
                   for (int c = 0; c < p.im.layer[L].n_pad; c += 16) {
                     uint32_t v[16];
                     ptx::tmem_ld16(d_addr + c, v);
@@ -1044,6 +1077,26 @@ int launch_field_fwd_tc(const NgmFieldFwdArgs& a, cudaStream_t stream) {
   p.tiles_per_field = (a.points_per_field + 127) / 128;
   p.total_tiles = p.tiles_per_field * a.num_fields;
   const int grid = tc_grid(p.total_tiles);
+  return launch_tc<1>(p, a.field.encoding == NGM_ENC_PERMUTO ? 0 : a.field.nerf_num_octaves, tc_smem_bytes(p.im), grid, stream);
+}
+
+// kNN path: every tile is 128 (point, neighbour) entries of ONE field; the tile count lives in tile_offsets[F]
+int launch_field_fwd_tc_gather(const NgmFieldFwdArgs& a, const int* entries, const int* entry_offsets,
+                               const int* tile_offsets, int knn_k, long long max_tiles, cudaStream_t stream) {
+  TcParams p{};
+  if (int rc = fill_common(p, a.field, a.num_fields, a.positions, a.orientations, a.field_slots, a.scale_mode,
+                           a.field_radius, a.workspace, stream))
+    return rc;
+  p.points = a.points;
+  p.out = a.out;
+  p.entries = entries;
+  p.entry_offsets = entry_offsets;
+  p.tile_offsets = tile_offsets;
+  p.knn_k = knn_k;
+  p.points_per_field = 1ll << 40;  // rows are bounded by the entry ranges
+  p.tiles_per_field = 1;
+  p.total_tiles = max_tiles;
+  const int grid = tc_grid(max_tiles);
   return launch_tc<1>(p, a.field.encoding == NGM_ENC_PERMUTO ? 0 : a.field.nerf_num_octaves, tc_smem_bytes(p.im), grid, stream);
 }
 

@@ -16,6 +16,9 @@ namespace ngm {
 
 int launch_field_fwd_simt_gather(const NgmFieldFwdArgs& a, const int* entries, const int* entry_offsets,
                                  const int* tile_offsets, int knn_k, long long max_tiles, cudaStream_t stream);
+int launch_field_fwd_tc_gather(const NgmFieldFwdArgs& a, const int* entries, const int* entry_offsets,
+                               const int* tile_offsets, int knn_k, long long max_tiles, cudaStream_t stream);
+size_t field_tc_workspace_bytes(const NgmFieldDesc& fd, int num_fields);
 
 namespace {
 
@@ -31,12 +34,13 @@ struct KnnWs {
   int* cursors;        // [F]
   int* entries;        // [N*K]
   float* pair_out;     // [N*K*4]
+  void* tc;            // fp16 path: per-field weight images
   size_t total;
 };
 
 size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 
-KnnWs carve(void* base, long long N, int K, int F) {
+KnnWs carve(void* base, long long N, int K, int F, size_t tc_bytes) {
   KnnWs w{};
   char* b = static_cast<char*>(base);
   size_t o = 0;
@@ -49,8 +53,27 @@ KnnWs carve(void* base, long long N, int K, int F) {
   w.cursors = reinterpret_cast<int*>(take((size_t)(F + 1) * 4));
   w.entries = reinterpret_cast<int*>(take((size_t)N * K * 4));
   w.pair_out = reinterpret_cast<float*>(take((size_t)N * K * 16));
+  w.tc = take(tc_bytes);
   w.total = o;
   return w;
+}
+
+// counters[f] += 1 for every active lane, one atomic per distinct field per warp (neighbouring points share their
+// nearest fields, so a warp usually holds 1-3 distinct values: 40 M same-address atomics per frame become ~2 M).
+// Returns the lane's slot.  Must be reached by all 32 lanes.
+__device__ __forceinline__ int warp_aggregated_inc(int* counters, int f, bool active) {
+  const unsigned live = __ballot_sync(0xffffffffu, active);
+  int slot = -1;
+  if (active) {
+    const unsigned peers = __match_any_sync(live, f);
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(peers) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(counters + f, __popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    slot = base + __popc(peers & ((1u << lane) - 1u));
+  }
+  return slot;
 }
 
 __global__ void __launch_bounds__(256) knn_assign_kernel(const float* __restrict__ points, long long N,
@@ -89,9 +112,8 @@ __global__ void __launch_bounds__(256) knn_assign_kernel(const float* __restrict
       }
     }
   }
-  if (!live) return;
   const float d0 = sqrtf(bd[0]);
-  const bool inside = d0 < radius;  // models.py:369: only the nearest centre is tested
+  const bool inside = live && d0 < radius;  // models.py:369: only the nearest centre is tested
   // softmax(-distance_factor * d) over the K neighbours (models.py:384)
   float logit[kMaxK], m = -INFINITY;
 #pragma unroll
@@ -103,10 +125,12 @@ __global__ void __launch_bounds__(256) knn_assign_kernel(const float* __restrict
     if (j < K) { logit[j] = expf(logit[j] - m); sum += logit[j]; }
 #pragma unroll
   for (int j = 0; j < kMaxK; ++j) {
-    if (j < K) {
-      pair_field[i * K + j] = inside ? bi[j] : -1;
-      pair_w[i * K + j] = logit[j] / sum;
-      if (inside) atomicAdd(counts + bi[j], 1);
+    if (j < K) {  // K is warp-uniform: every lane reaches the warp collective
+      if (live) {
+        pair_field[i * K + j] = inside ? bi[j] : -1;
+        pair_w[i * K + j] = logit[j] / sum;
+      }
+      warp_aggregated_inc(counts, bi[j], inside);
     }
   }
 }
@@ -149,11 +173,9 @@ __global__ void __launch_bounds__(256) knn_scatter_kernel(const int* __restrict_
                                                           const int* __restrict__ entry_offsets, int* __restrict__ cursors,
                                                           int* __restrict__ entries) {
   const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (e >= NK) return;
-  const int f = pair_field[e];
-  if (f < 0) return;
-  const int pos = atomicAdd(cursors + f, 1);
-  entries[entry_offsets[f] + pos] = (int)e;
+  const int f = e < NK ? pair_field[e] : -1;
+  const int pos = warp_aggregated_inc(cursors, f, f >= 0);
+  if (f >= 0) entries[entry_offsets[f] + pos] = (int)e;
 }
 
 __global__ void __launch_bounds__(256) knn_blend_kernel(const int* __restrict__ pair_field, const float* __restrict__ pair_w,
@@ -175,9 +197,13 @@ __global__ void __launch_bounds__(256) knn_blend_kernel(const int* __restrict__ 
 
 }  // namespace
 
-size_t knn_workspace_bytes(long long num_points, int num_knn, int num_fields) {
-  const int K = num_knn < num_fields ? num_knn : num_fields;
-  return carve(nullptr, num_points, K > 0 ? K : 1, num_fields).total;
+static size_t tc_bytes_of(const NgmKnnFwdArgs& a) {
+  return a.precision == NGM_PREC_FP16 ? field_tc_workspace_bytes(a.field, a.num_fields) : 0;
+}
+
+size_t knn_workspace_bytes(const NgmKnnFwdArgs& a) {
+  const int K = a.num_knn < a.num_fields ? a.num_knn : a.num_fields;
+  return carve(nullptr, a.num_points, K > 0 ? K : 1, a.num_fields, tc_bytes_of(a)).total;
 }
 
 int launch_fieldset_knn(const NgmKnnFwdArgs& a, cudaStream_t stream) {
@@ -185,7 +211,7 @@ int launch_fieldset_knn(const NgmKnnFwdArgs& a, cudaStream_t stream) {
   const int F = a.num_fields;
   const int K = a.num_knn < F ? a.num_knn : F;  // models.py:355-358
   if (N == 0) return NGM_OK;
-  const KnnWs w = carve(a.workspace, N, K, F);
+  const KnnWs w = carve(a.workspace, N, K, F, tc_bytes_of(a));
   NGM_CUDA(cudaMemsetAsync(w.counts, 0, (size_t)(F + 1) * sizeof(int), stream));
   const unsigned pb = (unsigned)((N + 255) / 256);
   knn_assign_kernel<<<pb, 256, 0, stream>>>(a.points, N, a.positions, F, K, a.field_radius, a.distance_factor,
@@ -208,9 +234,14 @@ int launch_fieldset_knn(const NgmKnnFwdArgs& a, cudaStream_t stream) {
   f.field_radius = a.scale_radius;
   f.num_fields = F;
   f.scale_mode = a.scale_mode;
-  f.precision = NGM_PREC_FP32;
+  f.precision = a.precision;
+  f.workspace = w.tc;
   const long long max_tiles = (NK + 127) / 128 + F;  // upper bound of sum_f ceil(count_f / 128)
-  if (int rc = launch_field_fwd_simt_gather(f, w.entries, w.entry_offsets, w.tile_offsets, K, max_tiles, stream)) return rc;
+  if (a.precision == NGM_PREC_FP16) {  // tcgen05 field kernel in gather mode
+    if (int rc = launch_field_fwd_tc_gather(f, w.entries, w.entry_offsets, w.tile_offsets, K, max_tiles, stream)) return rc;
+  } else if (int rc = launch_field_fwd_simt_gather(f, w.entries, w.entry_offsets, w.tile_offsets, K, max_tiles, stream)) {
+    return rc;
+  }
 
   knn_blend_kernel<<<pb, 256, 0, stream>>>(w.pair_field, w.pair_w, w.pair_out, N, K, a.outside_value, a.out);
   return check_launch("knn_blend_kernel");

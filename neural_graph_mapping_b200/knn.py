@@ -11,8 +11,11 @@ from . import _lib, models
 from .camera import sample_rays
 
 
-def fieldset_forward_knn(model, query_points, field_positions, field_orientations, field_ids, field_radius):
-    """``ngm_fieldset_knn_fwd``: (..., 3) world points -> (..., 4)."""
+def fieldset_forward_knn(model, query_points, field_positions, field_orientations, field_ids, field_radius,
+                         precision=None):
+    """``ngm_fieldset_knn_fwd``: (..., 3) world points -> (..., 4).  ``precision`` "fp16" evaluates the
+    bucketed (point, neighbour) entries with the tcgen05 field kernel in gather mode."""
+    precision = precision or getattr(model, "precision", None) or models.get_default_precision()
     if field_positions is None or field_orientations is None:
         raise ValueError("the kNN path needs field_positions and field_orientations")
     params = model.all_fields_params
@@ -42,7 +45,7 @@ def fieldset_forward_knn(model, query_points, field_positions, field_orientation
             a.outside_value = float(model._outside_value)
             a.num_knn = int(model._num_knn)
             a.scale_mode = _lib.SCALE[model._scale_mode]
-            a.precision = _lib.PREC["fp32"]
+            a.precision = _lib.PREC[precision]
             need = C.c_size_t(0)
             _lib.check(_lib.lib.ngm_fieldset_knn_workspace_bytes(C.byref(a), C.byref(need)))
             ws = torch.empty(max(need.value, 16), device=dev, dtype=torch.uint8)
@@ -54,7 +57,7 @@ def fieldset_forward_knn(model, query_points, field_positions, field_orientation
 def render_rays_knn(driver, ijs, c2ws, camera, field_ids, near, far, gt, overwrite, jitter):
     """``_render_ijs`` with use_vmap=False (ngm/run_mapping.py:586-595): sampler stage -> kNN
     field set (in blocks of ``_block_size`` points, like utils.batched_evaluation) -> compositor."""
-    from .renderer import Prediction, _next_seed, composite
+    from .renderer import Prediction, _next_seed, _precision, composite
 
     model = driver._model
     dev = ijs.device
@@ -79,7 +82,7 @@ def render_rays_knn(driver, ijs, c2ws, camera, field_ids, near, far, gt, overwri
         outs = []
         for s0 in range(0, pts.shape[0], int(driver._block_size)):
             outs.append(fieldset_forward_knn(model, pts[s0:s0 + int(driver._block_size)], positions, orientations,
-                                             field_ids, None))
+                                             field_ids, None, _precision(driver)))
         o = torch.cat(outs) if len(outs) > 1 else outs[0]
         n = dist.numel() // St
         gt_t = None if gt is None else _lib.dev_f32(gt, "gt").expand(leading).reshape(-1).contiguous()

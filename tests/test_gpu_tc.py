@@ -273,3 +273,61 @@ def test_render_fused_permuto_fp16_vs_fp32(L, W, S, inkernel, monkeypatch):
     assert (p16.rgbds[..., 3] - p32.rgbds[..., 3]).abs().mean().item() < 5e-3
     assert (p16.term_probs - p32.term_probs).abs().mean().item() < 3e-3
     assert p32.term_probs.std().item() > 1e-3, "degenerate scene: the comparison would be vacuous"
+
+
+@pytest.mark.parametrize("F,K,n,W,L", [(1, 2, 300, 16, 1), (40, 2, 5000, 128, 4), (300, 3, 4000, 64, 2)])
+def test_fieldset_knn_fp16_vs_oracle(F, K, n, W, L):
+    """kNN blend path with the tcgen05 field kernel in gather mode: fields without entries, a data-dependent tile
+    count per field, field_ids remap; against the oracle (fp16 tolerance)."""
+    import neural_graph_mapping_b200 as ngm
+
+    g = torch.Generator().manual_seed(F * 10 + K)
+    spec = R.FieldSpec("nerf", {"dim_in": 3, "num_octaves": 4}, L, 4, W, "no")
+    n_tab = min(F, 8)
+    params = R.stack_params([R.init_field_params(spec, g) for _ in range(n_tab)])
+    pos = torch.randn(F, 3, generator=g) * (1.0 if F < 100 else 4.0)
+    q = torch.randn(F, 4, generator=g)
+    ori = q / q.norm(dim=-1, keepdim=True)
+    fid = torch.randint(0, n_tab, (F,), generator=g)
+    pts = torch.randn(n, 3, generator=g) * (1.5 if F < 100 else 4.0)
+    rs = R.RenderSpec(field_radius=1.0, scale_mode="unit_cube", num_knn=K, distance_factor=10.0, outside_value=1.0)
+    ref = R.fieldset_forward_knn(pts, pos, ori, fid, spec, params, rs)
+    model = ngm.NeuralFieldSet(3, "neural_graph_mapping_b200.models.NeuralField",
+                               {"encoding_type": "neural_graph_mapping_b200.positional_encodings.PositionalEncodingNeRF",
+                                "encoding_kwargs": {"dim_in": 3, "num_octaves": 4}, "num_layers": L, "dim_out": 4,
+                                "dim_mlp_out": W}, K, 10.0, 1.0, field_radius=1.0, scale_mode="unit_cube",
+                               precision="fp16").to(DEV)
+    model.all_fields_params = {k: v.to(DEV) for k, v in params.items()}
+    with torch.no_grad():
+        y = model(pts.to(DEV), pos.to(DEV), ori.to(DEV), fid.to(DEV), False)
+    d = torch.cdist(pts, pos)
+    srt = torch.sort(d, dim=-1)[0]
+    margin = torch.ones(n, dtype=torch.bool)
+    for j in range(min(K, F - 1)):
+        margin &= (srt[:, j + 1] - srt[:, j]).abs() > 1e-5
+    margin &= (srt[:, 0] - 1.0).abs() > 1e-5
+    assert torch.isfinite(y).all()
+    inside = (ref != 1.0).any(-1)
+    assert torch.equal((y.cpu() != 1.0).any(-1)[margin], inside[margin]), "inside/outside classification differs"
+    scale = ref[inside].abs().max().item()
+    e = (y.cpu()[margin] - ref[margin]).abs()
+    assert e.max().item() < 2e-2 * scale and e.mean().item() < 3e-3 * scale, (e.max().item(), e.mean().item(), scale)
+
+
+@pytest.mark.parametrize("name", G.KNN_CASES)
+def test_render_knn_fp16_golden(name):
+    """_render_ijs(use_vmap=False) -- what the untouched driver calls for keyframe renders and evaluation
+    (run_mapping.py:429) -- with fp16 field evaluation, against the fp32 reference's golden outputs."""
+    import neural_graph_mapping_b200 as ngm
+
+    meta, a = G.load(name)
+    st = make_state(meta, a, DEV, "fp16")
+    st.eval()
+    cam = ngm.Camera(**meta["camera"])
+    with torch.no_grad():
+        p = st._render_ijs(a["ijs"].to(DEV), a["c2ws"].to(DEV), cam, jitter=a["jitter"].to(DEV))
+    col = (p.rgbds[..., :3].cpu() - a["out_rgbds"][..., :3]).abs()
+    dep = (p.rgbds[..., 3].cpu() - a["out_rgbds"][..., 3]).abs()
+    assert col.mean().item() < 2e-3, f"colour L1 {col.mean().item():.2e} (max {col.max().item():.2e})"
+    assert dep.mean().item() < 5e-3, f"depth L1 {dep.mean().item():.2e} (max {dep.max().item():.2e})"
+    assert (p.term_probs.cpu() - a["out_term_probs"]).abs().mean().item() < 3e-3

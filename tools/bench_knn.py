@@ -1,0 +1,37 @@
+"""Secondary measurement: the driver's eval path -- render_image / _render_ijs(use_vmap=False), K=2 blend over all
+fields (ngm/run_mapping.py:402-437, models.py:347-405) -- on the bench.py scene: 640x480 pixels x 64 samples,
+75 fields, NeRF-8 + 4x128 MLP.  fp32 = FFMA field kernel, fp16 = tcgen05 field kernel in gather mode."""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+import bench  # noqa: E402
+import neural_graph_mapping_b200 as ngm  # noqa: E402
+
+dev = "cuda:0"
+sc = bench.synthetic_scene(1234)
+cam = ngm.Camera(**bench.CAMERA)
+ijs = sc["ijs"].reshape(-1, 2).to(dev)
+near, far = sc["near"].reshape(-1).to(dev), sc["far"].reshape(-1).to(dev)
+c2w = sc["c2w"].to(dev)
+for prec, reps in (("fp16", 5), ("fp32", 1)):
+    st = ngm.RenderState(bench.config_dict(dev, prec))
+    st.set_fields(sc["params"], sc["positions"], sc["orientations"])
+    ts = []
+    with torch.no_grad():
+        for i in range(reps + 1):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            p = st._render_ijs(ijs, c2w, cam, None, False, near, far)
+            e1.record()
+            torch.cuda.synchronize()
+            if i > 0:
+                ts.append(e0.elapsed_time(e1))
+    ms = sum(ts) / len(ts)
+    print(json.dumps({"path": "kNN (use_vmap=False), K=2, 75 fields, 307200 rays x 64", "precision": prec,
+                      "ms_per_frame": round(ms, 3), "rays_per_s": round(307200 / ms * 1e3),
+                      "inside_fraction": round(float((p.term_probs > 0).float().mean()), 3)}), flush=True)
