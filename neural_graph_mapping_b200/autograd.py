@@ -131,7 +131,9 @@ def encode(proto, params: Dict[str, torch.Tensor], local: torch.Tensor) -> torch
 # MLP over stacked per-field parameters (ngm/models.py:143-182 under torch.vmap)
 # ------------------------------------------------------------------------------------------
 def field_forward(proto, params: Dict[str, torch.Tensor], local: torch.Tensor) -> torch.Tensor:
-    """(F, N, 3) field-local points -> (F, N, dim_out); differentiable in ``params``."""
+    """(F, N, 3) field-local points -> (F, N, dim_out); differentiable in ``params``.  Always fp32: the
+    upstream gradients of mean-reduced losses sit far below the fp16 range, so fp16-operand backward GEMMs would
+    need loss scaling the reference's training loop does not have (measured: 1.5x faster, gradients off)."""
     enc = outs = encode(proto, params, local)
     E = proto._dim_encoding
     for i in range(proto._num_layers + 1):
@@ -246,7 +248,7 @@ def _fill_composite_args(a, pk, isd, dist, depth, gt, cfg) -> None:
 # the training-time _render_ijs (use_vmap=True)
 # ------------------------------------------------------------------------------------------
 def render_rays_vmap(driver, camera, ijs, c2ws, params, positions, orientations, near, far, gt, overwrite,
-                     jitter, jitter_guided, seed):
+                     jitter, jitter_guided, seed, precision="fp32"):
     """Differentiable twin of the fused renderer; returns the six ``Prediction`` members."""
     from .camera import sample_rays
 
@@ -264,7 +266,7 @@ def render_rays_vmap(driver, camera, ijs, c2ws, params, positions, orientations,
             seed=seed, want_world=True, want_depth=True)
         local = world_to_local(world.view(F, R * St, 3), _lib.dev_f32(positions, "positions"),
                                _lib.dev_f32(orientations, "orientations"), model._scale_mode, model._field_radius)
-    outs = field_forward(proto, params, local)  # (F, R*St, 4), differentiable in params
+    outs = field_forward(proto, params, local)  # (F, R*St, 4), differentiable in params (fp32 whatever `precision`)
     mode = driver._geometry_mode
     isd = None
     if mode == "neus":

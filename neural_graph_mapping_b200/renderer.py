@@ -110,7 +110,7 @@ def render_rays(
             raise ValueError("out= is not supported on the differentiable path")
         return Prediction(*ag.render_rays_vmap(
             driver, camera, ijs, c2ws, params, positions, orientations, near_distances, far_distances, gt_distances,
-            overwrite, jitter, jitter_guided, 0 if jitter is not None else _next_seed()))
+            overwrite, jitter, jitter_guided, 0 if jitter is not None else _next_seed(), _precision(driver)))
     with torch.no_grad(), torch.cuda.device(dev):
         a.field, k2 = proto.field_desc(params, True)
         keep += k2

@@ -164,3 +164,4 @@ def test_training_field_forward_golden():
         e.points, e.out = xx.data_ptr(), out.data_ptr()
         _lib.check(_lib.lib.ngm_encode_fwd(C.byref(e), _lib.stream_ptr(torch.device(DEV))))
         assert torch.allclose(out, enc_t, atol=2e-5, rtol=2e-5), f"{name}: ngm_encode_fwd vs torch encoding"
+
