@@ -969,8 +969,8 @@ int nerf_octaves_supported(int o) { return o == 4 || o == 8; }
 // one persistent CTA per SM; NGM_TC_MAX_CTAS (tests) caps the grid so that small problems exercise the
 // multi-round / multi-segment paths of a CTA
 int tc_grid(long long total_tiles) {
-  static int cap = -1;
-  if (cap < 0) { const char* e = getenv("NGM_TC_MAX_CTAS"); cap = e ? atoi(e) : 0; }
+  const char* e = getenv("NGM_TC_MAX_CTAS");  // read per call: tests set it for single cases
+  const int cap = e ? atoi(e) : 0;
   long long g = num_sms();
   if (cap > 0 && cap < g) g = cap;
   return (int)(total_tiles < g ? total_tiles : g);
@@ -1043,6 +1043,8 @@ size_t tc_smem_bytes(const TcImage& im) {
   return need < 120 * 1024 ? 120 * 1024 : need;
 }
 
+#include "field_tc3.cuh"
+
 }  // namespace
 
 bool field_tc_supported(const NgmFieldDesc& fd, const char** why) {
@@ -1077,6 +1079,7 @@ int launch_field_fwd_tc(const NgmFieldFwdArgs& a, cudaStream_t stream) {
   p.tiles_per_field = (a.points_per_field + 127) / 128;
   p.total_tiles = p.tiles_per_field * a.num_fields;
   const int grid = tc_grid(p.total_tiles);
+  if (tc3_enabled() && tc3_supported(a.field, p.im)) return launch_tc3(p, a.field.nerf_num_octaves, grid, stream);
   return launch_tc<1>(p, a.field.encoding == NGM_ENC_PERMUTO ? 0 : a.field.nerf_num_octaves, tc_smem_bytes(p.im), grid, stream);
 }
 

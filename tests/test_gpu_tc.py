@@ -331,3 +331,37 @@ def test_render_knn_fp16_golden(name):
     assert col.mean().item() < 2e-3, f"colour L1 {col.mean().item():.2e} (max {col.max().item():.2e})"
     assert dep.mean().item() < 5e-3, f"depth L1 {dep.mean().item():.2e} (max {dep.max().item():.2e})"
     assert (p.term_probs.cpu() - a["out_term_probs"]).abs().mean().item() < 3e-3
+
+
+@pytest.mark.parametrize("slots", ["3", "2", "1"])
+def test_three_slot_field_kernel_experiment(slots, monkeypatch):
+    """csrc/field_tc3.cuh (NGM_TC3=1): static round-robin schedule over three tile slots, the third with its A operand
+    in shared memory (SS-mode tcgen05.mma).  Slower than the production kernel (see its header) but kept correct:
+    multi-segment tile ranges, partial last rounds, several fields."""
+    import neural_graph_mapping_b200 as ngm
+
+    monkeypatch.setenv("NGM_TC3", "1")
+    monkeypatch.setenv("NGM_TC3_SLOTS", slots)
+    monkeypatch.setenv("NGM_TC_MAX_CTAS", "3")  # few CTAs: every CTA walks several fields and rounds
+    g = torch.Generator().manual_seed(3)
+    F, n, W, L, O = 7, 128 * 11 + 50, 128, 4, 8
+    spec = R.FieldSpec("nerf", {"dim_in": 3, "num_octaves": O}, L, 4, W, "no")
+    params = R.stack_params([R.init_field_params(spec, g) for _ in range(F)])
+    pos = torch.randn(F, 3, generator=g)
+    q = torch.randn(F, 4, generator=g)
+    ori = q / q.norm(dim=-1, keepdim=True)
+    pts = pos[:, None] + torch.rand(F, n, 3, generator=g) * 1.6 - 0.8
+    rs = R.RenderSpec(field_radius=1.0, scale_mode="unit_cube")
+    ref = R.fieldset_forward_vmap(pts, pos, ori, spec, params, rs)
+    model = ngm.NeuralFieldSet(3, "neural_graph_mapping_b200.models.NeuralField",
+                               {"encoding_type": "neural_graph_mapping_b200.positional_encodings.PositionalEncodingNeRF",
+                                "encoding_kwargs": {"dim_in": 3, "num_octaves": O}, "num_layers": L, "dim_out": 4,
+                                "dim_mlp_out": W}, 2, 10.0, 1.0, field_radius=1.0, scale_mode="unit_cube",
+                               precision="fp16").to(DEV)
+    model.all_fields_params = {k: v.to(DEV) for k, v in params.items()}
+    model.set_vmap_fields(None)
+    with torch.no_grad():
+        y = model(pts.to(DEV), pos.to(DEV), ori.to(DEV), None, True)
+    scale = ref.abs().max().item()
+    e = (y.cpu() - ref).abs()
+    assert e.max().item() < 2e-2 * scale and e.mean().item() < 3e-3 * scale, (e.max().item(), e.mean().item(), scale)
