@@ -1,48 +1,44 @@
 // Three-slot form of the tcgen05 field kernel (included into field_tc.cu's translation unit).
 //
-// Why: with two tile slots, each owning its epilogue threads, a hidden layer costs a slot
-// MMA 512 + synchronisation ~550 + epilogue ~700 cycles, so the tensor pipe sees 2 x 512 of work per
-// ~1800 cycles (profiles/README.md).  A third tile in flight fills the gap, but TMEM (512 columns) only holds
-// 2 x (128 fp32 accumulator + 64 fp16 A-operand columns) + 128: the third slot keeps its accumulator in TMEM and
-// its A operand in SHARED memory (SS-mode MMA), and the register file only feeds two 256-thread epilogue teams.
-// So the schedule is static and round-robin instead of slot-owned:
+// Why: with two tile slots a hidden layer costs a slot MMA 512 + synchronisation ~550 + epilogue ~700 cycles,
+// so the tensor pipe sees 2 x 512 cycles of work per ~1800 (profiles/README.md).  A third tile in flight fills
+// the gap.  TMEM (512 columns) holds 2 x (128 fp32 accumulator + 64 fp16 A-operand columns) + 128, so the third
+// slot keeps its accumulator in TMEM and its A operand in SHARED memory (SS-mode tcgen05.mma), and there are no
+// spare columns to stage the next tile's layer-0 operand: it is staged in shared memory and installed by the
+// slot's own threads when the last layer has drained.
 //
-//   MMA order      (round r, layer l, slot s):  s fastest, then l, then r -- one issuer warp
-//   epilogue jobs  in the same order, job j handled by team j mod 2 (two teams of 8 warps, each warp = one TMEM
-//                  lane quadrant x one half of the columns); the epilogue itself is stateless (accumulator ->
-//                  bias + ReLU -> fp16 A operand of the next layer, to TMEM for slots 0/1, to the swizzled
-//                  shared-memory tile for slot 2)
-//   front end      3 warps encode the NEXT round's rows into a per-slot staging buffer; the team that drains a
-//                  slot's last layer installs the staged layer-0 operand for the slot's next tile
+//   warps 0-2                   MMA issuer of slot 0 / 1 / 2 (blocking mbarrier wait, elected lane issues, commit)
+//   warps 4-11 / 12-19 / 20-27  the 256 threads that OWN slot 0 / 1 / 2: two threads per row (TMEM lane), each
+//                               half of the columns of every epilogue; the h = 1 half also encodes the slot's next
+//                               tile into the staging buffer while the MMAs run
 //
-// Every hidden layer then offers the pipe 3 x 512 cycles of work per ~1700-cycle dependency chain.
-// Field stage (MODE 1 of tc_kernel: points in, raw MLP outputs out), NeRF encoding, W = 128-class MLPs.
+// 896 threads leave 72 registers per thread.
 //
 // STATUS: EXPERIMENT, selected only by NGM_TC3=1 (tests/test_gpu_tc.py keeps it correct).  Measured on the bench
-// workload (19.66 M points, 4 x 128): 2.84 ms with three tiles in flight, 2.91 ms with two, 4.66 ms with one,
-// against 2.16 ms of the production two-slot kernel whose epilogue threads are OWNED by their slot.  Removing the
-// encoding work changes nothing, so neither the front end nor the tensor pipe (46% busy) is the limit: every slot's
-// dependency chain stretches as slots are added (1.76 k -> 2.3 k -> 3.3 k cycles per layer) because the two shared
-// teams serialise jobs that complete together and the SS-slot epilogue (x16 loads + shared-memory stores) is the
-// slowest link.  Lessons kept in the code: (1) an mbarrier parity wait cannot tell phase k from k + 2 -- a waiter
-// must see every phase of a barrier, hence one accumulator barrier per OWNING team; (2) one issuer warp per slot:
-// a single issuer adds its ~600-cycle wake-up-to-commit latency to every MMA.  NGM_TC3_SLOTS=1|2|3 sets the
-// number of tiles in flight.
+// workload (19.66 M points, 4 x 128 MLP), field stage: 5.74 / 3.45 / 3.07 ms with 1 / 2 / 3 tiles in flight against
+// 2.16 ms of the production two-slot kernel.  The extra tile overlaps as intended (1.9x from one to three slots),
+// but every slot's dependency chain is longer here than in the two-slot kernel (2.2 k cycles per layer with one
+// tile in flight against 1.8 k: the layer-0 operand goes through shared memory and is installed on the critical
+// path, 28 warps share the four schedulers) and it stretches further as slots are added (3.5 k with three: the
+// epilogues' TMEM loads and stores compete with the accumulator traffic of the other slots' MMAs, which now keep
+// the tensor pipe busy most of the time).  A first variant with two epilogue teams SHARED by the three slots in a
+// static round-robin order (4.66 / 2.91 / 2.84 ms) lost to the serialisation of jobs that complete together.
+// Two lessons from it are kept: an mbarrier parity wait cannot tell phase k from phase k + 2, so every waiter must
+// see every phase of the barriers it waits on; and one issuer per slot, because a single issuer adds its
+// ~600-cycle wake-up-to-commit latency to every MMA.
+// Field stage only (MODE 1 of tc_kernel: points in, raw MLP outputs out), NeRF encoding;
+// NGM_TC3_SLOTS=1|2|3 sets the number of tiles in flight.
 
-constexpr int kThreads3 = 704;       // warps 0-2 MMA issuers of slots 0-2, warps 3-5 front end, warps 6-13 / 14-21 epilogue teams
-constexpr int kFeThreads = 96;
-constexpr int kTeamWarp0 = 6;
-constexpr int kStageRowBytes = 128;  // staging row: up to 64 halves (EP <= 64)
+constexpr int kThreads3 = 896;
+constexpr int kTeamWarp0 = 4;
+constexpr int kStageRowBytes = 128;      // staging row: up to 64 halves (EP <= 64)
 constexpr int kAcBytes = 2 * 128 * 128;  // slot 2's A operand: 2 atoms (K = 128) x 128 rows x 128 B
 
 struct Smem3 {
-  uint64_t a0_ready[3];     // layer-0 A operand installed + accumulator drained (256 team threads)
-  uint64_t a_ready[3];      // hidden-layer A operand stored (256 team threads)
-  uint64_t d_ready[2][3];   // accumulator complete (tcgen05.commit), one barrier per OWNING team and slot: a parity
-                            // wait cannot tell phase k from phase k + 2, so nobody may skip phases of a barrier --
-                            // with per-team barriers every waiter sees every phase of the barriers it waits on
-  uint64_t stage_full[3];   // staged rows written (96 front-end threads)
-  uint64_t stage_empty[3];  // staged rows consumed (256 team threads)
+  uint64_t a0_ready[3];    // layer-0 A operand installed + accumulator drained (256 threads of the slot)
+  uint64_t a_ready[3];     // hidden-layer A operand stored (256)
+  uint64_t d_ready[3];     // accumulator complete (tcgen05.commit)
+  uint64_t stage_full[3];  // staged rows of the next tile written (the 128 h = 1 threads)
   uint64_t w_ready;
   uint32_t tmem_base;
   uint32_t pad_;
@@ -59,19 +55,17 @@ __device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uin
       : "memory");
 }
 
-// NeRF features of one point as EP/2 packed half2 words (same arithmetic as encode_nerf_to_tmem)
+// NeRF features of one point -> one staging row, one input dimension at a time (OCT sines + OCT cosines live in
+// registers instead of all 6 * OCT features).  Row layout = the A operand: [sin: dim-major | cos: dim-major | 0 pad].
 template <int OCT>
-__device__ __forceinline__ void encode_nerf_words(float3 x, int start_octave, uint32_t (&w)[(6 * OCT + 15) / 16 * 8]) {
-  constexpr int E = 6 * OCT;
-  constexpr int EP = (E + 15) / 16 * 16;
+__device__ __forceinline__ void encode_nerf_row(float3 x, int start_octave, uint32_t* row_words) {
+  constexpr int E = 6 * OCT, EP = (E + 15) / 16 * 16;
   const float base = exp2f((float)start_octave);
   const float xs[3] = {x.x, x.y, x.z};
-  float fe[EP];
-#pragma unroll
-  for (int i = E; i < EP; ++i) fe[i] = 0.0f;
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
     const float t0 = xs[d] * base;
+    float sv[OCT], cv[OCT];
     float s = 0.f, c = 1.f;
 #pragma unroll
     for (int o = 0; o < OCT; ++o) {
@@ -82,12 +76,17 @@ __device__ __forceinline__ void encode_nerf_words(float3 x, int start_octave, ui
         c = fmaf(-2.0f * s, s, 1.0f);
         s = s2;
       }
-      fe[d * OCT + o] = s;
-      fe[3 * OCT + d * OCT + o] = c;
+      sv[o] = s;
+      cv[o] = c;
+    }
+#pragma unroll
+    for (int j = 0; j < OCT / 2; ++j) {
+      row_words[d * (OCT / 2) + j] = ptx::pack_half2(sv[2 * j], sv[2 * j + 1]);
+      row_words[3 * (OCT / 2) + d * (OCT / 2) + j] = ptx::pack_half2(cv[2 * j], cv[2 * j + 1]);
     }
   }
 #pragma unroll
-  for (int j = 0; j < EP / 2; ++j) w[j] = ptx::pack_half2(fe[2 * j], fe[2 * j + 1]);
+  for (int j = E / 2; j < EP / 2; ++j) row_words[j] = 0u;
 }
 
 template <int OCT>
@@ -95,9 +94,9 @@ __global__ void __launch_bounds__(kThreads3, 1) tc3_kernel(const TcParams p) {
   constexpr int EPW = (6 * OCT + 15) / 16 * 8;  // layer-0 A operand words per row
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
-  uint8_t* wsm = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);        // weight image (1024-B aligned)
-  uint8_t* acs = wsm + (p.im.total_bytes + 1023) / 1024 * 1024;                // slot 2's A operand (1024-B aligned)
-  uint8_t* stg = acs + kAcBytes;                                               // staging: [3][128][128 B]
+  uint8_t* wsm = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);  // weight image (1024-B aligned)
+  uint8_t* acs = wsm + (p.im.total_bytes + 1023) / 1024 * 1024;          // slot 2's A operand (1024-B aligned)
+  uint8_t* stg = acs + kAcBytes;                                         // staging: [3][128][128 B]
   Smem3& sm = *reinterpret_cast<Smem3*>(stg + 3 * 128 * kStageRowBytes);
   const uint32_t wsm_addr = ptx::smem_u32(wsm), acs_addr = ptx::smem_u32(acs);
 
@@ -109,10 +108,8 @@ __global__ void __launch_bounds__(kThreads3, 1) tc3_kernel(const TcParams p) {
     for (int s = 0; s < 3; ++s) {
       ptx::mbar_init(&sm.a0_ready[s], 256);
       ptx::mbar_init(&sm.a_ready[s], 256);
-      ptx::mbar_init(&sm.d_ready[0][s], 1);
-      ptx::mbar_init(&sm.d_ready[1][s], 1);
-      ptx::mbar_init(&sm.stage_full[s], kFeThreads);
-      ptx::mbar_init(&sm.stage_empty[s], 256);
+      ptx::mbar_init(&sm.d_ready[s], 1);
+      ptx::mbar_init(&sm.stage_full[s], 128);
     }
     ptx::mbar_init(&sm.w_ready, 1);
     ptx::fence_mbar_init();
@@ -125,14 +122,12 @@ __global__ void __launch_bounds__(kThreads3, 1) tc3_kernel(const TcParams p) {
   const long long t_begin = p.total_tiles * blockIdx.x / gridDim.x;
   const long long t_end = p.total_tiles * (blockIdx.x + 1) / gridDim.x;
   const int L = p.L, W = p.W;
+  const int NS = p.knn_k;  // tiles in flight (3; 1 or 2 for experiments)
   // TMEM columns: slot 0: D [0,128) A [128,192); slot 1: D [192,320) A [320,384); slot 2: D [384,512)
   auto d_col = [](int s) { return s == 0 ? 0u : (s == 1 ? 192u : 384u); };
 
   uint32_t w_phase = 0;
-  // completed-phase counters of the per-slot barriers (every role tracks all of them: jobs of the other team
-  // flip phases too)
-  int n_a0[3] = {0, 0, 0}, n_a[3] = {0, 0, 0}, n_d[3] = {0, 0, 0}, n_full[3] = {0, 0, 0}, n_empty[3] = {0, 0, 0};
-  int job = 0;  // global epilogue-job counter (team = job & 1)
+  int n_a0 = 0, n_a = 0, n_d = 0, n_full = 0;  // completed phases of this thread's slot barriers
 
   long long t = t_begin;
   while (t < t_end) {
@@ -141,8 +136,6 @@ __global__ void __launch_bounds__(kThreads3, 1) tc3_kernel(const TcParams p) {
     if (seg_end > t_end) seg_end = t_end;
     const int ntiles = (int)(seg_end - t);
     const long long tile0_in_field = t - f * p.tiles_per_field;
-    const int NS = p.knn_k;  // tiles in flight (3; 1 or 2 for experiments)
-    const int rounds = (ntiles + NS - 1) / NS;
     const long long slot = p.field_slots ? p.field_slots[f] : f;
 
     if (tid == 0) {  // stage this field's weight image (TMA engine)
@@ -156,28 +149,21 @@ __global__ void __launch_bounds__(kThreads3, 1) tc3_kernel(const TcParams p) {
 
     if (warp < 3) {
       // ===================== MMA issuer of slot `warp` (its tiles: warp, warp + NS, ...) =====================
-      // One issuer per slot: the ~600 cycles between a barrier wake-up and the commit (fence, descriptor set-up,
-      // MMA queue back-pressure) of the three slots overlap instead of adding up in one thread.
       const int s = warp;
       ptx::mbar_wait(&sm.w_ready, w_phase);
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint32_t wsm_u = __shfl_sync(0xffffffffu, wsm_addr, 0);
       const uint32_t acs_u = __shfl_sync(0xffffffffu, acs_addr, 0);
       const uint32_t d_addr = tmem_u + d_col(s);
-      int na0 = n_a0[0], na = n_a[0];  // this issuer only tracks its own slot (kept in element 0)
-      const int boot = ntiles < NS ? ntiles : NS;  // install-only jobs that open the segment
       if (s < NS) {
-        for (int r = 0; NS * r + s < ntiles; ++r) {
-          const int active = ntiles - NS * r < NS ? ntiles - NS * r : NS;  // tiles of this round
+        for (int ti = s; ti < ntiles; ti += NS) {
           for (int l = 0; l <= L; ++l) {
-            // global epilogue-job index of (r, l, s) -> the team that owns it (job parity)
-            const int owner = (job + boot + r * NS * (L + 1) + l * active + s) & 1;
             const TcLayer y = p.im.layer[l];
             const uint64_t bdesc0 = ptx::make_smem_desc_sw128(wsm_u + y.off);
             const uint32_t idesc = ptx::make_idesc_f16(y.n_pad);
             const int ksteps = y.k_pad / 16;
-            if (l == 0) { ptx::mbar_wait_lean(&sm.a0_ready[s], na0 & 1); ++na0; }
-            else        { ptx::mbar_wait_lean(&sm.a_ready[s], na & 1);   ++na; }
+            if (l == 0) { ptx::mbar_wait_lean(&sm.a0_ready[s], n_a0 & 1); ++n_a0; }
+            else        { ptx::mbar_wait_lean(&sm.a_ready[s], n_a & 1);   ++n_a; }
             ptx::tc_fence_after();
             if (ptx::elect_one()) {
               if (s < 2) {
@@ -193,71 +179,56 @@ __global__ void __launch_bounds__(kThreads3, 1) tc3_kernel(const TcParams p) {
                   }
                 }
               }
-              ptx::mma_commit(&sm.d_ready[owner][s]);
+              ptx::mma_commit(&sm.d_ready[s]);
             }
             __syncwarp();
           }
         }
       }
-      n_a0[0] = na0;
-      n_a[0] = na;
-      job += boot + ntiles * (L + 1);
-    } else if (warp < kTeamWarp0) {
-      // ===================== front end: rows of the next tiles -> staging =====================
-      const int ft = tid - 96;  // 0..95: rows ft (and ft + 96 for the first 32 threads)
-      for (int ti = 0; ti < ntiles; ++ti) {
-        const int s = ti % NS;
-        // the staging buffer of slot s is free once the previous tile's rows were installed
-        if (s == 0) { ptx::mbar_wait(&sm.stage_empty[0], (n_empty[0] + 1) & 1); ++n_empty[0]; }
-        else if (s == 1) { ptx::mbar_wait(&sm.stage_empty[1], (n_empty[1] + 1) & 1); ++n_empty[1]; }
-        else { ptx::mbar_wait(&sm.stage_empty[2], (n_empty[2] + 1) & 1); ++n_empty[2]; }
-        for (int row = ft; row < 128; row += kFeThreads) {
-          const long long gp = (tile0_in_field + ti) * 128 + row;
-          float3 fx = make_float3(0.f, 0.f, 0.f);
-          if (gp < p.points_per_field) {
-            const float* src = p.points + (f * p.points_per_field + gp) * 3;
-            float3 x = make_float3(__ldg(src), __ldg(src + 1), __ldg(src + 2));
-            if (p.positions) {
-              const float* c = p.positions + slot * 3;
-              const float* q = p.orientations + slot * 4;
-              x = make_float3(x.x - __ldg(c), x.y - __ldg(c + 1), x.z - __ldg(c + 2));
-              x = quat_inv_rotate(__ldg(q), __ldg(q + 1), __ldg(q + 2), __ldg(q + 3), x);
-            }
-            fx = scale_local(x, p.scale_mode, p.field_radius);
-          }
-          uint32_t w[EPW];
-          encode_nerf_words<OCT>(fx, p.nerf_start, w);
-          uint4* dst = reinterpret_cast<uint4*>(stg + (s * 128 + row) * kStageRowBytes);
-#pragma unroll
-          for (int j = 0; j < EPW / 4; ++j) dst[j] = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
-        }
-        ptx::mbar_arrive(&sm.stage_full[s]);
-      }
-    } else {
-      // ===================== epilogue teams =====================
-      const int team = (warp - kTeamWarp0) >> 3;
-      const int h = ((warp - kTeamWarp0) >> 2) & 1;  // column half
-      const int qwarp = warp & 3;           // TMEM lane quadrant
+    } else if (warp >= kTeamWarp0) {
+      // ===================== the 256 threads of slot s =====================
+      const int s = (warp - kTeamWarp0) >> 3;
+      const int h = ((warp - kTeamWarp0) >> 2) & 1;  // column half; h = 1 also runs the front end
+      const int qwarp = warp & 3;                    // TMEM lane quadrant
       const int row = qwarp * 32 + lane;
-      const uint32_t lane_base = tmem_base + ((uint32_t)(qwarp * 32) << 16);
+      const uint32_t d_addr = tmem_base + ((uint32_t)(qwarp * 32) << 16) + d_col(s);
       const uint32_t* bias2 = reinterpret_cast<const uint32_t*>(wsm + p.im.bias_h2_off);
       const float* bias_last = reinterpret_cast<const float*>(wsm + p.im.bias_last_off);
       const int w0 = ((W / 16 + 1) / 2) * 16;
       const int my_c0 = h ? w0 : 0, my_n = h ? W - w0 : w0;
-      ptx::mbar_wait(&sm.w_ready, w_phase);
+      uint32_t* my_stage = reinterpret_cast<uint32_t*>(stg + (s * 128 + row) * kStageRowBytes);
 
-      // install the staged layer-0 A operand of slot s (this thread: its row, its half of the words)
-      auto install = [&](int s) {  // (the caller has waited for stage_full[s])
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(stg + (s * 128 + row) * kStageRowBytes);
-        constexpr int HW = EPW / 2;  // words per half (EPW is a multiple of 8)
+      // front end of tile ti (h == 1 threads, one row each): point -> local -> NeRF features -> staging row
+      auto fe = [&](int ti) {
+        const long long gp = (tile0_in_field + ti) * 128 + row;
+        float3 fx = make_float3(0.f, 0.f, 0.f);
+        if (gp < p.points_per_field) {
+          const float* src = p.points + (f * p.points_per_field + gp) * 3;
+          float3 x = make_float3(__ldg(src), __ldg(src + 1), __ldg(src + 2));
+          if (p.positions) {
+            const float* c = p.positions + slot * 3;
+            const float* q = p.orientations + slot * 4;
+            x = make_float3(x.x - __ldg(c), x.y - __ldg(c + 1), x.z - __ldg(c + 2));
+            x = quat_inv_rotate(__ldg(q), __ldg(q + 1), __ldg(q + 2), __ldg(q + 3), x);
+          }
+          fx = scale_local(x, p.scale_mode, p.field_radius);
+        }
+        encode_nerf_row<OCT>(fx, p.nerf_start, my_stage);
+        ptx::mbar_arrive(&sm.stage_full[s]);
+      };
+      // install the staged layer-0 A operand (this thread: its row, its half of the words), then signal the issuer
+      auto install = [&]() {
+        ptx::mbar_wait_lean(&sm.stage_full[s], n_full & 1);
+        ++n_full;
+        constexpr int HW = EPW / 2;  // words per half (a multiple of 4)
         uint32_t w[HW];
 #pragma unroll
         for (int j = 0; j < HW; j += 4) {
-          const uint4 v = *reinterpret_cast<const uint4*>(src + h * HW + j);
+          const uint4 v = *reinterpret_cast<const uint4*>(my_stage + h * HW + j);
           w[j] = v.x; w[j + 1] = v.y; w[j + 2] = v.z; w[j + 3] = v.w;
         }
         if (s < 2) {
-          ptx::tmem_store_n<HW>(lane_base + d_col(s) + kACol + h * HW, w);
+          ptx::tmem_store_n<HW>(d_addr + kACol + h * HW, w);
           ptx::tc_wait_st();
           ptx::tc_fence_before();
         } else {  // K-major SWIZZLE_128B rows: 16-B chunk c of row r lives at chunk c ^ (r & 7)
@@ -268,61 +239,62 @@ __global__ void __launch_bounds__(kThreads3, 1) tc3_kernel(const TcParams p) {
           }
           ptx::fence_proxy_async();
         }
-        ptx::mbar_arrive(&sm.stage_empty[s]);
         ptx::mbar_arrive(&sm.a0_ready[s]);
       };
 
-      // bootstrap: the first round's layer-0 operands (three install-only jobs)
-#pragma unroll
-      for (int s = 0; s < 3; ++s) {
-        if (s < NS && s < ntiles) {
-          if ((job & 1) == team) {
-            ptx::mbar_wait_lean(&sm.stage_full[s], n_full[s] & 1);
-            install(s);
-          }
-          ++n_full[s];
-          ++job;
-        }
-      }
-      for (int r = 0; r < rounds; ++r) {
-        for (int l = 0; l <= L; ++l) {
-#pragma unroll
-          for (int s = 0; s < 3; ++s) {
-            const int ti = NS * r + s;
-            if (s >= NS || ti >= ntiles) continue;
-            const bool mine = (job & 1) == team;
-            ++job;
-            const bool next_tile = l == L && ti + NS < ntiles;
-            if (next_tile) ++n_full[s];
-            if (!mine) continue;
-            ptx::mbar_wait_lean(&sm.d_ready[team][s], n_d[s] & 1);  // n_d: OWN jobs on this slot so far
-            ++n_d[s];
+      if (s < NS && s < ntiles) {
+        ptx::mbar_wait(&sm.w_ready, w_phase);  // biases live in the image
+        if (h == 1) fe(s);
+        install();
+        for (int ti = s; ti < ntiles; ti += NS) {
+          const bool has_next = ti + NS < ntiles;
+          for (int l = 0; l <= L; ++l) {
+            ptx::mbar_wait_lean(&sm.d_ready[s], n_d & 1);
+            ++n_d;
             ptx::tc_fence_after();
-            const uint32_t d_addr = lane_base + d_col(s);
             if (l < L) {
-              // ---------- hidden layer: accumulator -> bias + ReLU -> next A operand ----------
+              // ---------- hidden layer: accumulator -> bias + ReLU -> next A operand (16 columns per step) ----------
               const uint32_t* b2 = bias2 + l * (W / 2);
-              if (s < 2) {
-                if (my_n > 0) hidden_epilogue(d_addr, d_addr + kACol, b2, my_c0, my_n);
-                ptx::tc_wait_st();
-                ptx::tc_fence_before();
-              } else {
-                for (int c = my_c0; c < my_c0 + my_n; c += 16) {
-                  uint32_t v[16];
-                  ptx::tmem_ld16(d_addr + c, v);
-                  ptx::tc_wait_ld();
-                  uint32_t w[8];
-                  cvt16(v, b2 + c / 2, w);
-                  // columns c..c+15 = K elements of atom c/64, 16-B chunks (c%64)/8 and +1
+              int c = my_c0;
+              const int cend = my_c0 + my_n;
+              for (; c + 32 <= cend; c += 32) {  // 32 columns per TMEM load: one exposed load latency per step
+                uint32_t v[32];
+                ptx::tmem_ld32(d_addr + c, v);
+                ptx::tc_wait_ld();
+                uint32_t w[16];
+                cvt16(v, b2 + c / 2, w);
+                cvt16(v + 16, b2 + c / 2 + 8, w + 8);
+                if (s < 2) {
+                  ptx::tmem_st16(d_addr + kACol + c / 2, w);
+                } else {  // columns c..c+31 = K elements of atom c/64, four 16-B chunks from (c%64)/8
+                  uint8_t* base = acs + (c >> 6) * (128 * 128) + row * 128;
+                  const int ck = (c & 63) >> 3;
+#pragma unroll
+                  for (int j = 0; j < 4; ++j)
+                    *reinterpret_cast<uint4*>(base + (((ck + j) ^ (row & 7)) << 4)) =
+                        make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+                }
+              }
+              for (; c < cend; c += 16) {
+                uint32_t v[16];
+                ptx::tmem_ld16(d_addr + c, v);
+                ptx::tc_wait_ld();
+                uint32_t w[8];
+                cvt16(v, b2 + c / 2, w);
+                if (s < 2) {
+                  ptx::tmem_st8(d_addr + kACol + c / 2, w);
+                } else {
                   uint8_t* base = acs + (c >> 6) * (128 * 128) + row * 128;
                   const int ck = (c & 63) >> 3;
                   *reinterpret_cast<uint4*>(base + ((ck ^ (row & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
                   *reinterpret_cast<uint4*>(base + (((ck + 1) ^ (row & 7)) << 4)) = make_uint4(w[4], w[5], w[6], w[7]);
                 }
-                ptx::tc_fence_before();
-                ptx::fence_proxy_async();
               }
+              if (s < 2) ptx::tc_wait_st(); else ptx::fence_proxy_async();
+              ptx::tc_fence_before();
               ptx::mbar_arrive(&sm.a_ready[s]);
+              // front end of the slot's next tile, in the wait for this layer's successor MMA
+              if (l == 0 && h == 1 && has_next) fe(ti + NS);
             } else {
               // ---------- last layer: outputs to HBM, then the slot's next layer-0 operand ----------
               if (h == 0) {
@@ -341,13 +313,7 @@ __global__ void __launch_bounds__(kThreads3, 1) tc3_kernel(const TcParams p) {
                 }
                 ptx::tc_fence_before();
               }
-              if (next_tile) {
-                // staged rows of the slot's next tile: phase n_full - 1 (counted above).  Skipping the phases
-                // installed by the other team is safe HERE: the single staging buffer hand-shakes through
-                // stage_empty, so this barrier is never more than one phase ahead of or behind its waiter.
-                ptx::mbar_wait_lean(&sm.stage_full[s], (n_full[s] - 1) & 1);
-                install(s);
-              }
+              if (has_next) install();
             }
           }
         }
