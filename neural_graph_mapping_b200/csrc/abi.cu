@@ -35,6 +35,7 @@ int launch_sample_rays(const NgmSampleArgs& a, cudaStream_t stream);
 int launch_composite(const NgmCompositeArgs& a, cudaStream_t stream);
 int launch_neus_isd(const float* sd, const int64_t* slots, int num_fields, float* out, cudaStream_t stream);
 int launch_field_fwd_simt(const NgmFieldFwdArgs& a, cudaStream_t stream);
+size_t field_simt_workspace_bytes(const NgmFieldFwdArgs& a);
 size_t field_simt_smem_bytes(const NgmFieldDesc& fd, int* act_stride, int* enc_stride);
 // fp16 tcgen05 path (field_tc.cu)
 bool field_tc_supported(const NgmFieldDesc& fd, const char** why);
@@ -97,7 +98,7 @@ static int validate_field(const NgmFieldDesc& fd) {
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct RenderWorkspace {
-  size_t points_world, distances, depths, outs, rows_half, isd, tc, total;
+  size_t points_world, distances, depths, outs, rows_half, rows_f32, rows_f32_bytes, isd, tc, total;
 };
 
 static RenderWorkspace render_workspace(const NgmRenderArgs& a) {
@@ -116,6 +117,11 @@ static RenderWorkspace render_workspace(const NgmRenderArgs& a) {
   if (precoded) {  // fp16 A-operand rows of the permutohedral encoding
     const size_t ep = (size_t)(a.field.dim_encoding + 15) / 16 * 16;
     w.rows_half = off; off = align_up(off + n * ep * 2, 256);
+  }
+  if (!fused && a.precision == NGM_PREC_FP32 && a.field.encoding == NGM_ENC_PERMUTO && a.field.permuto_feats == 2) {
+    w.rows_f32 = off;  // fp32 rows for the FFMA field kernel
+    w.rows_f32_bytes = n * (size_t)a.field.dim_encoding * sizeof(float);
+    off = align_up(off + w.rows_f32_bytes, 256);
   }
   w.isd = off;         off = align_up(off + (size_t)a.num_fields * sizeof(float), 256);
   w.tc = off;
@@ -161,7 +167,7 @@ int ngm_sample_rays(const NgmSampleArgs* a, void* stream) {
 
 int ngm_field_fwd_workspace_bytes(const NgmFieldFwdArgs* a, size_t* out) {
   NGM_CHECK_ARG(a && out, "null args");
-  *out = a->precision == NGM_PREC_FP16 ? field_tc_workspace_bytes(a->field, a->num_fields) : 0;
+  *out = a->precision == NGM_PREC_FP16 ? field_tc_workspace_bytes(a->field, a->num_fields) : field_simt_workspace_bytes(*a);
   return NGM_OK;
 }
 
@@ -411,8 +417,8 @@ int ngm_render_rays_fwd(const NgmRenderArgs* a, void* stream_) {
   f.num_fields = a->num_fields;
   f.scale_mode = a->scale_mode;
   f.precision = a->precision;
-  f.workspace = ws + w.tc;
-  f.workspace_bytes = w.total - w.tc;
+  f.workspace = w.rows_f32_bytes ? ws + w.rows_f32 : ws + w.tc;
+  f.workspace_bytes = w.rows_f32_bytes ? w.rows_f32_bytes : w.total - w.tc;
   if (int rc = ngm_field_fwd(&f, stream_)) return rc;
 
   NgmCompositeArgs c{};

@@ -88,6 +88,46 @@ __global__ void __launch_bounds__(256) permuto_bwd_kernel(NgmEncodeArgs a) {
 // one thread per (point, group of four levels), so that the 4 x 4 table gathers of a thread are independent and the
 // whole GPU's warps hide the L2 latency (inside the persistent MMA kernel only 8 warps per SM could).
 // Row layout = the kernel's A operand: EP halves per point (levels, optional raw points, zero padding).
+// Same rows in fp32 (E floats per point) for the reference-arithmetic field kernel: the FFMA kernel then reads its
+// layer-0 input instead of gathering with 256 threads per SM.
+__global__ void __launch_bounds__(256) permuto_rows_f32_kernel(PermutoRowsArgs a) {
+  const NgmFieldDesc& fd = a.field;
+  const int L = fd.permuto_levels, groups = (L + 3) / 4, E = fd.dim_encoding;
+  const size_t level_elems = ((size_t)1 << fd.permuto_log2_capacity) * 2;
+  const long long total = a.num_points * groups;
+  float* out = reinterpret_cast<float*>(a.out);
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(idx % groups);
+    const long long pt = idx / groups;
+    const long long f = pt / a.points_per_field;
+    const long long slot = a.field_slots ? a.field_slots[f] : f;
+    const float* src = a.points_world + pt * 3;
+    float3 x = make_float3(__ldg(src), __ldg(src + 1), __ldg(src + 2));
+    if (a.positions) {
+      const float* c = a.positions + slot * 3;
+      const float* q = a.orientations + slot * 4;
+      x = make_float3(x.x - __ldg(c), x.y - __ldg(c + 1), x.z - __ldg(c + 2));
+      x = quat_inv_rotate(__ldg(q), __ldg(q + 1), __ldg(q + 2), __ldg(q + 3), x);
+    }
+    x = scale_local(x, a.scale_mode, a.field_radius);
+    const float xs[3] = {x.x, x.y, x.z};
+    const float* table = fd.enc_param0 + slot * fd.enc_param0_stride;
+    const float* shift = fd.enc_param1 + slot * fd.enc_param1_stride;
+    float* row = out + pt * E;
+    for (int i = 0; i < 4 && 4 * g + i < L; ++i) {
+      const int l = 4 * g + i;
+      float f2[2];
+      permuto_level<2>(xs, table + (size_t)l * level_elems, shift + l * 3, fd.permuto_scale + l * 3,
+                       fd.permuto_log2_capacity, 2, f2);
+      row[2 * l] = f2[0];
+      row[2 * l + 1] = f2[1];
+    }
+    if (g == groups - 1 && fd.permuto_concat_points)
+      for (int c = 0; c < 3; ++c) row[2 * L + c] = xs[c] * fd.permuto_concat_scaling;
+  }
+}
+
 __global__ void __launch_bounds__(256) permuto_rows_half_kernel(PermutoRowsArgs a) {
   const NgmFieldDesc& fd = a.field;
   const int L = fd.permuto_levels, groups = (L + 3) / 4, words = a.EP / 2;
@@ -152,6 +192,15 @@ int launch_encode_fwd(const NgmEncodeArgs& a, cudaStream_t stream) {
   const long long per_point = fd.encoding == NGM_ENC_PERMUTO ? fd.permuto_levels + 1 : fd.dim_encoding;
   encode_fwd_kernel<<<grid_for((long long)a.num_fields * a.points_per_field * per_point), 256, 0, stream>>>(a);
   return check_launch("encode_fwd_kernel");
+}
+
+int launch_permuto_rows_f32(const PermutoRowsArgs& a, cudaStream_t stream) {
+  if (a.num_points == 0) return NGM_OK;
+  const long long items = a.num_points * ((a.field.permuto_levels + 3) / 4);
+  long long blocks = (items + 255) / 256;
+  const long long cap = (long long)num_sms() * 64;
+  permuto_rows_f32_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, stream>>>(a);
+  return check_launch("permuto_rows_f32_kernel");
 }
 
 int launch_permuto_rows_half(const PermutoRowsArgs& a, cudaStream_t stream) {

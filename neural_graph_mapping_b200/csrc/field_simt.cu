@@ -19,8 +19,10 @@ namespace {
 constexpr int TP = 128;        // points per tile
 constexpr int NTHREADS = 256;
 constexpr int KC = 16;         // k-chunk
-constexpr int NT = 64;         // accumulators per thread; 2 halves -> 128 outputs per pass
-constexpr int NPASS = 2 * NT;
+// accumulators per thread NT (template parameter): 64 -> 128 outputs per pass (wide MLPs, 148 registers, one CTA
+// per SM); 16 -> 32 outputs per pass for MLPs of width <= 32 such as the reference's default field
+// (neural_graph_map.yaml:15-17): both thread halves busy and three CTAs per SM.  Same summation order either way.
+constexpr int NT_WIDE = 64, NT_NARROW = 16;
 
 __host__ __device__ inline int row_stride(int width) {
   int s = (width + KC - 1) / KC * KC;  // readable in whole 16-float chunks
@@ -48,6 +50,7 @@ struct SimtParams {
   const int* tile_offsets;   // [F + 1]  tiles of 128 entries per field
   int knn_k;
   int num_fields;
+  const float* enc_rows;     // precoded layer-0 input (num_fields * points_per_field, E), or nullptr: encode in-kernel
 };
 
 __device__ __forceinline__ void encode_tile(const SimtParams& p, long long slot, const float (*xs)[4],
@@ -86,7 +89,9 @@ __device__ __forceinline__ void encode_tile(const SimtParams& p, long long slot,
   }
 }
 
-__global__ void __launch_bounds__(NTHREADS, 1) field_fwd_simt_kernel(SimtParams p) {
+template <int NT>
+__global__ void __launch_bounds__(NTHREADS, NT <= 16 ? 3 : 1) field_fwd_simt_kernel(SimtParams p) {
+  constexpr int NPASS = 2 * NT;
   extern __shared__ __align__(16) float smem[];
   const NgmFieldDesc& fd = p.fd;
   const int E = fd.dim_encoding, W = fd.dim_mlp_out, L = fd.num_layers;
@@ -148,7 +153,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_fwd_simt_kernel(SimtParams 
     }
     __syncthreads();
     // ---- encoding -> act0 (and a persistent copy for the skip connections) ----
-    encode_tile(p, slot, xs, act0, AS);
+    if (p.enc_rows) {  // rows produced by the whole-GPU row encoder (encode.cu)
+      const int Epad = (E + KC - 1) / KC * KC;
+      for (int idx = tid; idx < TP * Epad; idx += NTHREADS) {
+        const int q = idx / Epad, c = idx - q * Epad;
+        const long long gp = p0 + q;
+        act0[q * AS + c] = (c < E && gp < p.points_per_field) ? __ldg(p.enc_rows + (f * p.points_per_field + gp) * E + c) : 0.0f;
+      }
+    } else {
+      encode_tile(p, slot, xs, act0, AS);
+    }
     __syncthreads();
     if (keep_enc) {
       for (int idx = tid; idx < TP * E; idx += NTHREADS) {
@@ -176,15 +190,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_fwd_simt_kernel(SimtParams 
           __syncthreads();  // previous chunk consumed / activations of previous layer complete
           {                 // stage W[nb .. nb+128) x [k0 .. k0+16) -> wsm[n][kk], zero padded
             const int n = tid >> 1, kk0 = (tid & 1) * 8;
-            float v[8];
+            if (n < NPASS) {
+              float v[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int k = k0 + kk0 + i;
-              v[i] = (n < ncount && k < K) ? __ldg(Wg + (size_t)(nb + n) * K + k) : 0.0f;
+              for (int i = 0; i < 8; ++i) {
+                const int k = k0 + kk0 + i;
+                v[i] = (n < ncount && k < K) ? __ldg(Wg + (size_t)(nb + n) * K + k) : 0.0f;
+              }
+              float4* d = reinterpret_cast<float4*>(wsm + n * KC + kk0);
+              d[0] = make_float4(v[0], v[1], v[2], v[3]);
+              d[1] = make_float4(v[4], v[5], v[6], v[7]);
             }
-            float4* d = reinterpret_cast<float4*>(wsm + n * KC + kk0);
-            d[0] = make_float4(v[0], v[1], v[2], v[3]);
-            d[1] = make_float4(v[4], v[5], v[6], v[7]);
           }
           __syncthreads();
           if (jmax > 0) {
@@ -266,13 +282,36 @@ size_t field_simt_smem_bytes(const NgmFieldDesc& fd, int* act_stride, int* enc_s
   const int ES = fd.skip_mode != NGM_SKIP_NO ? row_stride(E) : 0;
   if (act_stride) *act_stride = AS;
   if (enc_stride) *enc_stride = ES;
-  return sizeof(float) * ((size_t)TP * 4 + NPASS * KC + 2 * (size_t)TP * AS + (size_t)TP * ES);
+  return sizeof(float) * ((size_t)TP * 4 + 2 * NT_WIDE * KC + 2 * (size_t)TP * AS + (size_t)TP * ES);
 }
 
 int launch_field_fwd_simt_gather(const NgmFieldFwdArgs& a, const int* entries, const int* entry_offsets,
                                  const int* tile_offsets, int knn_k, long long max_tiles, cudaStream_t stream);
 
+int launch_permuto_rows_f32(const PermutoRowsArgs& a, cudaStream_t stream);
+
+// permutohedral rows for the fp32 kernel: worth it when the caller provides the workspace (E floats per point)
+size_t field_simt_workspace_bytes(const NgmFieldFwdArgs& a) {
+  if (a.field.encoding != NGM_ENC_PERMUTO || a.field.permuto_feats != 2) return 0;
+  return (size_t)a.num_fields * (size_t)a.points_per_field * (size_t)a.field.dim_encoding * sizeof(float);
+}
+
 int launch_field_fwd_simt(const NgmFieldFwdArgs& a, cudaStream_t stream) {
+  const size_t need = field_simt_workspace_bytes(a);
+  if (need && a.workspace && a.workspace_bytes >= need) {
+    PermutoRowsArgs e{};
+    e.field = a.field;
+    e.points_world = a.points;
+    e.positions = a.positions; e.orientations = a.orientations;
+    e.field_slots = reinterpret_cast<const long long*>(a.field_slots);
+    e.out = static_cast<uint32_t*>(a.workspace);
+    e.num_points = (long long)a.num_fields * a.points_per_field;
+    e.points_per_field = a.points_per_field;
+    e.field_radius = a.field_radius;
+    e.scale_mode = a.scale_mode;
+    if (int rc = launch_permuto_rows_f32(e, stream)) return rc;
+    return launch_field_fwd_simt_gather(a, nullptr, nullptr, nullptr, -1, 0, stream);  // knn_k = -1: rows precoded
+  }
   return launch_field_fwd_simt_gather(a, nullptr, nullptr, nullptr, 1, 0, stream);
 }
 
@@ -286,6 +325,7 @@ int launch_field_fwd_simt_gather(const NgmFieldFwdArgs& a, const int* entries, c
   p.entry_offsets = entry_offsets;
   p.tile_offsets = tile_offsets;
   p.knn_k = knn_k;
+  p.enc_rows = (!entries && knn_k == -1) ? static_cast<const float*>(a.workspace) : nullptr;
   p.num_fields = a.num_fields;
   p.fd = a.field;
   p.points = a.points;
@@ -301,16 +341,18 @@ int launch_field_fwd_simt_gather(const NgmFieldFwdArgs& a, const int* entries, c
   NGM_UNSUPPORTED(smem > 227 * 1024,
                   "fp32 field kernel needs %zu B shared memory (> 227 KB): dim_mlp_out=%d dim_encoding=%d too wide",
                   smem, a.field.dim_mlp_out, a.field.dim_encoding);
-  static bool attr_set = false;
-  if (!attr_set) {
-    NGM_CUDA(cudaFuncSetAttribute(field_fwd_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
   p.total_tiles = entries ? max_tiles : p.tiles_per_field * a.num_fields;
   if (p.total_tiles <= 0) return NGM_OK;
   const long long cap = (long long)num_sms() * 64;
   const unsigned grid = (unsigned)(p.total_tiles < cap ? p.total_tiles : cap);
-  field_fwd_simt_kernel<<<grid, NTHREADS, smem, stream>>>(p);
+  const bool narrow = a.field.dim_mlp_out <= 2 * NT_NARROW && a.field.dim_out <= 2 * NT_NARROW;
+  if (narrow) {
+    NGM_CUDA(cudaFuncSetAttribute(field_fwd_simt_kernel<NT_NARROW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    field_fwd_simt_kernel<NT_NARROW><<<grid, NTHREADS, smem, stream>>>(p);
+  } else {
+    NGM_CUDA(cudaFuncSetAttribute(field_fwd_simt_kernel<NT_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    field_fwd_simt_kernel<NT_WIDE><<<grid, NTHREADS, smem, stream>>>(p);
+  }
   return check_launch("field_fwd_simt_kernel");
 }
 
