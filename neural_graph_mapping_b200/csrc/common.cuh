@@ -61,6 +61,10 @@ struct PermutoRowsArgs {
   long long num_points, points_per_field;
   float field_radius;
   int scale_mode, EP;
+  // gather mode (kNN path): row e = (point e / knn_k, neighbour e % knn_k), evaluated by field pair_field[e]
+  // (-1: the point is outside every field, no row); positions / orientations are then indexed by that field
+  const int* pair_field;
+  int knn_k;
 };
 
 // ---- Philox4x32-10 counter RNG (in-kernel sampling jitter when no jitter tensor is given) ----

@@ -100,13 +100,19 @@ __global__ void __launch_bounds__(256) permuto_rows_f32_kernel(PermutoRowsArgs a
        idx += (long long)gridDim.x * blockDim.x) {
     const int g = (int)(idx % groups);
     const long long pt = idx / groups;
-    const long long f = pt / a.points_per_field;
+    long long f = pt / a.points_per_field, src_pt = pt;
+    if (a.pair_field) {
+      f = __ldg(a.pair_field + pt);
+      if (f < 0) continue;
+      src_pt = pt / a.knn_k;
+    }
     const long long slot = a.field_slots ? a.field_slots[f] : f;
-    const float* src = a.points_world + pt * 3;
+    const long long pose = a.pair_field ? f : slot;
+    const float* src = a.points_world + src_pt * 3;
     float3 x = make_float3(__ldg(src), __ldg(src + 1), __ldg(src + 2));
     if (a.positions) {
-      const float* c = a.positions + slot * 3;
-      const float* q = a.orientations + slot * 4;
+      const float* c = a.positions + pose * 3;
+      const float* q = a.orientations + pose * 4;
       x = make_float3(x.x - __ldg(c), x.y - __ldg(c + 1), x.z - __ldg(c + 2));
       x = quat_inv_rotate(__ldg(q), __ldg(q + 1), __ldg(q + 2), __ldg(q + 3), x);
     }
@@ -137,12 +143,18 @@ __global__ void __launch_bounds__(256) permuto_rows_half_kernel(PermutoRowsArgs 
        idx += (long long)gridDim.x * blockDim.x) {
     const int g = (int)(idx % groups);
     const long long pt = idx / groups;
-    const long long f = pt / a.points_per_field;
+    long long f = pt / a.points_per_field, src_pt = pt;
+    if (a.pair_field) {
+      f = __ldg(a.pair_field + pt);
+      if (f < 0) continue;
+      src_pt = pt / a.knn_k;
+    }
     const long long slot = a.field_slots ? a.field_slots[f] : f;
-    const float* src = a.points_world + pt * 3;
+    const long long pose = a.pair_field ? f : slot;
+    const float* src = a.points_world + src_pt * 3;
     float3 x = make_float3(__ldg(src), __ldg(src + 1), __ldg(src + 2));
-    const float* c = a.positions + slot * 3;
-    const float* q = a.orientations + slot * 4;
+    const float* c = a.positions + pose * 3;
+    const float* q = a.orientations + pose * 4;
     x = make_float3(x.x - __ldg(c), x.y - __ldg(c + 1), x.z - __ldg(c + 2));
     x = quat_inv_rotate(__ldg(q), __ldg(q + 1), __ldg(q + 2), __ldg(q + 3), x);
     x = scale_local(x, a.scale_mode, a.field_radius);

@@ -158,7 +158,15 @@ __global__ void __launch_bounds__(NTHREADS, NT <= 16 ? 3 : 1) field_fwd_simt_ker
       for (int idx = tid; idx < TP * Epad; idx += NTHREADS) {
         const int q = idx / Epad, c = idx - q * Epad;
         const long long gp = p0 + q;
-        act0[q * AS + c] = (c < E && gp < p.points_per_field) ? __ldg(p.enc_rows + (f * p.points_per_field + gp) * E + c) : 0.0f;
+        float v = 0.0f;
+        if (c < E) {
+          if (gather) {
+            if (q < ent_cnt) v = __ldg(p.enc_rows + (long long)__ldg(p.entries + ent_base + q) * E + c);
+          } else if (gp < p.points_per_field) {
+            v = __ldg(p.enc_rows + (f * p.points_per_field + gp) * E + c);
+          }
+        }
+        act0[q * AS + c] = v;
       }
     } else {
       encode_tile(p, slot, xs, act0, AS);
@@ -325,7 +333,9 @@ int launch_field_fwd_simt_gather(const NgmFieldFwdArgs& a, const int* entries, c
   p.entry_offsets = entry_offsets;
   p.tile_offsets = tile_offsets;
   p.knn_k = knn_k;
-  p.enc_rows = (!entries && knn_k == -1) ? static_cast<const float*>(a.workspace) : nullptr;
+  // precoded layer-0 rows: knn_k == -1 (dense call) or a.workspace given in gather mode (fp32 call from knn.cu)
+  p.enc_rows = ((!entries && knn_k == -1) || (entries && a.precision == NGM_PREC_FP32 && a.workspace))
+                   ? static_cast<const float*>(a.workspace) : nullptr;
   p.num_fields = a.num_fields;
   p.fd = a.field;
   p.points = a.points;

@@ -801,6 +801,11 @@ __global__ void __launch_bounds__(threads_of(MODE), 1) tc_kernel(const TcParams 
             const long long gp = (tile0_in_field + ti) * 128 + row;
             valid = gp < p.points_per_field;
             rr = valid ? f * p.points_per_field + gp : 0;
+            if (gather) {  // rows are indexed by the (point, neighbour) entry
+              const int e = __ldg(p.entry_offsets + f) + (int)gp;
+              valid = e < __ldg(p.entry_offsets + f + 1);
+              rr = valid ? __ldg(p.entries + e) : 0;
+            }
           } else {
             const int sample = __float_as_int(fx.x);
             valid = sample >= 0;
@@ -1085,8 +1090,10 @@ int launch_field_fwd_tc(const NgmFieldFwdArgs& a, cudaStream_t stream) {
 
 // kNN path: every tile is 128 (point, neighbour) entries of ONE field; the tile count lives in tile_offsets[F]
 int launch_field_fwd_tc_gather(const NgmFieldFwdArgs& a, const int* entries, const int* entry_offsets,
-                               const int* tile_offsets, int knn_k, long long max_tiles, cudaStream_t stream) {
+                               const int* tile_offsets, int knn_k, long long max_tiles, const void* rows_half,
+                               cudaStream_t stream) {
   TcParams p{};
+  p.raw_a = static_cast<const __half*>(rows_half);  // pre-encoded rows (permutohedral), indexed by entry; or nullptr
   if (int rc = fill_common(p, a.field, a.num_fields, a.positions, a.orientations, a.field_slots, a.scale_mode,
                            a.field_radius, a.workspace, stream))
     return rc;

@@ -17,7 +17,10 @@ namespace ngm {
 int launch_field_fwd_simt_gather(const NgmFieldFwdArgs& a, const int* entries, const int* entry_offsets,
                                  const int* tile_offsets, int knn_k, long long max_tiles, cudaStream_t stream);
 int launch_field_fwd_tc_gather(const NgmFieldFwdArgs& a, const int* entries, const int* entry_offsets,
-                               const int* tile_offsets, int knn_k, long long max_tiles, cudaStream_t stream);
+                               const int* tile_offsets, int knn_k, long long max_tiles, const void* rows_half,
+                               cudaStream_t stream);
+int launch_permuto_rows_f32(const PermutoRowsArgs& a, cudaStream_t stream);
+int launch_permuto_rows_half(const PermutoRowsArgs& a, cudaStream_t stream);
 size_t field_tc_workspace_bytes(const NgmFieldDesc& fd, int num_fields);
 
 namespace {
@@ -35,12 +38,13 @@ struct KnnWs {
   int* entries;        // [N*K]
   float* pair_out;     // [N*K*4]
   void* tc;            // fp16 path: per-field weight images
+  void* rows;          // permutohedral encoding: pre-encoded layer-0 rows per entry (fp32: E floats, fp16: EP halves)
   size_t total;
 };
 
 size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 
-KnnWs carve(void* base, long long N, int K, int F, size_t tc_bytes) {
+KnnWs carve(void* base, long long N, int K, int F, size_t tc_bytes, size_t row_bytes) {
   KnnWs w{};
   char* b = static_cast<char*>(base);
   size_t o = 0;
@@ -54,6 +58,7 @@ KnnWs carve(void* base, long long N, int K, int F, size_t tc_bytes) {
   w.entries = reinterpret_cast<int*>(take((size_t)N * K * 4));
   w.pair_out = reinterpret_cast<float*>(take((size_t)N * K * 16));
   w.tc = take(tc_bytes);
+  w.rows = take((size_t)N * K * row_bytes);
   w.total = o;
   return w;
 }
@@ -201,9 +206,18 @@ static size_t tc_bytes_of(const NgmKnnFwdArgs& a) {
   return a.precision == NGM_PREC_FP16 ? field_tc_workspace_bytes(a.field, a.num_fields) : 0;
 }
 
+// bytes of one pre-encoded row (0: the field kernel encodes in-line)
+static size_t row_bytes_of(const NgmKnnFwdArgs& a) {
+  if (a.field.encoding != NGM_ENC_PERMUTO || a.field.permuto_feats != 2) return 0;
+  if (a.precision == NGM_PREC_FP16) return (size_t)((a.field.dim_encoding + 15) / 16 * 16) * 2;
+  // fp32: measured no gain on this path (the narrow FFMA kernel already runs three CTAs per SM and hides the
+  // gathers: 39.8 ms in-kernel against 42.0 ms with fp32 rows on the 640x480x64 eval frame), so it encodes in-line
+  return 0;
+}
+
 size_t knn_workspace_bytes(const NgmKnnFwdArgs& a) {
   const int K = a.num_knn < a.num_fields ? a.num_knn : a.num_fields;
-  return carve(nullptr, a.num_points, K > 0 ? K : 1, a.num_fields, tc_bytes_of(a)).total;
+  return carve(nullptr, a.num_points, K > 0 ? K : 1, a.num_fields, tc_bytes_of(a), row_bytes_of(a)).total;
 }
 
 int launch_fieldset_knn(const NgmKnnFwdArgs& a, cudaStream_t stream) {
@@ -211,7 +225,8 @@ int launch_fieldset_knn(const NgmKnnFwdArgs& a, cudaStream_t stream) {
   const int F = a.num_fields;
   const int K = a.num_knn < F ? a.num_knn : F;  // models.py:355-358
   if (N == 0) return NGM_OK;
-  const KnnWs w = carve(a.workspace, N, K, F, tc_bytes_of(a));
+  const size_t row_bytes = row_bytes_of(a);
+  const KnnWs w = carve(a.workspace, N, K, F, tc_bytes_of(a), row_bytes);
   NGM_CUDA(cudaMemsetAsync(w.counts, 0, (size_t)(F + 1) * sizeof(int), stream));
   const unsigned pb = (unsigned)((N + 255) / 256);
   knn_assign_kernel<<<pb, 256, 0, stream>>>(a.points, N, a.positions, F, K, a.field_radius, a.distance_factor,
@@ -236,11 +251,31 @@ int launch_fieldset_knn(const NgmKnnFwdArgs& a, cudaStream_t stream) {
   f.scale_mode = a.scale_mode;
   f.precision = a.precision;
   f.workspace = w.tc;
+  if (row_bytes) {  // permutohedral encoding: one whole-GPU pass encodes every (point, neighbour) entry
+    PermutoRowsArgs e{};
+    e.field = a.field;
+    e.points_world = a.points;
+    e.positions = a.positions; e.orientations = a.orientations;
+    e.field_slots = reinterpret_cast<const long long*>(a.field_slots);
+    e.out = static_cast<uint32_t*>(w.rows);
+    e.num_points = NK;
+    e.points_per_field = 1;
+    e.field_radius = a.scale_radius;
+    e.scale_mode = a.scale_mode;
+    e.EP = (a.field.dim_encoding + 15) / 16 * 16;
+    e.pair_field = w.pair_field;
+    e.knn_k = K;
+    if (int rc = a.precision == NGM_PREC_FP16 ? launch_permuto_rows_half(e, stream) : launch_permuto_rows_f32(e, stream))
+      return rc;
+  }
   const long long max_tiles = (NK + 127) / 128 + F;  // upper bound of sum_f ceil(count_f / 128)
   if (a.precision == NGM_PREC_FP16) {  // tcgen05 field kernel in gather mode
-    if (int rc = launch_field_fwd_tc_gather(f, w.entries, w.entry_offsets, w.tile_offsets, K, max_tiles, stream)) return rc;
-  } else if (int rc = launch_field_fwd_simt_gather(f, w.entries, w.entry_offsets, w.tile_offsets, K, max_tiles, stream)) {
-    return rc;
+    if (int rc = launch_field_fwd_tc_gather(f, w.entries, w.entry_offsets, w.tile_offsets, K, max_tiles,
+                                            row_bytes ? w.rows : nullptr, stream))
+      return rc;
+  } else {
+    f.workspace = row_bytes ? w.rows : nullptr;  // fp32: the gather-mode kernel reads these rows
+    if (int rc = launch_field_fwd_simt_gather(f, w.entries, w.entry_offsets, w.tile_offsets, K, max_tiles, stream)) return rc;
   }
 
   knn_blend_kernel<<<pb, 256, 0, stream>>>(w.pair_field, w.pair_w, w.pair_out, N, K, a.outside_value, a.out);

@@ -12,14 +12,26 @@ import torch  # noqa: E402
 import bench  # noqa: E402
 import neural_graph_mapping_b200 as ngm  # noqa: E402
 
+import copy  # noqa: E402
+
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+import bench_variants as bv  # noqa: E402
+
 dev = "cuda:0"
-sc = bench.synthetic_scene(1234)
 cam = ngm.Camera(**bench.CAMERA)
-ijs = sc["ijs"].reshape(-1, 2).to(dev)
-near, far = sc["near"].reshape(-1).to(dev), sc["far"].reshape(-1).to(dev)
-c2w = sc["c2w"].to(dev)
-for prec, reps in (("fp16", 5), ("fp32", 1)):
-    st = ngm.RenderState(bench.config_dict(dev, prec))
+runs = [("nerf8_4x128", "fp16", 5), ("nerf8_4x128", "fp32", 1),
+        ("permuto_1x32 (reference default field)", "fp16", 3), ("permuto_1x32 (reference default field)", "fp32", 3)]
+for variant, prec, reps in runs:
+    enc, ekw, E, L, W = bv.VARIANTS[variant]
+    sc = bv.scene(E, L, W, enc)
+    ijs = sc["ijs"].reshape(-1, 2).to(dev)
+    near, far = sc["near"].reshape(-1).to(dev), sc["far"].reshape(-1).to(dev)
+    c2w = sc["c2w"].to(dev)
+    cfg = copy.deepcopy(bench.config_dict(dev, prec))
+    cfg["model_kwargs"]["field_kwargs"].update(
+        encoding_type=f"neural_graph_mapping_b200.positional_encodings.{enc}", encoding_kwargs=dict(ekw), num_layers=L,
+        dim_mlp_out=W)
+    st = ngm.RenderState(cfg)
     st.set_fields(sc["params"], sc["positions"], sc["orientations"])
     ts = []
     with torch.no_grad():
@@ -32,6 +44,6 @@ for prec, reps in (("fp16", 5), ("fp32", 1)):
             if i > 0:
                 ts.append(e0.elapsed_time(e1))
     ms = sum(ts) / len(ts)
-    print(json.dumps({"path": "kNN (use_vmap=False), K=2, 75 fields, 307200 rays x 64", "precision": prec,
+    print(json.dumps({"path": "kNN (use_vmap=False), K=2, 75 fields, 307200 rays x 64", "field": variant, "precision": prec,
                       "ms_per_frame": round(ms, 3), "rays_per_s": round(307200 / ms * 1e3),
                       "inside_fraction": round(float((p.term_probs > 0).float().mean()), 3)}), flush=True)
