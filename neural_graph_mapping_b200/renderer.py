@@ -260,6 +260,14 @@ def quadrature(driver, sample_colors, sample_geometries, sample_distances, sampl
             dvar.reshape(leading), term.reshape(leading), weights.reshape(*leading, -1))
 
 
+# render_image pixel blocks: the reference cuts the image into `pixel_block_size` (8,192) pixel blocks to bound the
+# memory of its PyTorch intermediates (ngm/run_mapping.py:424-435).  Pixels are independent, so the block size only
+# changes memory and launch count; the CUDA path needs ~200 B of workspace per sample and renders a 640x480x64 frame
+# in 11.1 ms as one block against 12.9 ms as 38 blocks (tools/bench_knn.py).  Blocks are therefore at least this
+# many pixels (0 = exactly the reference's blocks).
+IMAGE_BLOCK_PIXELS = 1 << 19
+
+
 @torch.no_grad()
 def render_image(driver, c2w: torch.Tensor, camera, progressbar: bool = False):
     """Drop-in for ``NeuralGraphMap.render_image`` (ngm/run_mapping.py:402-437)."""
@@ -267,7 +275,7 @@ def render_image(driver, c2w: torch.Tensor, camera, progressbar: bool = False):
     dev = driver._device
     ijs = torch.cartesian_prod(torch.arange(h, device=dev), torch.arange(w, device=dev))
     rgbds, _, d_vars, _, _, _ = batched_evaluation(
-        lambda x: driver._render_ijs(x, c2w, camera), ijs, block_size=driver._pixel_block_size,
+        lambda x: driver._render_ijs(x, c2w, camera), ijs, block_size=max(int(driver._pixel_block_size), IMAGE_BLOCK_PIXELS),
         progressbar=progressbar)
     return rgbds.reshape(h, w, 4), d_vars.reshape(h, w)
 

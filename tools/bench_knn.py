@@ -47,3 +47,28 @@ for variant, prec, reps in runs:
     print(json.dumps({"path": "kNN (use_vmap=False), K=2, 75 fields, 307200 rays x 64", "field": variant, "precision": prec,
                       "ms_per_frame": round(ms, 3), "rays_per_s": round(307200 / ms * 1e3),
                       "inside_fraction": round(float((p.term_probs > 0).float().mean()), 3)}), flush=True)
+
+
+# render_image (the driver's call, run_mapping.py:402-437): whole 640x480 frame, reference block size vs ours
+from neural_graph_mapping_b200 import renderer  # noqa: E402
+
+enc, ekw, E, L, W = bv.VARIANTS["nerf8_4x128"]
+sc = bv.scene(E, L, W, enc)
+cfg = copy.deepcopy(bench.config_dict(dev, "fp16"))
+cfg["eval_near_distance"], cfg["eval_far_distance"], cfg["eval_num_samples"] = 1.0, 3.0, 64
+st = ngm.RenderState(cfg)
+st.set_fields(sc["params"], sc["positions"], sc["orientations"])
+st.eval()
+for blk in (0, renderer.IMAGE_BLOCK_PIXELS):
+    renderer.IMAGE_BLOCK_PIXELS = blk
+    ts = []
+    for i in range(4):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        img, dv = st.render_image(sc["c2w"].to(dev), cam)
+        e1.record()
+        torch.cuda.synchronize()
+        if i > 0:
+            ts.append(e0.elapsed_time(e1))
+    print(json.dumps({"call": "render_image 640x480, eval samples", "min_block_pixels": blk,
+                      "ms_per_frame": round(sum(ts) / len(ts), 3)}), flush=True)
