@@ -22,8 +22,7 @@ SURVEY.md 8(f).
 from __future__ import annotations
 
 import ctypes as C
-import math
-from typing import Dict, Optional
+from typing import Dict
 
 import torch
 

@@ -7,7 +7,7 @@ single all-gather of the rendered tiles (9 fp32 = 36 B per ray: rgbd 4, colour v
 """
 from __future__ import annotations
 
-from typing import Optional, Tuple
+from typing import Tuple
 
 import torch
 

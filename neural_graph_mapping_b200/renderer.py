@@ -18,7 +18,7 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib, models
-from .camera import Camera, camera_struct, sample_rays
+from .camera import camera_struct
 from .utils import batched_evaluation, str_to_object
 
 # ngm/run_mapping.py:59-69

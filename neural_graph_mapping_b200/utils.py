@@ -3,7 +3,7 @@ from __future__ import annotations
 
 import inspect
 from pydoc import locate
-from typing import Any, Callable, Tuple
+from typing import Any, Callable
 
 import torch
 
