@@ -40,6 +40,8 @@ size_t field_simt_smem_bytes(const NgmFieldDesc& fd, int* act_stride, int* enc_s
 // fp16 tcgen05 path (field_tc.cu)
 bool field_tc_supported(const NgmFieldDesc& fd, const char** why);
 size_t field_tc_workspace_bytes(const NgmFieldDesc& fd, int num_fields);
+size_t field_tc_fwd_workspace_bytes(const NgmFieldFwdArgs& a);
+bool tc_rows_required(const NgmFieldDesc& fd);
 int launch_field_fwd_tc(const NgmFieldFwdArgs& a, cudaStream_t stream);
 bool render_fused_tc_ok(const NgmRenderArgs& a);
 int launch_render_fused_tc(const NgmRenderArgs& a, void* tc_ws, float* isd_ws, const void* rows_half, const float* dist,
@@ -125,7 +127,11 @@ static RenderWorkspace render_workspace(const NgmRenderArgs& a) {
   }
   w.isd = off;         off = align_up(off + (size_t)a.num_fields * sizeof(float), 256);
   w.tc = off;
-  if (a.precision == NGM_PREC_FP16) off = align_up(off + field_tc_workspace_bytes(a.field, a.num_fields), 256);
+  if (a.precision == NGM_PREC_FP16) {
+    off = align_up(off + field_tc_workspace_bytes(a.field, a.num_fields), 256);
+    if (!fused && tc_rows_required(a.field))  // staged path (> 128 samples per ray): rows of the dense field evaluation
+      off = align_up(off + n * ((size_t)(a.field.dim_encoding + 15) / 16 * 16) * 2, 256);
+  }
   w.total = off;
   return w;
 }
@@ -167,7 +173,7 @@ int ngm_sample_rays(const NgmSampleArgs* a, void* stream) {
 
 int ngm_field_fwd_workspace_bytes(const NgmFieldFwdArgs* a, size_t* out) {
   NGM_CHECK_ARG(a && out, "null args");
-  *out = a->precision == NGM_PREC_FP16 ? field_tc_workspace_bytes(a->field, a->num_fields) : field_simt_workspace_bytes(*a);
+  *out = a->precision == NGM_PREC_FP16 ? field_tc_fwd_workspace_bytes(*a) : field_simt_workspace_bytes(*a);
   return NGM_OK;
 }
 
@@ -186,7 +192,7 @@ int ngm_field_fwd(const NgmFieldFwdArgs* a, void* stream) {
   if (a->precision == NGM_PREC_FP16) {
     const char* why = nullptr;
     NGM_UNSUPPORTED(!field_tc_supported(a->field, &why), "fp16 tensor-core path unsupported: %s", why);
-    size_t need = field_tc_workspace_bytes(a->field, a->num_fields);
+    size_t need = field_tc_fwd_workspace_bytes(*a);
     if (need > a->workspace_bytes || (need && !a->workspace)) {
       set_error("workspace too small: need %zu B, have %zu B", need, a->workspace_bytes);
       return NGM_ERR_WORKSPACE;

@@ -206,6 +206,54 @@ int launch_encode_fwd(const NgmEncodeArgs& a, cudaStream_t stream) {
   return check_launch("encode_fwd_kernel");
 }
 
+// fp16 A-operand rows for the encodings whose features are independent functions of the point (NeRF, Fourier,
+// Triplane): one thread per (point, 8 features).  This is what puts Fourier and Triplane fields on the tcgen05
+// renderer: the fused kernel reads these rows like the permutohedral ones.
+__global__ void __launch_bounds__(256) feature_rows_half_kernel(PermutoRowsArgs a) {
+  const NgmFieldDesc& fd = a.field;
+  const int E = fd.dim_encoding, groups = a.EP / 8;
+  const long long total = a.num_points * groups;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(idx % groups);
+    const long long pt = idx / groups;
+    long long f = pt / a.points_per_field, src_pt = pt;
+    if (a.pair_field) {
+      f = __ldg(a.pair_field + pt);
+      if (f < 0) continue;
+      src_pt = pt / a.knn_k;
+    }
+    const long long slot = a.field_slots ? a.field_slots[f] : f;
+    const long long pose = a.pair_field ? f : slot;
+    const float* src = a.points_world + src_pt * 3;
+    float3 x = make_float3(__ldg(src), __ldg(src + 1), __ldg(src + 2));
+    if (a.positions) {
+      const float* c = a.positions + pose * 3;
+      const float* q = a.orientations + pose * 4;
+      x = make_float3(x.x - __ldg(c), x.y - __ldg(c + 1), x.z - __ldg(c + 2));
+      x = quat_inv_rotate(__ldg(q), __ldg(q + 1), __ldg(q + 2), __ldg(q + 3), x);
+    }
+    x = scale_local(x, a.scale_mode, a.field_radius);
+    const float xs[3] = {x.x, x.y, x.z};
+    const float* ep = fd.enc_param0 ? fd.enc_param0 + slot * fd.enc_param0_stride : nullptr;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = 8 * g + i;
+      v[i] = 0.0f;
+      if (c < E) {
+        if (fd.encoding == NGM_ENC_NERF) v[i] = nerf_feature(xs, c, fd.nerf_num_octaves, fd.nerf_start_octave);
+        else if (fd.encoding == NGM_ENC_FOURIER) v[i] = fourier_feature(xs, c, ep, fd.fourier_raw_coords);
+        else v[i] = triplane_feature(xs, c, ep, fd.triplane_resolution, fd.triplane_components, fd.triplane_mode);
+      }
+    }
+    __half2 h[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+    *reinterpret_cast<uint4*>(a.out + pt * (a.EP / 2) + 4 * g) = *reinterpret_cast<const uint4*>(h);
+  }
+}
+
 int launch_permuto_rows_f32(const PermutoRowsArgs& a, cudaStream_t stream) {
   if (a.num_points == 0) return NGM_OK;
   const long long items = a.num_points * ((a.field.permuto_levels + 3) / 4);
@@ -217,6 +265,13 @@ int launch_permuto_rows_f32(const PermutoRowsArgs& a, cudaStream_t stream) {
 
 int launch_permuto_rows_half(const PermutoRowsArgs& a, cudaStream_t stream) {
   if (a.num_points == 0) return NGM_OK;
+  if (a.field.encoding != NGM_ENC_PERMUTO) {
+    const long long items = a.num_points * (a.EP / 8);
+    long long blocks = (items + 255) / 256;
+    const long long cap = (long long)num_sms() * 64;
+    feature_rows_half_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, stream>>>(a);
+    return check_launch("feature_rows_half_kernel");
+  }
   const long long items = a.num_points * ((a.field.permuto_levels + 3) / 4);
   long long blocks = (items + 255) / 256;
   const long long cap = (long long)num_sms() * 64;  // 8 resident CTAs per SM x 8 rounds, then grid-stride

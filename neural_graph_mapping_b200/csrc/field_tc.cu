@@ -1013,6 +1013,11 @@ int launch_tc(const TcParams& p_in, int octaves, size_t smem, int grid, cudaStre
 
 int ep_of(const NgmFieldDesc& fd) { return (fd.dim_encoding + 15) / 16 * 16; }
 
+// kernel variant: 4 / 8 = NeRF front end in the kernel; 0 = permutohedral front end or pre-encoded rows
+int tc_oct(const NgmFieldDesc& fd) {
+  return fd.encoding == NGM_ENC_NERF && nerf_octaves_supported(fd.nerf_num_octaves) ? fd.nerf_num_octaves : 0;
+}
+
 int fill_common(TcParams& p, const NgmFieldDesc& fd, int num_fields, const float* positions, const float* orientations,
                 const int64_t* slots, int scale_mode, float radius, void* workspace, cudaStream_t stream) {
   p.E = fd.dim_encoding;
@@ -1052,11 +1057,21 @@ size_t tc_smem_bytes(const TcImage& im) {
 
 }  // namespace
 
+// Encodings without an in-kernel front end (Fourier, Triplane, NeRF with an octave count other than 4 / 8) always
+// reach the kernel as pre-encoded fp16 rows.
+bool tc_rows_required(const NgmFieldDesc& fd) {
+  return fd.encoding == NGM_ENC_FOURIER || fd.encoding == NGM_ENC_TRIPLANE ||
+         (fd.encoding == NGM_ENC_NERF && !nerf_octaves_supported(fd.nerf_num_octaves));
+}
+
 bool field_tc_supported(const NgmFieldDesc& fd, const char** why) {
   const char* w = nullptr;
-  if (fd.encoding != NGM_ENC_NERF && fd.encoding != NGM_ENC_PERMUTO)
-    w = "only the NeRF and permutohedral encodings are on the tcgen05 path in this revision";
-  else if (fd.encoding == NGM_ENC_NERF && !nerf_octaves_supported(fd.nerf_num_octaves)) w = "num_octaves must be 4 or 8";
+  if (fd.encoding != NGM_ENC_NERF && fd.encoding != NGM_ENC_PERMUTO && fd.encoding != NGM_ENC_FOURIER &&
+      fd.encoding != NGM_ENC_TRIPLANE)
+    w = "unknown encoding";
+  else if ((fd.encoding == NGM_ENC_FOURIER || fd.encoding == NGM_ENC_TRIPLANE ||
+            (fd.encoding == NGM_ENC_NERF && !nerf_octaves_supported(fd.nerf_num_octaves))) && ep_of(fd) > 64)
+    w = "pre-encoded rows: encoding wider than 64 features";  // (these encodings reach the kernel as fp16 rows)
   else if (fd.encoding == NGM_ENC_PERMUTO && fd.permuto_feats != 2) w = "permutohedral: nr_feat_per_level must be 2 on the tcgen05 path";
   else if (fd.encoding == NGM_ENC_PERMUTO && ep_of(fd) > 64) w = "permutohedral: encoding wider than 64 features";
   else if (fd.skip_mode != NGM_SKIP_NO) w = "skip connections are only on the fp32 path";
@@ -1073,6 +1088,15 @@ size_t field_tc_workspace_bytes(const NgmFieldDesc& fd, int num_fields) {
   return (size_t)make_image(fd, ep_of(fd)).total_bytes * (size_t)(num_fields > 0 ? num_fields : 1);
 }
 
+// dense field evaluation: weight images, then (for encodings without an in-kernel front end) one fp16 row per point
+size_t field_tc_fwd_workspace_bytes(const NgmFieldFwdArgs& a) {
+  size_t n = (field_tc_workspace_bytes(a.field, a.num_fields) + 255) / 256 * 256;
+  if (tc_rows_required(a.field)) n += (size_t)a.num_fields * (size_t)a.points_per_field * (size_t)ep_of(a.field) * 2;
+  return n;
+}
+
+int launch_permuto_rows_half(const PermutoRowsArgs& a, cudaStream_t stream);
+
 int launch_field_fwd_tc(const NgmFieldFwdArgs& a, cudaStream_t stream) {
   TcParams p{};
   if (int rc = fill_common(p, a.field, a.num_fields, a.positions, a.orientations, a.field_slots, a.scale_mode,
@@ -1083,9 +1107,25 @@ int launch_field_fwd_tc(const NgmFieldFwdArgs& a, cudaStream_t stream) {
   p.out = a.out;
   p.tiles_per_field = (a.points_per_field + 127) / 128;
   p.total_tiles = p.tiles_per_field * a.num_fields;
+  if (tc_rows_required(a.field)) {
+    PermutoRowsArgs e{};
+    e.field = a.field;
+    e.points_world = a.points;
+    e.positions = a.positions; e.orientations = a.orientations;
+    e.field_slots = reinterpret_cast<const long long*>(a.field_slots);
+    e.out = reinterpret_cast<uint32_t*>(static_cast<char*>(a.workspace) +
+                                        (field_tc_workspace_bytes(a.field, a.num_fields) + 255) / 256 * 256);
+    e.num_points = (long long)a.num_fields * a.points_per_field;
+    e.points_per_field = a.points_per_field;
+    e.field_radius = a.field_radius;
+    e.scale_mode = a.scale_mode;
+    e.EP = p.EP;
+    if (int rc = launch_permuto_rows_half(e, stream)) return rc;
+    p.raw_a = reinterpret_cast<const __half*>(e.out);
+  }
   const int grid = tc_grid(p.total_tiles);
   if (tc3_enabled() && tc3_supported(a.field, p.im)) return launch_tc3(p, a.field.nerf_num_octaves, grid, stream);
-  return launch_tc<1>(p, a.field.encoding == NGM_ENC_PERMUTO ? 0 : a.field.nerf_num_octaves, tc_smem_bytes(p.im), grid, stream);
+  return launch_tc<1>(p, tc_oct(a.field), tc_smem_bytes(p.im), grid, stream);
 }
 
 // kNN path: every tile is 128 (point, neighbour) entries of ONE field; the tile count lives in tile_offsets[F]
@@ -1107,7 +1147,7 @@ int launch_field_fwd_tc_gather(const NgmFieldFwdArgs& a, const int* entries, con
   p.tiles_per_field = 1;
   p.total_tiles = max_tiles;
   const int grid = tc_grid(max_tiles);
-  return launch_tc<1>(p, a.field.encoding == NGM_ENC_PERMUTO ? 0 : a.field.nerf_num_octaves, tc_smem_bytes(p.im), grid, stream);
+  return launch_tc<1>(p, tc_oct(a.field), tc_smem_bytes(p.im), grid, stream);
 }
 
 // debug / unit-test entry: D = A (fp16, given) x W^T with the production weight packing, smem
@@ -1174,8 +1214,8 @@ bool render_tc_precoded(const NgmRenderArgs& a) {
   const char* e = getenv("NGM_TC_PERMUTO_INKERNEL");  // read per call: tests compare both front ends
   const bool inkernel = e && e[0] == '1';
   const long long St = a.num_samples + (a.gt ? a.num_samples_guided : 0);
-  return a.field.encoding == NGM_ENC_PERMUTO && !inkernel &&
-         (long long)a.num_fields * a.rays_per_field * St < (1ll << 31);
+  const bool fits = (long long)a.num_fields * a.rays_per_field * St < (1ll << 31);
+  return tc_rows_required(a.field) || (a.field.encoding == NGM_ENC_PERMUTO && !inkernel && fits);
 }
 
 int launch_render_fused_tc(const NgmRenderArgs& a, void* tc_ws, float* isd_ws, const void* rows_half, const float* dist,
@@ -1216,7 +1256,7 @@ int launch_render_fused_tc(const NgmRenderArgs& a, void* tc_ws, float* isd_ws, c
   p.tiles_per_field = (a.rays_per_field + p.rpt - 1) / p.rpt;
   p.total_tiles = p.tiles_per_field * a.num_fields;
   const int grid = tc_grid(p.total_tiles);
-  return launch_tc<0>(p, a.field.encoding == NGM_ENC_PERMUTO ? 0 : a.field.nerf_num_octaves, tc_smem_bytes(p.im), grid, stream);
+  return launch_tc<0>(p, tc_oct(a.field), tc_smem_bytes(p.im), grid, stream);
 }
 
 }  // namespace ngm

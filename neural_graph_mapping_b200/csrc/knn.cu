@@ -22,6 +22,7 @@ int launch_field_fwd_tc_gather(const NgmFieldFwdArgs& a, const int* entries, con
 int launch_permuto_rows_f32(const PermutoRowsArgs& a, cudaStream_t stream);
 int launch_permuto_rows_half(const PermutoRowsArgs& a, cudaStream_t stream);
 size_t field_tc_workspace_bytes(const NgmFieldDesc& fd, int num_fields);
+bool tc_rows_required(const NgmFieldDesc& fd);
 
 namespace {
 
@@ -208,8 +209,10 @@ static size_t tc_bytes_of(const NgmKnnFwdArgs& a) {
 
 // bytes of one pre-encoded row (0: the field kernel encodes in-line)
 static size_t row_bytes_of(const NgmKnnFwdArgs& a) {
+  const size_t half_row = (size_t)((a.field.dim_encoding + 15) / 16 * 16) * 2;
+  if (a.precision == NGM_PREC_FP16 && tc_rows_required(a.field)) return half_row;  // Fourier / Triplane: always rows
   if (a.field.encoding != NGM_ENC_PERMUTO || a.field.permuto_feats != 2) return 0;
-  if (a.precision == NGM_PREC_FP16) return (size_t)((a.field.dim_encoding + 15) / 16 * 16) * 2;
+  if (a.precision == NGM_PREC_FP16) return half_row;
   // fp32: measured no gain on this path (the narrow FFMA kernel already runs three CTAs per SM and hides the
   // gathers: 39.8 ms in-kernel against 42.0 ms with fp32 rows on the 640x480x64 eval frame), so it encodes in-line
   return 0;

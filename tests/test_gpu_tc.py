@@ -405,3 +405,55 @@ def test_fieldset_knn_permuto_vs_oracle(prec):
         assert e.max().item() < 2e-3 * max(scale, 1.0) and e.mean().item() < 1e-4 * max(scale, 1.0), (e.max().item(), e.mean().item())
     else:
         assert e.max().item() < 2e-2 * scale and e.mean().item() < 3e-3 * scale, (e.max().item(), e.mean().item(), scale)
+
+
+_ROW_ENCODINGS = [
+    ("fourier", "PositionalEncodingFourier", {"dim_in": 3, "dim_out": 35, "mu": 0.0, "sigma": 2.0, "raw_coords": True}),
+    ("triplane", "TriplaneEncoding", {"resolution": 16, "num_components": 32, "init_scale": 0.5, "mode": "sum"}),
+    ("nerf", "PositionalEncodingNeRF", {"dim_in": 3, "num_octaves": 6}),
+]
+
+
+@pytest.mark.parametrize("kind,enc_cls,ekw", _ROW_ENCODINGS)
+def test_row_encoded_fields_fp16(kind, enc_cls, ekw):
+    """Encodings without an in-kernel front end (Fourier, Triplane, NeRF with 6 octaves) on the tcgen05 path through
+    pre-encoded fp16 rows: dense field evaluation, the fused renderer and the kNN path, against the fp32 kernels."""
+    import neural_graph_mapping_b200 as ngm
+
+    meta, a = G.load("vmap_guided_nrgbd")
+    g = torch.Generator().manual_seed(len(kind))
+    F, Rr, S, W, L = 3, 200, 32, 64, 2
+    spec = R.FieldSpec(kind, dict(ekw), L, 4, W, "no")
+    params = R.stack_params([R.init_field_params(spec, g) for _ in range(F)])
+    params[f"_linears.{L}.weight"][:, 3] *= 10.0
+    params[f"_linears.{L}.bias"][:, 3] += 0.3
+    fk = {"encoding_type": f"neural_graph_mapping.positional_encodings.{enc_cls}", "encoding_kwargs": dict(ekw),
+          "num_layers": L, "dim_out": 4, "dim_mlp_out": W, "skip_mode": "no", "initial_geometry_bias": 0.0,
+          "neus_initial_sd": 1.0}
+    meta = dict(meta, num_samples=S, num_samples_depth_guided=0, field_kwargs=fk)
+    arrays = {f"param:{k}": v for k, v in params.items()}
+    arrays["positions"], arrays["orientations"] = a["positions"][:F], a["orientations"][:F]
+    ijs = torch.stack([torch.randint(0, 480, (F, Rr), generator=g), torch.randint(0, 640, (F, Rr), generator=g)], -1)
+    near = torch.rand(F, Rr, generator=g) * 0.5 + 0.3
+    far = near + 1.5
+    jit = torch.rand(F, Rr, S, generator=g)
+    cam = ngm.Camera(**meta["camera"])
+    pts = arrays["positions"][:, None] + torch.rand(F, 700, 3, generator=g) * 1.6 - 0.8
+    out = {}
+    for prec in ("fp32", "fp16"):
+        st = make_state(meta, arrays, DEV, prec)
+        with torch.no_grad():
+            pr = st._render_ijs(ijs.to(DEV), a["c2ws"][:F, :1].expand(F, Rr, 4, 4).to(DEV), cam, torch.arange(F, device=DEV),
+                                True, near.to(DEV), far.to(DEV), None, jitter=jit.to(DEV))
+            st._model.set_vmap_fields(None)
+            dense = st._model(pts.to(DEV), arrays["positions"].to(DEV), arrays["orientations"].to(DEV), None, True)
+            knn = st._model(pts.reshape(-1, 3).to(DEV), arrays["positions"].to(DEV), arrays["orientations"].to(DEV), None, False)
+        out[prec] = (pr, dense, knn)
+    p32, d32, k32 = out["fp32"]
+    p16, d16, k16 = out["fp16"]
+    scale = d32.abs().max().item()
+    assert (d16 - d32).abs().max().item() < 2e-2 * scale and (d16 - d32).abs().mean().item() < 3e-3 * scale
+    assert (k16 - k32).abs().mean().item() < 3e-3 * scale
+    assert (p16.rgbds[..., :3] - p32.rgbds[..., :3]).abs().mean().item() < 2e-3
+    assert (p16.rgbds[..., 3] - p32.rgbds[..., 3]).abs().mean().item() < 5e-3
+    assert (p16.term_probs - p32.term_probs).abs().mean().item() < 3e-3
