@@ -1,5 +1,7 @@
 #!/bin/bash
-# A/B of kernel variants selected by NGM_TC_FLAGS: one short bench per value, prints fused / field-stage ms.
+# A/B timing on ONE GPU box: one short bench per argument, prints fused / field-stage ms.  An argument of the form
+# lib:<path> switches the library build (NGM_B200_LIB) for the following runs; any other argument is exported as
+# NGM_TC_FLAGS (a free experiment knob a development build may read) and labels the run.
 TAG=${1:-sweep}; shift
 mkdir -p gpurun_out
 # an argument of the form lib:<path> switches the library for the following values
