@@ -80,9 +80,9 @@ def _per_ray(x, leading, device, name):
     return t, 0.0
 
 
-def sample_rays(camera, ijs, num_samples, near, far, gt=None, num_samples_guided=0, range_guided=0.0,
-                c2ws=None, jitter=None, jitter_guided=None, seed=0, offset=0, want_world=False, want_depth=False):
-    """``ngm_sample_rays``: returns (points_cam, distances[, points_world][, depths])."""
+def sample_rays_args(camera, ijs, num_samples, near, far, gt=None, num_samples_guided=0, range_guided=0.0,
+                     c2ws=None, jitter=None, jitter_guided=None, seed=0, offset=0, want_world=False, want_depth=False):
+    """The ``NgmSampleArgs`` of one ``ngm_sample_rays`` call: (args, outputs, tensors the args point into)."""
     if not ijs.is_cuda:
         raise RuntimeError("ijs must be a CUDA tensor: neural_graph_mapping_b200 has no CPU path")
     dev = ijs.device
@@ -131,6 +131,14 @@ def sample_rays(camera, ijs, num_samples, near, far, gt=None, num_samples_guided
         dz = torch.empty(*leading, St, device=dev)
         a.depths = dz.data_ptr()
         outs.append(dz)
+    return a, tuple(outs), (ij, near_t, far_t, gt_t, jt, jg, c2w_t)
+
+
+def sample_rays(camera, ijs, *args, **kwargs):
+    """``ngm_sample_rays``: returns (points_cam, distances[, points_world][, depths]); arguments as
+    :func:`sample_rays_args`."""
+    a, outs, _keep = sample_rays_args(camera, ijs, *args, **kwargs)
+    dev = ijs.device
     with torch.cuda.device(dev):
         _lib.check(_lib.lib.ngm_sample_rays(C.byref(a), _lib.stream_ptr(dev)))
-    return tuple(outs)
+    return outs

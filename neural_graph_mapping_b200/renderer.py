@@ -188,10 +188,10 @@ def render_rays(
     return Prediction(rgbd, cvar, dvar, term, freespace, tsdf)
 
 
-def composite(colors, geometries, distances, depths, geometry_mode, geometry_factor, color_factor=1.0,
-              neus_isd=None, rays_per_isd=1, gt=None, truncation=0.0, overwrite_behind_camera=False,
-              want_weights=False, want_aux=(False, False), color_stride=None, geometry_stride=None):
-    """``ngm_composite`` on flattened rays.  colors/geometries may alias one packed (N,S,4) tensor."""
+def composite_args(colors, geometries, distances, depths, geometry_mode, geometry_factor, color_factor=1.0,
+                   neus_isd=None, rays_per_isd=1, gt=None, truncation=0.0, overwrite_behind_camera=False,
+                   want_weights=False, want_aux=(False, False), color_stride=None, geometry_stride=None):
+    """The ``NgmCompositeArgs`` of one ``ngm_composite`` call and its freshly allocated outputs."""
     dev = distances.device
     N, S = distances.shape
     a = _lib.NgmCompositeArgs()
@@ -222,9 +222,17 @@ def composite(colors, geometries, distances, depths, geometry_mode, geometry_fac
     if want_aux[1]:
         ts, ts_m = torch.empty(N, S, device=dev), torch.empty(N, S, device=dev, dtype=torch.bool)
         a.tsdf, a.tsdf_mask = ts.data_ptr(), ts_m.data_ptr()
+    return a, (rgbd, cvar, dvar, term, weights, (fs, fs_m, ts, ts_m))
+
+
+def composite(colors, geometries, distances, depths, *args, **kwargs):
+    """``ngm_composite`` on flattened rays.  colors/geometries may alias one packed (N,S,4) tensor; arguments as
+    :func:`composite_args`."""
+    a, outs = composite_args(colors, geometries, distances, depths, *args, **kwargs)
+    dev = distances.device
     with torch.cuda.device(dev):
         _lib.check(_lib.lib.ngm_composite(C.byref(a), _lib.stream_ptr(dev)))
-    return rgbd, cvar, dvar, term, weights, (fs, fs_m, ts, ts_m)
+    return outs
 
 
 def quadrature(driver, sample_colors, sample_geometries, sample_distances, sample_depths, neus_isds) -> Tuple:
