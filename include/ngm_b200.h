@@ -216,6 +216,32 @@ typedef struct NgmCompositeBwdArgs {
   float* workspace;         /* >= 2 * num_rays * S floats */
 } NgmCompositeBwdArgs;
 
+/* ---- training: Adam on the active fields, in place ---------------------------------------------
+ * Replaces the optimizer half of NeuralGraphMap._update_step together with the moment gather of
+ * _set_vmap_fields (ngm/run_mapping.py:679-707, 1191-1221): torch.optim.Adam (plain Adam, weight decay
+ * added to the gradient; :347-362) on the gathered rows, then the scatter of parameters and moments back
+ * into the full per-field tables.  One descriptor per parameter tensor that received a gradient. */
+#define NGM_ADAM_MAX_PARAMS 24
+typedef struct NgmAdamParam {
+  float* param_all;       /* (num_fields_total, row): all_fields_params[name], updated in place at field_ids */
+  float* exp_avg_all;     /* (num_fields_total, row): _optim_state[name]["exp_avg"], in place */
+  float* exp_avg_sq_all;  /* (num_fields_total, row): _optim_state[name]["exp_avg_sq"], in place */
+  const float* grad;      /* (num_active, row): vmap_fields_params[name].grad */
+  float* param_active;    /* (num_active, row): vmap_fields_params[name], receives the updated rows; or NULL */
+  int64_t row;            /* elements per field */
+} NgmAdamParam;
+typedef struct NgmAdamArgs {
+  const NgmAdamParam* params;  /* HOST array of num_params descriptors (<= NGM_ADAM_MAX_PARAMS) */
+  const int64_t* field_ids;    /* device (num_active): row of each active field in the full tables, unique;
+                                  NULL = identity */
+  int64_t num_active;
+  int64_t step;                /* Adam's step count INCLUDING this update (>= 1); shared by all fields of a
+                                  parameter tensor, as in the reference (:1213) */
+  double lr, beta1, beta2, eps, weight_decay; /* torch.optim.Adam's hyper-parameters (Python floats = doubles) */
+  int32_t num_params;
+  int32_t _pad;
+} NgmAdamArgs;
+
 /* ---- fused render --------------------------------------------------------------------
  * Replaces NeuralGraphMap._render_ijs with use_vmap=True (ngm/run_mapping.py:440-666):
  * sampler -> world->local -> encoding -> per-field MLP -> compositor for
@@ -281,7 +307,7 @@ int ngm_abi_version(void);
 const char* ngm_last_error(void);
 /* sizeof() of the structs above as compiled, so a binding can verify its mirror:
  * which = 0 NgmCamera, 1 NgmFieldDesc, 2 NgmSampleArgs, 3 NgmFieldFwdArgs, 4 NgmCompositeArgs, 5 NgmRenderArgs,
- * 6 NgmKnnFwdArgs, 7 NgmCompositeBwdArgs, 8 NgmEncodeArgs */
+ * 6 NgmKnnFwdArgs, 7 NgmCompositeBwdArgs, 8 NgmEncodeArgs, 9 NgmAdamParam, 10 NgmAdamArgs */
 size_t ngm_struct_size(int which);
 /* number of CUDA kernels this library has launched in this process (bench.py's gpu_launches) */
 uint64_t ngm_launch_count(void);
@@ -292,6 +318,7 @@ int ngm_composite(const NgmCompositeArgs* args, void* stream);  /* run_mapping.p
 int ngm_composite_bwd(const NgmCompositeBwdArgs* args, void* stream); /* autograd of run_mapping.py:610-639, 709-799 */
 int ngm_encode_fwd(const NgmEncodeArgs* args, void* stream);    /* positional_encodings.py forward()s */
 int ngm_encode_bwd(const NgmEncodeArgs* args, void* stream);    /* d lattice_values of the permutohedral encoding */
+int ngm_adam_step(const NgmAdamArgs* args, void* stream);       /* run_mapping.py:679-707, 1191-1221 */
 int ngm_render_rays_fwd(const NgmRenderArgs* args, void* stream); /* run_mapping.py:440-666 (use_vmap=True) */
 int ngm_fieldset_knn_fwd(const NgmKnnFwdArgs* args, void* stream); /* models.py:347-405 (use_vmap=False) */
 int ngm_fieldset_knn_workspace_bytes(const NgmKnnFwdArgs* args, size_t* out);

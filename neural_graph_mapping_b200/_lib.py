@@ -98,6 +98,20 @@ class NgmEncodeArgs(C.Structure):
     ]
 
 
+class NgmAdamParam(C.Structure):
+    _fields_ = [("param_all", _fp), ("exp_avg_all", _fp), ("exp_avg_sq_all", _fp), ("grad", _fp),
+                ("param_active", _fp), ("row", C.c_int64)]
+
+
+class NgmAdamArgs(C.Structure):
+    _fields_ = [("params", C.POINTER(NgmAdamParam)), ("field_ids", _fp), ("num_active", C.c_int64),
+                ("step", C.c_int64), ("lr", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double),
+                ("eps", C.c_double), ("weight_decay", C.c_double), ("num_params", C.c_int32), ("_pad", C.c_int32)]
+
+
+NGM_ADAM_MAX_PARAMS = 24
+
+
 class NgmRenderArgs(C.Structure):
     _fields_ = [
         ("field", NgmFieldDesc), ("cam", NgmCamera), ("rays_per_field", C.c_int64), ("ijs", _fp), ("c2ws", _fp),
@@ -125,9 +139,9 @@ class NgmKnnFwdArgs(C.Structure):
 
 
 STRUCTS = [NgmCamera, NgmFieldDesc, NgmSampleArgs, NgmFieldFwdArgs, NgmCompositeArgs, NgmRenderArgs, NgmKnnFwdArgs,
-           NgmCompositeBwdArgs, NgmEncodeArgs]
+           NgmCompositeBwdArgs, NgmEncodeArgs, NgmAdamParam, NgmAdamArgs]
 EXPORTS = [
-    "ngm_abi_version", "ngm_last_error", "ngm_struct_size", "ngm_launch_count", "ngm_sample_rays", "ngm_field_fwd", "ngm_composite", "ngm_composite_bwd", "ngm_encode_fwd", "ngm_encode_bwd",
+    "ngm_abi_version", "ngm_last_error", "ngm_struct_size", "ngm_launch_count", "ngm_sample_rays", "ngm_field_fwd", "ngm_composite", "ngm_composite_bwd", "ngm_encode_fwd", "ngm_encode_bwd", "ngm_adam_step",
     "ngm_render_rays_fwd", "ngm_debug_tc_gemm", "ngm_debug_tc_trace", "ngm_debug_tc_trace_peek", "ngm_debug_tmem_bw", "ngm_fieldset_knn_fwd", "ngm_fieldset_knn_workspace_bytes", "ngm_field_fwd_workspace_bytes", "ngm_render_workspace_bytes",
 ]
 
@@ -146,7 +160,7 @@ lib.ngm_launch_count.restype = C.c_uint64
 for _name, _arg in [("ngm_sample_rays", NgmSampleArgs), ("ngm_field_fwd", NgmFieldFwdArgs),
                     ("ngm_composite", NgmCompositeArgs), ("ngm_render_rays_fwd", NgmRenderArgs),
                     ("ngm_fieldset_knn_fwd", NgmKnnFwdArgs), ("ngm_composite_bwd", NgmCompositeBwdArgs),
-                    ("ngm_encode_fwd", NgmEncodeArgs), ("ngm_encode_bwd", NgmEncodeArgs)]:
+                    ("ngm_encode_fwd", NgmEncodeArgs), ("ngm_encode_bwd", NgmEncodeArgs), ("ngm_adam_step", NgmAdamArgs)]:
     getattr(lib, _name).restype = C.c_int
     getattr(lib, _name).argtypes = [C.POINTER(_arg), C.c_void_p]
 lib.ngm_fieldset_knn_workspace_bytes.restype = C.c_int

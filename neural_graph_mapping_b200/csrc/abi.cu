@@ -57,6 +57,7 @@ int launch_fieldset_knn(const NgmKnnFwdArgs& a, cudaStream_t stream);
 int launch_composite_bwd(const NgmCompositeBwdArgs& b, cudaStream_t stream);
 int launch_encode_fwd(const NgmEncodeArgs& a, cudaStream_t stream);
 int launch_encode_bwd(const NgmEncodeArgs& a, cudaStream_t stream);
+int launch_adam_step(const NgmAdamArgs& a, cudaStream_t stream);
 int tc_trace_read(unsigned long long* out, int max_events);
 int tc_trace_peek(unsigned long long* out, int max_events);
 int tmem_bw_bench(int warps, int iters, int mode, unsigned long long* host_cycles);
@@ -159,6 +160,8 @@ size_t ngm_struct_size(int which) {
     case 6: return sizeof(NgmKnnFwdArgs);
     case 7: return sizeof(NgmCompositeBwdArgs);
     case 8: return sizeof(NgmEncodeArgs);
+    case 9: return sizeof(NgmAdamParam);
+    case 10: return sizeof(NgmAdamArgs);
     default: return 0;
   }
 }
@@ -230,6 +233,24 @@ int ngm_composite_bwd(const NgmCompositeBwdArgs* b, void* stream) {
   if (a->geometry_mode == NGM_GEOM_NEUS)
     NGM_CHECK_ARG(a->neus_isd && a->rays_per_isd > 0, "neus mode needs neus_isd");
   return launch_composite_bwd(*b, (cudaStream_t)stream);
+}
+
+int ngm_adam_step(const NgmAdamArgs* a, void* stream) {
+  NGM_CHECK_ARG(a != nullptr, "null args");
+  NGM_CHECK_ARG(a->num_params >= 0 && a->num_params <= NGM_ADAM_MAX_PARAMS, "num_params %d outside [0, %d]", a->num_params,
+                NGM_ADAM_MAX_PARAMS);
+  NGM_CHECK_ARG(a->num_active >= 0, "negative num_active");
+  NGM_CHECK_ARG(a->step >= 1, "step must count this update (>= 1)");
+  NGM_CHECK_ARG(a->lr >= 0.0 && a->eps >= 0.0 && a->weight_decay >= 0.0, "negative lr / eps / weight_decay");
+  NGM_CHECK_ARG(a->beta1 >= 0.0 && a->beta1 < 1.0 && a->beta2 >= 0.0 && a->beta2 < 1.0, "betas outside [0, 1)");
+  NGM_CHECK_ARG(a->num_params == 0 || a->params, "params missing");
+  for (int i = 0; i < a->num_params; ++i) {
+    const NgmAdamParam& d = a->params[i];
+    NGM_CHECK_ARG(d.row >= 0, "negative row size");
+    NGM_CHECK_ARG(d.row == 0 || a->num_active == 0 || (d.param_all && d.exp_avg_all && d.exp_avg_sq_all && d.grad),
+                  "parameter %d: missing table / moment / gradient pointer", i);
+  }
+  return launch_adam_step(*a, (cudaStream_t)stream);
 }
 
 static int validate_encoding(const NgmFieldDesc& fd) {

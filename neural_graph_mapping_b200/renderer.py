@@ -86,7 +86,7 @@ def render_rays(
     keep = []
     a = _lib.NgmRenderArgs()
     proto = model._prototype_field
-    if hasattr(driver, "_set_vmap_fields"):
+    if getattr(driver, "_reference_flow", True) and hasattr(driver, "_set_vmap_fields"):
         # the reference driver: keep its side effects (gather copy + optimizer remap, :500,668-707)
         driver._set_vmap_fields(field_ids)
         params = model.vmap_fields_params
@@ -288,17 +288,29 @@ def render_image(driver, c2w: torch.Tensor, camera, progressbar: bool = False):
     return rgbds.reshape(h, w, 4), d_vars.reshape(h, w)
 
 
-def install(driver_cls) -> None:
+def install(driver_cls, optimizer: bool = True) -> None:
     """Patch the reference's ``NeuralGraphMap`` so its renderer runs on libngm_b200 while the
-    SLAM driver, keyframe selection and loop-closure code stay untouched callers."""
+    SLAM driver, keyframe selection and loop-closure code stay untouched callers.  With ``optimizer`` the Adam
+    update of the active fields (``_set_vmap_fields`` / ``_update_step``) runs as one in-place launch too;
+    ``_init_optimizer``, ``_add_fields`` and ``_optim_state`` stay the driver's own."""
     driver_cls._render_ijs = render_rays
     driver_cls._quadrature = quadrature
     driver_cls.render_image = render_image
+    if optimizer:
+        from . import optim
+
+        driver_cls._set_vmap_fields = optim.set_vmap_fields
+        driver_cls._update_step = optim.update_step
 
 
 class RenderState:
     """Stand-alone holder of exactly the driver state the renderer reads, built from the
     reference's own config keys (ngm/run_mapping.py:116-215, ngm/config/neural_graph_map.yaml)."""
+
+    # False: ``_render_ijs`` reads ``all_fields_params`` in place through field slots (no gather copy per call).
+    # True: the reference driver's flow -- every ``_render_ijs`` first calls ``_set_vmap_fields`` (:500) and runs
+    # on the gathered ``vmap_fields_params``, which ``_update_step`` then optimises.
+    _reference_flow = False
 
     def __init__(self, config: dict) -> None:
         self._config = config
@@ -337,8 +349,13 @@ class RenderState:
         self._global_map_dict = {  # run_mapping.py:231-246
             "positions": torch.zeros(32, 3, device=self._device),
             "orientations": torch.zeros(32, 4, device=self._device),
+            "training_iterations": torch.zeros(32, device=self._device, dtype=torch.long),
             "num": 0,
         }
+        self._learning_rate = config.get("learning_rate", 1e-3)  # run_mapping.py:347-362
+        self._adam_eps = config.get("adam_eps", 1e-8)
+        self._adam_weight_decay = config.get("adam_weight_decay", 0.0)
+        self._optim_state = None
         self.train()
 
     def eval(self) -> None:  # run_mapping.py:1966-1969
@@ -358,6 +375,17 @@ class RenderState:
         self._global_map_dict["positions"] = positions.to(dev).float().contiguous()
         self._global_map_dict["orientations"] = orientations.to(dev).float().contiguous()
         self._global_map_dict["num"] = positions.shape[0]
+        self._global_map_dict["training_iterations"] = torch.zeros(positions.shape[0], device=dev, dtype=torch.long)
+
+    def _set_vmap_fields(self, field_ids: torch.Tensor) -> None:
+        from . import optim
+
+        optim.set_vmap_fields(self, field_ids)
+
+    def _update_step(self, loss_dict: dict, field_ids: torch.Tensor) -> None:
+        from . import optim
+
+        optim.update_step(self, loss_dict, field_ids)
 
     _render_ijs = render_rays
     _quadrature = quadrature

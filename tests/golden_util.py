@@ -81,3 +81,14 @@ def params(arrays, prefix="param:"):
 VMAP_CASES = ["c1_vmap_256x32", "vmap_guided_nrgbd", "vmap_behind_camera", "vmap_neus",
               "vmap_density", "vmap_occupancy", "c2_vmap_w128_s64"]
 KNN_CASES = ["knn_render", "knn_render_w128"]
+
+
+def replay_training(meta, a, iteration_fn, grow_fn):
+    """Drive ``iteration_fn(it, inputs)`` / ``grow_fn(rows)`` through the fixture's schedule."""
+    for st in meta["steps"]:
+        if "grow" in st:
+            it = st["before_iteration"]
+            grow_fn({k[len(f"grow{it}:param:"):]: v for k, v in a.items() if k.startswith(f"grow{it}:param:")})
+        else:
+            it = st["iteration"]
+            iteration_fn(it, {k[len(f"it{it}:"):]: v for k, v in a.items() if k.startswith(f"it{it}:")})

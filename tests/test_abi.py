@@ -53,6 +53,25 @@ def test_argument_errors_without_gpu(lib_mod):
     assert b"num_layers" in lib_mod.lib.ngm_last_error()
 
 
+def test_adam_argument_errors_without_gpu(lib_mod):
+    a = lib_mod.NgmAdamArgs()
+    a.num_active, a.step, a.lr, a.beta1, a.beta2 = 4, 0, 1e-3, 0.9, 0.999
+    assert lib_mod.lib.ngm_adam_step(ctypes.byref(a), None) == -1
+    assert b"step" in lib_mod.lib.ngm_last_error()
+    a.step, a.beta2 = 1, 1.0
+    assert lib_mod.lib.ngm_adam_step(ctypes.byref(a), None) == -1
+    assert b"betas" in lib_mod.lib.ngm_last_error()
+    a.beta2, a.num_params = 0.999, lib_mod.NGM_ADAM_MAX_PARAMS + 1
+    assert lib_mod.lib.ngm_adam_step(ctypes.byref(a), None) == -1
+    d = (lib_mod.NgmAdamParam * 1)()
+    d[0].row = 8  # pointers missing
+    a.params, a.num_params = d, 1
+    assert lib_mod.lib.ngm_adam_step(ctypes.byref(a), None) == -1
+    assert b"missing" in lib_mod.lib.ngm_last_error()
+    a.num_active = 0  # nothing to do: valid, and no launch
+    assert lib_mod.lib.ngm_adam_step(ctypes.byref(a), None) == 0
+
+
 def test_no_cpu_fallback(lib_mod):
     import torch
 
