@@ -377,6 +377,21 @@ class RenderState:
         self._global_map_dict["num"] = positions.shape[0]
         self._global_map_dict["training_iterations"] = torch.zeros(positions.shape[0], device=dev, dtype=torch.long)
 
+    def save_model(self, path: str) -> None:
+        """The checkpoint half of ``NeuralGraphMap.save_model`` (ngm/run_mapping.py:2147-2156): same three keys,
+        same tensors (stacked per-field parameters in the reference's state-dict names, the over-allocated map
+        tables with their ``num``), so either side loads the other's file."""
+        torch.save({"map_dict": self._global_map_dict, "all_fields_params": self._model.all_fields_params,
+                    "state_dict": self._model.state_dict()}, path)
+
+    def load_model(self, path: str) -> None:
+        """``NeuralGraphMap.load_model`` (ngm/run_mapping.py:2166-2173).  The map tables may be over-allocated
+        (32 rows doubled on demand, :231-262); ``num`` rows are valid and the renderer reads only those."""
+        d = torch.load(path, map_location=self._device)
+        self._global_map_dict = d["map_dict"]
+        self._model.all_fields_params = d["all_fields_params"]
+        self._model.load_state_dict(d["state_dict"])
+
     def _set_vmap_fields(self, field_ids: torch.Tensor) -> None:
         from . import optim
 
