@@ -242,6 +242,57 @@ typedef struct NgmAdamArgs {
   int32_t _pad;
 } NgmAdamArgs;
 
+/* ---- training: multi-view target sampling ------------------------------------------------------
+ * The two data-parallel halves of NeuralGraphMap._sample_target_mv (ngm/run_mapping.py:1261-1459), around its one
+ * data-dependent step (drop fields no keyframe sees, draw keyframes with torch.multinomial: :1364-1383).
+ * Keyframe store as the driver holds it: contiguous poses `_c_c2w_tensor` (num_frames,4,4), the RGB-D buffer
+ * `_nc_rgbd_tensor` (num_stored,H,W,4) and the index map `_frame_cid_to_ncid` between them (:1674-1713). */
+typedef struct NgmTargetVisArgs {
+  NgmCamera cam;
+  const float* c2ws;              /* (num_frames, 4, 4) camera-to-world, OpenGL */
+  const float* rgbds;             /* (num_stored, H, W, 4): channel 3 = depth */
+  const int64_t* frame_to_store;  /* (num_frames) row of each frame in rgbds; NULL = identity */
+  const float* positions;         /* field positions table, (>= max field id + 1, 3) */
+  const int64_t* field_ids;       /* (num_fields) rows of the candidate fields; NULL = identity */
+  const float* probe_offsets;     /* (num_probes, 3) unit vectors (:1322-1323) */
+  int64_t num_frames;
+  int32_t num_fields;
+  int32_t num_probes;
+  float train_radius;
+  int32_t _pad;
+  uint8_t* field_kf_mask;         /* out (num_fields, num_frames): field visible in keyframe (:1356-1362) */
+  float* min_xys;                 /* out (num_fields, num_frames, 2): probes' image bounding box, clamped (:1386) */
+  float* max_xys;                 /* out (num_fields, num_frames, 2)  (:1387-1389) */
+} NgmTargetVisArgs;
+
+typedef struct NgmTargetRaysArgs {
+  NgmCamera cam;
+  const float* c2ws;              /* as above */
+  const float* rgbds;
+  const int64_t* frame_to_store;
+  const float* positions;
+  const int64_t* field_ids;       /* (num_fields) rows of the target fields (those some keyframe sees) */
+  const int64_t* frame_cids;      /* (num_fields, rays_per_field) drawn keyframe of every ray (:1381-1383) */
+  const float* uv;                /* (num_fields, rays_per_field, 2) uniform draws in [0,1) (:1398-1400) */
+  const float* min_xys;           /* (num_fields, num_frames, 2): rows of the target fields */
+  const float* max_xys;
+  int64_t num_frames;
+  int64_t rays_per_field;
+  int32_t num_fields;
+  float train_radius;
+  /* outputs = the members of the reference's Target (:43-58), all (num_fields, rays_per_field, ...) */
+  int64_t* ijs;                   /* (.., 2) [row, column] */
+  float* out_c2ws;                /* (.., 4, 4) */
+  float* near;
+  float* far;
+  float* gt;                      /* gt_distances */
+  float* out_rgbds;               /* (.., 4) */
+  uint8_t* rgb_mask;              /* bool */
+  uint8_t* depth_mask;            /* bool */
+  float* term_probs;
+  uint8_t* term_mask;             /* bool */
+} NgmTargetRaysArgs;
+
 /* ---- fused render --------------------------------------------------------------------
  * Replaces NeuralGraphMap._render_ijs with use_vmap=True (ngm/run_mapping.py:440-666):
  * sampler -> world->local -> encoding -> per-field MLP -> compositor for
@@ -307,7 +358,8 @@ int ngm_abi_version(void);
 const char* ngm_last_error(void);
 /* sizeof() of the structs above as compiled, so a binding can verify its mirror:
  * which = 0 NgmCamera, 1 NgmFieldDesc, 2 NgmSampleArgs, 3 NgmFieldFwdArgs, 4 NgmCompositeArgs, 5 NgmRenderArgs,
- * 6 NgmKnnFwdArgs, 7 NgmCompositeBwdArgs, 8 NgmEncodeArgs, 9 NgmAdamParam, 10 NgmAdamArgs */
+ * 6 NgmKnnFwdArgs, 7 NgmCompositeBwdArgs, 8 NgmEncodeArgs, 9 NgmAdamParam, 10 NgmAdamArgs,
+ * 11 NgmTargetVisArgs, 12 NgmTargetRaysArgs */
 size_t ngm_struct_size(int which);
 /* number of CUDA kernels this library has launched in this process (bench.py's gpu_launches) */
 uint64_t ngm_launch_count(void);
@@ -319,6 +371,8 @@ int ngm_composite_bwd(const NgmCompositeBwdArgs* args, void* stream); /* autogra
 int ngm_encode_fwd(const NgmEncodeArgs* args, void* stream);    /* positional_encodings.py forward()s */
 int ngm_encode_bwd(const NgmEncodeArgs* args, void* stream);    /* d lattice_values of the permutohedral encoding */
 int ngm_adam_step(const NgmAdamArgs* args, void* stream);       /* run_mapping.py:679-707, 1191-1221 */
+int ngm_target_visibility(const NgmTargetVisArgs* args, void* stream); /* run_mapping.py:1319-1362, 1386-1389 */
+int ngm_target_rays(const NgmTargetRaysArgs* args, void* stream);      /* run_mapping.py:1398-1445 */
 int ngm_render_rays_fwd(const NgmRenderArgs* args, void* stream); /* run_mapping.py:440-666 (use_vmap=True) */
 int ngm_fieldset_knn_fwd(const NgmKnnFwdArgs* args, void* stream); /* models.py:347-405 (use_vmap=False) */
 int ngm_fieldset_knn_workspace_bytes(const NgmKnnFwdArgs* args, size_t* out);

@@ -12,7 +12,7 @@ INCLUDE = os.path.join(os.path.dirname(PKG_DIR), "include")
 LIB_PATH = os.path.join(PKG_DIR, "libngm_b200.so")
 STAMP = os.path.join(PKG_DIR, ".libngm_b200.stamp")
 
-SOURCES = ["abi.cu", "sampler.cu", "composite.cu", "composite_bwd.cu", "encode.cu", "adam.cu", "field_simt.cu", "field_tc.cu", "knn.cu", "tmem_bench.cu"]
+SOURCES = ["abi.cu", "sampler.cu", "composite.cu", "composite_bwd.cu", "encode.cu", "adam.cu", "targets.cu", "field_simt.cu", "field_tc.cu", "knn.cu", "tmem_bench.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",

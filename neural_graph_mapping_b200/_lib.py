@@ -112,6 +112,21 @@ class NgmAdamArgs(C.Structure):
 NGM_ADAM_MAX_PARAMS = 24
 
 
+class NgmTargetVisArgs(C.Structure):
+    _fields_ = [("cam", NgmCamera), ("c2ws", _fp), ("rgbds", _fp), ("frame_to_store", _fp), ("positions", _fp),
+                ("field_ids", _fp), ("probe_offsets", _fp), ("num_frames", C.c_int64), ("num_fields", C.c_int32),
+                ("num_probes", C.c_int32), ("train_radius", C.c_float), ("_pad", C.c_int32),
+                ("field_kf_mask", _fp), ("min_xys", _fp), ("max_xys", _fp)]
+
+
+class NgmTargetRaysArgs(C.Structure):
+    _fields_ = [("cam", NgmCamera), ("c2ws", _fp), ("rgbds", _fp), ("frame_to_store", _fp), ("positions", _fp),
+                ("field_ids", _fp), ("frame_cids", _fp), ("uv", _fp), ("min_xys", _fp), ("max_xys", _fp),
+                ("num_frames", C.c_int64), ("rays_per_field", C.c_int64), ("num_fields", C.c_int32),
+                ("train_radius", C.c_float), ("ijs", _fp), ("out_c2ws", _fp), ("near", _fp), ("far", _fp), ("gt", _fp),
+                ("out_rgbds", _fp), ("rgb_mask", _fp), ("depth_mask", _fp), ("term_probs", _fp), ("term_mask", _fp)]
+
+
 class NgmRenderArgs(C.Structure):
     _fields_ = [
         ("field", NgmFieldDesc), ("cam", NgmCamera), ("rays_per_field", C.c_int64), ("ijs", _fp), ("c2ws", _fp),
@@ -139,9 +154,10 @@ class NgmKnnFwdArgs(C.Structure):
 
 
 STRUCTS = [NgmCamera, NgmFieldDesc, NgmSampleArgs, NgmFieldFwdArgs, NgmCompositeArgs, NgmRenderArgs, NgmKnnFwdArgs,
-           NgmCompositeBwdArgs, NgmEncodeArgs, NgmAdamParam, NgmAdamArgs]
+           NgmCompositeBwdArgs, NgmEncodeArgs, NgmAdamParam, NgmAdamArgs,
+           NgmTargetVisArgs, NgmTargetRaysArgs]
 EXPORTS = [
-    "ngm_abi_version", "ngm_last_error", "ngm_struct_size", "ngm_launch_count", "ngm_sample_rays", "ngm_field_fwd", "ngm_composite", "ngm_composite_bwd", "ngm_encode_fwd", "ngm_encode_bwd", "ngm_adam_step",
+    "ngm_abi_version", "ngm_last_error", "ngm_struct_size", "ngm_launch_count", "ngm_sample_rays", "ngm_field_fwd", "ngm_composite", "ngm_composite_bwd", "ngm_encode_fwd", "ngm_encode_bwd", "ngm_adam_step", "ngm_target_visibility", "ngm_target_rays",
     "ngm_render_rays_fwd", "ngm_debug_tc_gemm", "ngm_debug_tc_trace", "ngm_debug_tc_trace_peek", "ngm_debug_tmem_bw", "ngm_fieldset_knn_fwd", "ngm_fieldset_knn_workspace_bytes", "ngm_field_fwd_workspace_bytes", "ngm_render_workspace_bytes",
 ]
 
@@ -160,7 +176,8 @@ lib.ngm_launch_count.restype = C.c_uint64
 for _name, _arg in [("ngm_sample_rays", NgmSampleArgs), ("ngm_field_fwd", NgmFieldFwdArgs),
                     ("ngm_composite", NgmCompositeArgs), ("ngm_render_rays_fwd", NgmRenderArgs),
                     ("ngm_fieldset_knn_fwd", NgmKnnFwdArgs), ("ngm_composite_bwd", NgmCompositeBwdArgs),
-                    ("ngm_encode_fwd", NgmEncodeArgs), ("ngm_encode_bwd", NgmEncodeArgs), ("ngm_adam_step", NgmAdamArgs)]:
+                    ("ngm_encode_fwd", NgmEncodeArgs), ("ngm_encode_bwd", NgmEncodeArgs), ("ngm_adam_step", NgmAdamArgs),
+                    ("ngm_target_visibility", NgmTargetVisArgs), ("ngm_target_rays", NgmTargetRaysArgs)]:
     getattr(lib, _name).restype = C.c_int
     getattr(lib, _name).argtypes = [C.POINTER(_arg), C.c_void_p]
 lib.ngm_fieldset_knn_workspace_bytes.restype = C.c_int

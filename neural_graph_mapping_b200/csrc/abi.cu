@@ -58,6 +58,8 @@ int launch_composite_bwd(const NgmCompositeBwdArgs& b, cudaStream_t stream);
 int launch_encode_fwd(const NgmEncodeArgs& a, cudaStream_t stream);
 int launch_encode_bwd(const NgmEncodeArgs& a, cudaStream_t stream);
 int launch_adam_step(const NgmAdamArgs& a, cudaStream_t stream);
+int launch_target_visibility(const NgmTargetVisArgs& a, cudaStream_t stream);
+int launch_target_rays(const NgmTargetRaysArgs& a, cudaStream_t stream);
 int tc_trace_read(unsigned long long* out, int max_events);
 int tc_trace_peek(unsigned long long* out, int max_events);
 int tmem_bw_bench(int warps, int iters, int mode, unsigned long long* host_cycles);
@@ -162,6 +164,8 @@ size_t ngm_struct_size(int which) {
     case 8: return sizeof(NgmEncodeArgs);
     case 9: return sizeof(NgmAdamParam);
     case 10: return sizeof(NgmAdamArgs);
+    case 11: return sizeof(NgmTargetVisArgs);
+    case 12: return sizeof(NgmTargetRaysArgs);
     default: return 0;
   }
 }
@@ -251,6 +255,29 @@ int ngm_adam_step(const NgmAdamArgs* a, void* stream) {
                   "parameter %d: missing table / moment / gradient pointer", i);
   }
   return launch_adam_step(*a, (cudaStream_t)stream);
+}
+
+int ngm_target_visibility(const NgmTargetVisArgs* a, void* stream) {
+  NGM_CHECK_ARG(a != nullptr, "null args");
+  NGM_CHECK_ARG(a->num_fields >= 0 && a->num_frames >= 0 && a->num_probes > 0, "bad field / frame / probe counts");
+  NGM_CHECK_ARG(a->cam.fx != 0.f && a->cam.fy != 0.f && a->cam.width > 0 && a->cam.height > 0, "bad camera");
+  if (a->num_fields == 0 || a->num_frames == 0) return NGM_OK;
+  NGM_CHECK_ARG(a->c2ws && a->rgbds && a->positions && a->probe_offsets, "missing keyframe store / positions / probes");
+  NGM_CHECK_ARG(a->field_kf_mask && a->min_xys && a->max_xys, "missing output");
+  return launch_target_visibility(*a, (cudaStream_t)stream);
+}
+
+int ngm_target_rays(const NgmTargetRaysArgs* a, void* stream) {
+  NGM_CHECK_ARG(a != nullptr, "null args");
+  NGM_CHECK_ARG(a->num_fields >= 0 && a->rays_per_field >= 0 && a->num_frames > 0, "bad field / ray / frame counts");
+  NGM_CHECK_ARG(a->cam.fx != 0.f && a->cam.fy != 0.f && a->cam.width > 0 && a->cam.height > 0, "bad camera");
+  if (a->num_fields == 0 || a->rays_per_field == 0) return NGM_OK;
+  NGM_CHECK_ARG(a->c2ws && a->rgbds && a->positions && a->frame_cids && a->uv && a->min_xys && a->max_xys,
+                "missing input");
+  NGM_CHECK_ARG(a->ijs && a->out_c2ws && a->near && a->far && a->gt && a->out_rgbds && a->rgb_mask && a->depth_mask &&
+                    a->term_probs && a->term_mask,
+                "missing output");
+  return launch_target_rays(*a, (cudaStream_t)stream);
 }
 
 static int validate_encoding(const NgmFieldDesc& fd) {

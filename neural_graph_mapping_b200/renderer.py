@@ -288,11 +288,12 @@ def render_image(driver, c2w: torch.Tensor, camera, progressbar: bool = False):
     return rgbds.reshape(h, w, 4), d_vars.reshape(h, w)
 
 
-def install(driver_cls, optimizer: bool = True) -> None:
+def install(driver_cls, optimizer: bool = True, targets: bool = True) -> None:
     """Patch the reference's ``NeuralGraphMap`` so its renderer runs on libngm_b200 while the
     SLAM driver, keyframe selection and loop-closure code stay untouched callers.  With ``optimizer`` the Adam
     update of the active fields (``_set_vmap_fields`` / ``_update_step``) runs as one in-place launch too;
-    ``_init_optimizer``, ``_add_fields`` and ``_optim_state`` stay the driver's own."""
+    ``_init_optimizer``, ``_add_fields`` and ``_optim_state`` stay the driver's own.  With ``targets`` the
+    multi-view target sampling right before the render (``_sample_target_mv``) runs as two launches."""
     driver_cls._render_ijs = render_rays
     driver_cls._quadrature = quadrature
     driver_cls.render_image = render_image
@@ -301,6 +302,10 @@ def install(driver_cls, optimizer: bool = True) -> None:
 
         driver_cls._set_vmap_fields = optim.set_vmap_fields
         driver_cls._update_step = optim.update_step
+    if targets:
+        from .targets import sample_target_mv
+
+        driver_cls._sample_target_mv = sample_target_mv
 
 
 class RenderState:
@@ -391,6 +396,13 @@ class RenderState:
         self._global_map_dict = d["map_dict"]
         self._model.all_fields_params = d["all_fields_params"]
         self._model.load_state_dict(d["state_dict"])
+
+    def _sample_target_mv(self, current_field_ids: torch.Tensor):
+        """Needs the driver's keyframe store on this object: ``_camera``, ``_c_c2w_tensor``, ``_nc_rgbd_tensor``,
+        ``_frame_cid_to_ncid``, ``_num_train_fields``, ``_num_rays_per_field`` (run_mapping.py:140-141, 1674-1713)."""
+        from .targets import sample_target_mv
+
+        return sample_target_mv(self, current_field_ids)
 
     def _set_vmap_fields(self, field_ids: torch.Tensor) -> None:
         from . import optim

@@ -72,6 +72,28 @@ def test_adam_argument_errors_without_gpu(lib_mod):
     assert lib_mod.lib.ngm_adam_step(ctypes.byref(a), None) == 0
 
 
+def test_target_argument_errors_without_gpu(lib_mod):
+    v = lib_mod.NgmTargetVisArgs()
+    v.num_fields, v.num_frames, v.num_probes = 2, 3, 0
+    assert lib_mod.lib.ngm_target_visibility(ctypes.byref(v), None) == -1
+    v.num_probes = 20
+    assert lib_mod.lib.ngm_target_visibility(ctypes.byref(v), None) == -1  # zero focal length
+    assert b"camera" in lib_mod.lib.ngm_last_error()
+    v.cam = lib_mod.NgmCamera(50.0, 50.0, 31.5, 23.5, 64, 48)
+    assert lib_mod.lib.ngm_target_visibility(ctypes.byref(v), None) == -1  # pointers missing
+    v.num_fields = 0
+    assert lib_mod.lib.ngm_target_visibility(ctypes.byref(v), None) == 0   # nothing to do
+    r = lib_mod.NgmTargetRaysArgs()
+    r.cam = v.cam
+    r.num_fields, r.rays_per_field, r.num_frames = 2, 8, 0
+    assert lib_mod.lib.ngm_target_rays(ctypes.byref(r), None) == -1
+    r.num_frames = 3
+    assert lib_mod.lib.ngm_target_rays(ctypes.byref(r), None) == -1
+    assert b"missing" in lib_mod.lib.ngm_last_error()
+    r.rays_per_field = 0
+    assert lib_mod.lib.ngm_target_rays(ctypes.byref(r), None) == 0
+
+
 def test_no_cpu_fallback(lib_mod):
     import torch
 

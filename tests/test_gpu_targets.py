@@ -1,0 +1,241 @@
+"""Multi-view target sampling on the GPU (ngm_target_visibility / ngm_target_rays, targets.sample_target_mv) against
+the golden output of the unmodified reference's _sample_target_mv (ngm/run_mapping.py:1261-1459) and the oracle."""
+import types
+
+import pytest
+import torch
+
+import golden_util as G
+from oracle import restatement as R
+from oracle import targets as T
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _driver(meta, a, camera):
+    d = types.SimpleNamespace()
+    d._device, d._camera = DEV, camera
+    d._field_radius = meta["field_radius"]
+    d._num_train_fields, d._num_rays_per_field = meta["num_train_fields"], meta["num_rays_per_field"]
+    d._global_map_dict = {"positions": a["positions"].to(DEV), "num": meta["num_fields"]}
+    d._c_c2w_tensor, d._nc_rgbd_tensor = a["c2ws"].to(DEV), a["rgbds"].to(DEV)
+    d._frame_cid_to_ncid = a["frame_to_store"].to(DEV)
+    return d
+
+
+def _compare_targets(t, ref, where):
+    for k in t._fields:
+        ours, want = getattr(t, k).cpu(), getattr(ref, k) if not isinstance(ref, dict) else ref["out:" + k]
+        assert ours.shape == want.shape, (where, k, ours.shape, want.shape)
+        if want.dtype.is_floating_point:
+            assert torch.allclose(ours, want.float(), atol=2e-5, rtol=2e-5), (where, k, (ours - want).abs().max().item())
+        else:
+            assert ours.dtype == want.dtype or k == "ijs", (where, k, ours.dtype)
+            assert torch.equal(ours.to(want.dtype), want), (where, k)
+
+
+def test_sample_target_mv_golden():
+    import neural_graph_mapping_b200 as ngm
+    from neural_graph_mapping_b200 import targets
+
+    meta, a = G.load("target_mv")
+    drv = _driver(meta, a, ngm.Camera(**meta["camera"]))
+    draws = {k[len("draw:"):]: v.to(DEV) for k, v in a.items() if k.startswith("draw:")}
+    t = targets.sample_target_mv(drv, a["current_field_ids"].to(DEV), draws)
+    assert t.ijs.dtype == torch.int64 and t.depth_mask.dtype == torch.bool and t.term_probs.dtype == torch.float32
+    _compare_targets(t, a, "golden")
+
+
+def test_target_visibility_vs_oracle():
+    """Every field of the fixture (including the two no keyframe sees) against the oracle's intermediates."""
+    import neural_graph_mapping_b200 as ngm
+    from neural_graph_mapping_b200 import targets
+
+    meta, a = G.load("target_mv")
+    cam = ngm.Camera(**meta["camera"])
+    off = a["draw:probe_offsets"] / a["draw:probe_offsets"].norm(dim=-1, keepdim=True)
+    ids = torch.arange(meta["num_fields"])
+    mask, lo, hi = targets.target_visibility(cam, a["c2ws"].to(DEV), a["rgbds"].to(DEV), a["frame_to_store"].to(DEV),
+                                             a["positions"].to(DEV), ids.to(DEV), off.to(DEV), meta["field_radius"])
+    m_ref, lo_ref, hi_ref, _ = T.visibility(G.camera_spec(meta["camera"]), a["c2ws"], a["rgbds"], a["frame_to_store"],
+                                            a["positions"], ids, off, meta["field_radius"])
+    assert torch.equal(mask.cpu(), m_ref)
+    assert not m_ref[8].any() and not m_ref[9].any() and m_ref.any()
+    # boxes of frames behind which a probe sits project to huge coordinates before the clamp: compare relatively
+    assert torch.allclose(lo.cpu(), lo_ref, atol=2e-3, rtol=1e-4) and torch.allclose(hi.cpu(), hi_ref, atol=2e-3, rtol=1e-4)
+
+
+@pytest.mark.parametrize("F,K,Rr", [(32, 40, 512), (1, 1, 7), (5, 300, 64)])
+def test_target_rays_random_scenes_vs_oracle(F, K, Rr):
+    """NRGBD camera (640x480), the reference's default batch (32 fields x 512 rays) and edge shapes: both kernels
+    against the oracle on identical draws.  Pixels whose float coordinate sits on an integer edge may differ, so
+    integer outputs must agree on all but a handful of rays and everything else is compared on the agreeing rays."""
+    import neural_graph_mapping_b200 as ngm
+    from neural_graph_mapping_b200 import targets
+
+    g = torch.Generator().manual_seed(F * 1000 + K)
+    camd = dict(width=640, height=480, fx=554.2562584220408, fy=554.2562584220408, cx=319.5, cy=239.5, pixel_center=0.0)
+    cam, cs = ngm.Camera(**camd), R.CameraSpec(**camd)
+    n_all = F + 3
+    pos = torch.randn(n_all, 3, generator=g) * torch.tensor([1.0, 0.7, 0.5]) + torch.tensor([0.0, 0.0, -3.0])
+    c2ws = torch.eye(4).repeat(K, 1, 1)
+    ang = (torch.rand(K, generator=g) - 0.5) * 0.6
+    c2ws[:, 0, 0], c2ws[:, 0, 2], c2ws[:, 2, 0], c2ws[:, 2, 2] = ang.cos(), ang.sin(), -ang.sin(), ang.cos()
+    c2ws[:, :3, 3] = (torch.rand(K, 3, generator=g) - 0.5)
+    stored = min(K + 2, 12)
+    rgbds = torch.rand(stored, 480, 640, 4, generator=g)
+    rgbds[..., 3] = rgbds[..., 3] * 3.0 + 2.5
+    rgbds[..., 3][torch.rand(stored, 480, 640, generator=g) < 0.1] = 0.0
+    f2s = torch.randint(0, stored, (K,), generator=g)
+    ids = torch.randperm(n_all, generator=g)[:F]
+    off = torch.randn(20, 3, generator=g)
+    off = off / off.norm(dim=-1, keepdim=True)
+    mask, lo, hi = targets.target_visibility(cam, c2ws.to(DEV), rgbds.to(DEV), f2s.to(DEV), pos.to(DEV), ids.to(DEV),
+                                             off.to(DEV), 1.0)
+    m_ref, lo_ref, hi_ref, _ = T.visibility(cs, c2ws, rgbds, f2s, pos, ids, off, 1.0)
+    assert (mask.cpu() != m_ref).float().mean().item() < 2e-3
+    fm = m_ref.any(-1)
+    if not fm.any():
+        pytest.skip("no field visible in this random scene")
+    ids_v, m_v, lo_v, hi_v = ids[fm], m_ref[fm], lo_ref[fm], hi_ref[fm]
+    cids = torch.multinomial(m_v.float(), Rr, replacement=True, generator=g)
+    uv = torch.rand(len(ids_v), Rr, 2, generator=g)
+    t = targets.target_rays(cam, c2ws.to(DEV), rgbds.to(DEV), f2s.to(DEV), pos.to(DEV), ids_v.to(DEV), cids.to(DEV),
+                            uv.to(DEV), lo_v.to(DEV), hi_v.to(DEV), 1.0)
+    ref = T.rays(cs, c2ws, rgbds, f2s, pos, ids_v, cids, uv, lo_v, hi_v, 1.0)
+    same = (t.ijs.cpu() == ref.ijs).all(-1)
+    assert (~same).float().mean().item() < 2e-3
+    assert torch.equal(t.c2ws.cpu(), ref.c2ws)
+    for k in ("near_distances", "far_distances", "gt_distances", "rgbds", "term_probs"):
+        o, w = getattr(t, k).cpu()[same], getattr(ref, k)[same]
+        assert torch.allclose(o, w, atol=2e-5, rtol=2e-5), (k, (o - w).abs().max().item())
+    for k in ("rgb_mask", "depth_mask", "term_mask"):
+        assert (getattr(t, k).cpu()[same] != getattr(ref, k)[same]).float().mean().item() < 1e-3, k
+
+
+def test_mapping_iteration_end_to_end():
+    """Target sampling -> render under autograd -> the reference's losses -> Adam, all through the drop-ins, twice
+    with the same seed: bit-identical targets, a finite loss, parameters of exactly the target fields move."""
+    import neural_graph_mapping_b200 as ngm
+    from neural_graph_mapping_b200 import optim, targets
+    from tests_support import product_field_kwargs
+
+    meta, a = G.load("target_mv")
+    tmeta, ta = G.load("train_steps")
+    cfg = dict(tmeta["config"])
+    cfg["model_kwargs"] = dict(cfg["model_kwargs"], field_type="neural_graph_mapping_b200.models.NeuralField",
+                               field_kwargs=product_field_kwargs(tmeta["field_kwargs"]))
+    cfg.update(device=DEV, num_samples_coarse=8, num_samples_depth_guided=16, learning_rate=1e-3, adam_eps=1e-15,
+               adam_weight_decay=1e-5)
+    st = ngm.RenderState(cfg)
+    st._reference_flow = True
+    n = meta["num_fields"]
+    g = torch.Generator().manual_seed(3)
+    proto = {k: v[:1] for k, v in G.params(ta, "init:param:").items()}
+    params = {k: (v.repeat(n, *([1] * (v.dim() - 1))) + 0.05 * torch.randn(n, *v.shape[1:], generator=g)) for k, v in proto.items()}
+    q = torch.randn(n, 4, generator=g)
+    st.set_fields(params, a["positions"][:n], q / q.norm(dim=-1, keepdim=True))
+    for k, v in _driver(meta, a, ngm.Camera(**meta["camera"])).__dict__.items():
+        if k not in ("_global_map_dict", "_device"):
+            setattr(st, k, v)
+    before = {k: v.clone() for k, v in st._model.all_fields_params.items()}
+    cur = a["current_field_ids"].to(DEV)
+    torch.manual_seed(11)
+    t1 = targets.sample_target_mv(st, cur)
+    torch.manual_seed(11)
+    t2 = targets.sample_target_mv(st, cur)
+    for k in t1._fields:
+        assert torch.equal(getattr(t1, k), getattr(t2, k)), k
+    assert t1.ijs.shape[1:] == (meta["num_rays_per_field"], 2) and 8 not in t1.field_ids.tolist()
+    pred = st._render_ijs(t1.ijs, t1.c2ws, st._camera, t1.field_ids, True, t1.near_distances, t1.far_distances,
+                          t1.gt_distances)
+    # (the reference's photometric / depth terms average over rays with term_probs > 0.8 and are NaN when no ray of
+    # an untrained field passes, ngm/run_mapping.py:1787; this smoke test uses mask-free terms instead)
+    loss = (pred.rgbds[..., :3] - t1.rgbds[..., :3]).abs().mean() + ((pred.term_probs - t1.term_probs) ** 2).mean()
+    if pred.tsdf_residuals is not None and pred.tsdf_residuals.numel():
+        loss = loss + (pred.tsdf_residuals ** 2).mean()
+    losses = {"combined": loss}
+    assert torch.isfinite(losses["combined"])
+    st._update_step(losses, t1.field_ids)
+    moved = (st._model.all_fields_params["_linears.0.weight"] != before["_linears.0.weight"]).flatten(1).any(1)
+    want = torch.zeros(n, dtype=torch.bool, device=DEV)
+    want[t1.field_ids] = True
+    assert torch.equal(moved, want)
+    assert st._global_map_dict["training_iterations"].tolist() == want.long().tolist()
+    assert all(int(s["step"].item()) == 1 for k, s in st._optim_state.items() if k != "_neus_sd")
+
+
+def test_target_errors():
+    import neural_graph_mapping_b200 as ngm
+    from neural_graph_mapping_b200 import targets
+
+    meta, a = G.load("target_mv")
+    cam = ngm.Camera(**meta["camera"])
+    off = torch.randn(20, 3)
+    ids = torch.arange(3)
+    with pytest.raises(RuntimeError, match="no CPU"):
+        targets.target_visibility(cam, a["c2ws"], a["rgbds"], a["frame_to_store"], a["positions"], ids, off, 1.0)
+    with pytest.raises(ValueError, match="keyframe buffer"):
+        targets.target_visibility(cam, a["c2ws"].to(DEV), a["rgbds"][:, :10].to(DEV), a["frame_to_store"].to(DEV),
+                                  a["positions"].to(DEV), ids.to(DEV), off.to(DEV), 1.0)
+    with pytest.raises(ValueError, match="number of frames"):
+        targets.target_visibility(cam, a["c2ws"].to(DEV), a["rgbds"].to(DEV), a["frame_to_store"][:2].to(DEV),
+                                  a["positions"].to(DEV), ids.to(DEV), off.to(DEV), 1.0)
+
+
+def test_target_sampling_timing_report(capsys):
+    """Not a pass/fail criterion: prints (pytest -s) the device time of one target-sampling call at the reference's
+    default shape (32 train fields x 512 rays, 640x480 keyframes) for the two-launch path and for the reference's
+    torch sequence (oracle/targets.py run on the GPU: the same ops the reference issues)."""
+    import neural_graph_mapping_b200 as ngm
+    from neural_graph_mapping_b200 import targets
+
+    g = torch.Generator().manual_seed(1)
+    camd = dict(width=640, height=480, fx=554.2562584220408, fy=554.2562584220408, cx=319.5, cy=239.5, pixel_center=0.0)
+    K, n = 100, 64
+    meta = {"field_radius": 1.0, "num_train_fields": 32, "num_rays_per_field": 512, "num_fields": n}
+    c2ws = torch.eye(4).repeat(K, 1, 1)
+    c2ws[:, :3, 3] = torch.rand(K, 3, generator=g) - 0.5
+    rgbds = torch.rand(K, 480, 640, 4, generator=g)
+    rgbds[..., 3] = rgbds[..., 3] * 3.0 + 2.5
+    a = {"positions": torch.randn(n, 3, generator=g) * torch.tensor([1.0, 0.7, 0.5]) + torch.tensor([0.0, 0.0, -3.0]),
+         "c2ws": c2ws, "rgbds": rgbds, "frame_to_store": torch.arange(K)}
+    drv = _driver(meta, a, ngm.Camera(**camd))
+    cs = R.CameraSpec(**camd)
+    cur = torch.arange(20, device=DEV)
+
+    def ours():
+        return targets.sample_target_mv(drv, cur)
+
+    def torch_sequence():
+        so = torch.multinomial(torch.ones(len(cur), device=DEV), 16)
+        dist = torch.ones(n, device=DEV)
+        dist[cur[so]] = 0.0
+        sr = torch.multinomial(dist, 16)
+        ids = T.choose_fields(cur, 32, n, so, sr)
+        off = torch.randn(20, 3, device=DEV)
+        off = off / off.norm(dim=-1, keepdim=True)
+        m, lo, hi, _ = T.visibility(cs, drv._c_c2w_tensor, drv._nc_rgbd_tensor, drv._frame_cid_to_ncid,
+                                    drv._global_map_dict["positions"], ids, off, 1.0)
+        fm = m.any(-1)
+        cids = torch.multinomial(m[fm].float(), 512, replacement=True)
+        uv = torch.rand(int(fm.sum()), 512, 2, device=DEV)
+        return T.rays(cs, drv._c_c2w_tensor, drv._nc_rgbd_tensor, drv._frame_cid_to_ncid,
+                      drv._global_map_dict["positions"], ids[fm], cids, uv, lo[fm], hi[fm], 1.0)
+
+    out = {}
+    for name, fn in (("two_launch_path", ours), ("torch_sequence", torch_sequence)):
+        ts = []
+        for i in range(13):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            t = fn()
+            e1.record()
+            torch.cuda.synchronize()
+            if i >= 3:
+                ts.append(e0.elapsed_time(e1))
+        out[name] = sum(ts) / len(ts)
+        assert t.ijs.shape[1:] == (512, 2)
+    with capsys.disabled():
+        print("\nTARGET_SAMPLING_MS", {k: round(v, 4) for k, v in out.items()})
