@@ -92,3 +92,32 @@ def replay_training(meta, a, iteration_fn, grow_fn):
         else:
             it = st["iteration"]
             iteration_fn(it, {k[len(f"it{it}:"):]: v for k, v in a.items() if k.startswith(f"it{it}:")})
+
+
+def rigid_from_quaternion(q, t):
+    """(..., 4, 4) camera/world transform from a real-first unit quaternion and a translation."""
+    w, x, y, z = q.unbind(-1)
+    rot = torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w),
+                       2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w),
+                       2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)], -1).view(*q.shape[:-1], 3, 3)
+    T = torch.eye(4).repeat(*q.shape[:-1], 1, 1)
+    T[..., :3, :3] = rot
+    T[..., :3, 3] = t
+    return T
+
+
+def quaternion_multiply(a, b):
+    """Real-first Hamilton product (pytorch3d.transforms.quaternion_multiply's convention up to sign)."""
+    aw, ax, ay, az = a.unbind(-1)
+    bw, bx, by, bz = b.unbind(-1)
+    return torch.stack([aw * bw - ax * bx - ay * by - az * bz, aw * bx + ax * bw + ay * bz - az * by,
+                        aw * by - ax * bz + ay * bw + az * bx, aw * bz + ax * by - ay * bx + az * bw], -1)
+
+
+def loop_closure_update(positions, orientations, kf_ids, delta_q, delta_t):
+    """What NeuralGraphMap._update_field_poses does to the fields when keyframe k's pose changes from P_k to
+    D_k P_k (ngm/run_mapping.py:846-884, 937-952: absolute -> relative to the anchoring keyframe with the old poses,
+    relative -> absolute with the new ones, i.e. X' = D_k X): positions D_k p, orientations q(D_k) (x) q."""
+    D = rigid_from_quaternion(delta_q, delta_t)[kf_ids]
+    new_pos = torch.einsum("fdk,fk->fd", D[:, :3, :3], positions) + D[:, :3, 3]
+    return new_pos, quaternion_multiply(delta_q[kf_ids], orientations), D

@@ -157,3 +157,42 @@ def test_c2_philox_jitter_reproducible():
     _check_invariants(a, scene["far"])
     # different jitter, same scene: the two frames agree to Monte-Carlo accuracy of 64 strata
     assert (a.rgbds - c.rgbds).abs().mean().item() < 0.05
+
+
+@pytest.mark.parametrize("precision", ["fp16", "fp32"])
+def test_c5_loop_closure_rerender_invariance(precision):
+    """BASELINE config 5 (pose-graph update + re-render) on the full C2 frame: keyframes 1 and 2 of three move by
+    seeded rigid transforms, _update_field_poses (ngm/run_mapping.py:937-952) moves the fields anchored to them, and
+    the keyframes re-rendered from their new poses show the same pixels (world coordinates change, field-local ones
+    do not -- up to rounding, which the 2^7 pi octave of NeRF-8 amplifies)."""
+    import golden_util as G
+
+    F, Rr = bench.F_FIELDS, bench.R_RAYS
+    scene = bench.synthetic_scene(1234)
+    g = torch.Generator().manual_seed(55)
+    jitter = torch.rand(F, Rr, S, generator=g)
+    st, cam = _state(scene, precision)
+    before = _render(st, cam, scene, jitter)
+    kf_ids = torch.arange(F) % 3
+    dq = torch.randn(3, 4, generator=g)
+    dq = dq / dq.norm(dim=-1, keepdim=True)
+    dq[0] = torch.tensor([1.0, 0.0, 0.0, 0.0])
+    dt = torch.randn(3, 3, generator=g) * 0.5
+    dt[0] = 0.0
+    pos2, ori2, D = G.loop_closure_update(scene["positions"], scene["orientations"], kf_ids, dq, dt)
+    moved = dict(scene, positions=pos2, orientations=ori2)
+    st2, _ = _state(moved, precision)
+    c2ws = (D @ scene["c2w"])[:, None].expand(F, Rr, 4, 4)
+    after = _render(st2, cam, moved, jitter, c2ws=c2ws)
+    untouched = kf_ids == 0
+    d_rgb = (after.rgbds - before.rgbds).abs()
+    assert d_rgb[untouched.to(d_rgb.device)].max().item() < 1e-5  # identity transform: same arithmetic
+    if precision == "fp32":
+        assert d_rgb.mean().item() < 5e-5 and d_rgb.max().item() < 2e-2, (d_rgb.mean().item(), d_rgb.max().item())
+    else:
+        assert d_rgb.mean().item() < 5e-4, d_rgb.mean().item()
+    assert (after.term_probs - before.term_probs).abs().mean().item() < (5e-5 if precision == "fp32" else 5e-4)
+    # negative control: cameras moved but fields left behind -- the frame must change by far more than that
+    stale = _render(st, cam, scene, jitter, c2ws=c2ws)
+    d_stale = (stale.rgbds - before.rgbds).abs()[(~untouched).to(d_rgb.device)]
+    assert d_stale.mean().item() > 10 * max(d_rgb.mean().item(), 1e-5), (d_stale.mean().item(), d_rgb.mean().item())

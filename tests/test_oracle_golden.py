@@ -105,3 +105,29 @@ def test_live_reference_if_present():
     pts2, dist2 = R.sample_ijs_uniform(ijs, G.camera_spec(meta["camera"]), 6, 0.3, 2.0, jit)
     _close(pts2, pts)
     _close(dist2, dist)
+
+
+def test_loop_closure_rerender_invariance():
+    """BASELINE config 5's property on the oracle: after a pose-graph update moves keyframe k by a rigid D_k and
+    _update_field_poses moves the fields anchored to k with it, re-rendering keyframe k gives the same pixels."""
+    meta, a = G.load("c2_vmap_w128_s64")
+    fs, rs, cam = G.field_spec(meta["field_kwargs"]), G.render_spec(meta), G.camera_spec(meta["camera"])
+    g = torch.Generator().manual_seed(9)
+    F = a["ijs"].shape[0]
+    fid = a["field_ids"]
+    n_all = a["positions"].shape[0]
+    kf_ids = torch.arange(n_all) % 3
+    dq = torch.randn(3, 4, generator=g)
+    dq = dq / dq.norm(dim=-1, keepdim=True)
+    dq[0] = torch.tensor([1.0, 0.0, 0.0, 0.0])  # the first third of the keyframes is not touched
+    dt = torch.randn(3, 3, generator=g)
+    dt[0] = 0.0
+    pos2, ori2, D = G.loop_closure_update(a["positions"], a["orientations"], kf_ids, dq, dt)
+    c2ws2 = D[fid][:, None] @ a["c2ws"]  # every ray of field f comes from the keyframe f is anchored to
+    kw = dict(field_ids=fid, use_vmap=True, near_distances=a["near"], far_distances=a["far"], jitter=a["jitter"])
+    with torch.no_grad():
+        p1 = R.render_rays(a["ijs"], a["c2ws"], cam, rs, fs, G.params(a), a["positions"], a["orientations"], **kw)
+        p2 = R.render_rays(a["ijs"], c2ws2, cam, rs, fs, G.params(a), pos2, ori2, **kw)
+    assert F >= 2 and not torch.equal(pos2[fid], a["positions"][fid])
+    assert torch.allclose(p1.rgbds, p2.rgbds, atol=2e-3) and (p1.rgbds - p2.rgbds).abs().mean().item() < 1e-4
+    assert torch.allclose(p1.term_probs, p2.term_probs, atol=2e-3)
