@@ -293,6 +293,23 @@ typedef struct NgmTargetRaysArgs {
   uint8_t* term_mask;             /* bool */
 } NgmTargetRaysArgs;
 
+/* Which fields does the current frame observe: NeuralGraphMap._get_observed_fields (ngm/run_mapping.py:1643-1670)
+ * after its torch.nonzero / torch.multinomial choice of valid depth pixels. */
+typedef struct NgmObservedArgs {
+  NgmCamera cam;
+  const float* depth;         /* depth of pixel p (row-major index) at depth[p * pixel_stride]; 4 for channel 3
+                                 of an (H, W, 4) RGB-D image */
+  const int64_t* pixel_ids;   /* (num_points) row-major indices of the drawn pixels with depth != 0 */
+  const float* c2w;           /* (4, 4) pose of the current frame */
+  const float* positions;     /* (num_fields, 3): the first num_fields rows of the positions table */
+  int64_t pixel_stride;
+  int32_t num_points;         /* <= 2048 (the reference draws 500) */
+  int32_t num_fields;
+  float field_radius;
+  int32_t _pad;
+  uint8_t* observed;          /* out (num_fields): 1 = observed */
+} NgmObservedArgs;
+
 /* ---- fused render --------------------------------------------------------------------
  * Replaces NeuralGraphMap._render_ijs with use_vmap=True (ngm/run_mapping.py:440-666):
  * sampler -> world->local -> encoding -> per-field MLP -> compositor for
@@ -359,7 +376,7 @@ const char* ngm_last_error(void);
 /* sizeof() of the structs above as compiled, so a binding can verify its mirror:
  * which = 0 NgmCamera, 1 NgmFieldDesc, 2 NgmSampleArgs, 3 NgmFieldFwdArgs, 4 NgmCompositeArgs, 5 NgmRenderArgs,
  * 6 NgmKnnFwdArgs, 7 NgmCompositeBwdArgs, 8 NgmEncodeArgs, 9 NgmAdamParam, 10 NgmAdamArgs,
- * 11 NgmTargetVisArgs, 12 NgmTargetRaysArgs */
+ * 11 NgmTargetVisArgs, 12 NgmTargetRaysArgs, 13 NgmObservedArgs */
 size_t ngm_struct_size(int which);
 /* number of CUDA kernels this library has launched in this process (bench.py's gpu_launches) */
 uint64_t ngm_launch_count(void);
@@ -373,6 +390,7 @@ int ngm_encode_bwd(const NgmEncodeArgs* args, void* stream);    /* d lattice_val
 int ngm_adam_step(const NgmAdamArgs* args, void* stream);       /* run_mapping.py:679-707, 1191-1221 */
 int ngm_target_visibility(const NgmTargetVisArgs* args, void* stream); /* run_mapping.py:1319-1362, 1386-1389 */
 int ngm_target_rays(const NgmTargetRaysArgs* args, void* stream);      /* run_mapping.py:1398-1445 */
+int ngm_observed_fields(const NgmObservedArgs* args, void* stream);    /* run_mapping.py:1643-1670 */
 int ngm_render_rays_fwd(const NgmRenderArgs* args, void* stream); /* run_mapping.py:440-666 (use_vmap=True) */
 int ngm_fieldset_knn_fwd(const NgmKnnFwdArgs* args, void* stream); /* models.py:347-405 (use_vmap=False) */
 int ngm_fieldset_knn_workspace_bytes(const NgmKnnFwdArgs* args, size_t* out);

@@ -119,6 +119,12 @@ class NgmTargetVisArgs(C.Structure):
                 ("field_kf_mask", _fp), ("min_xys", _fp), ("max_xys", _fp)]
 
 
+class NgmObservedArgs(C.Structure):
+    _fields_ = [("cam", NgmCamera), ("depth", _fp), ("pixel_ids", _fp), ("c2w", _fp), ("positions", _fp),
+                ("pixel_stride", C.c_int64), ("num_points", C.c_int32), ("num_fields", C.c_int32),
+                ("field_radius", C.c_float), ("_pad", C.c_int32), ("observed", _fp)]
+
+
 class NgmTargetRaysArgs(C.Structure):
     _fields_ = [("cam", NgmCamera), ("c2ws", _fp), ("rgbds", _fp), ("frame_to_store", _fp), ("positions", _fp),
                 ("field_ids", _fp), ("frame_cids", _fp), ("uv", _fp), ("min_xys", _fp), ("max_xys", _fp),
@@ -155,9 +161,9 @@ class NgmKnnFwdArgs(C.Structure):
 
 STRUCTS = [NgmCamera, NgmFieldDesc, NgmSampleArgs, NgmFieldFwdArgs, NgmCompositeArgs, NgmRenderArgs, NgmKnnFwdArgs,
            NgmCompositeBwdArgs, NgmEncodeArgs, NgmAdamParam, NgmAdamArgs,
-           NgmTargetVisArgs, NgmTargetRaysArgs]
+           NgmTargetVisArgs, NgmTargetRaysArgs, NgmObservedArgs]
 EXPORTS = [
-    "ngm_abi_version", "ngm_last_error", "ngm_struct_size", "ngm_launch_count", "ngm_sample_rays", "ngm_field_fwd", "ngm_composite", "ngm_composite_bwd", "ngm_encode_fwd", "ngm_encode_bwd", "ngm_adam_step", "ngm_target_visibility", "ngm_target_rays",
+    "ngm_abi_version", "ngm_last_error", "ngm_struct_size", "ngm_launch_count", "ngm_sample_rays", "ngm_field_fwd", "ngm_composite", "ngm_composite_bwd", "ngm_encode_fwd", "ngm_encode_bwd", "ngm_adam_step", "ngm_target_visibility", "ngm_target_rays", "ngm_observed_fields",
     "ngm_render_rays_fwd", "ngm_debug_tc_gemm", "ngm_debug_tc_trace", "ngm_debug_tc_trace_peek", "ngm_debug_tmem_bw", "ngm_fieldset_knn_fwd", "ngm_fieldset_knn_workspace_bytes", "ngm_field_fwd_workspace_bytes", "ngm_render_workspace_bytes",
 ]
 
@@ -177,7 +183,8 @@ for _name, _arg in [("ngm_sample_rays", NgmSampleArgs), ("ngm_field_fwd", NgmFie
                     ("ngm_composite", NgmCompositeArgs), ("ngm_render_rays_fwd", NgmRenderArgs),
                     ("ngm_fieldset_knn_fwd", NgmKnnFwdArgs), ("ngm_composite_bwd", NgmCompositeBwdArgs),
                     ("ngm_encode_fwd", NgmEncodeArgs), ("ngm_encode_bwd", NgmEncodeArgs), ("ngm_adam_step", NgmAdamArgs),
-                    ("ngm_target_visibility", NgmTargetVisArgs), ("ngm_target_rays", NgmTargetRaysArgs)]:
+                    ("ngm_target_visibility", NgmTargetVisArgs), ("ngm_target_rays", NgmTargetRaysArgs),
+                    ("ngm_observed_fields", NgmObservedArgs)]:
     getattr(lib, _name).restype = C.c_int
     getattr(lib, _name).argtypes = [C.POINTER(_arg), C.c_void_p]
 lib.ngm_fieldset_knn_workspace_bytes.restype = C.c_int

@@ -60,6 +60,7 @@ int launch_encode_bwd(const NgmEncodeArgs& a, cudaStream_t stream);
 int launch_adam_step(const NgmAdamArgs& a, cudaStream_t stream);
 int launch_target_visibility(const NgmTargetVisArgs& a, cudaStream_t stream);
 int launch_target_rays(const NgmTargetRaysArgs& a, cudaStream_t stream);
+int launch_observed_fields(const NgmObservedArgs& a, cudaStream_t stream);
 int tc_trace_read(unsigned long long* out, int max_events);
 int tc_trace_peek(unsigned long long* out, int max_events);
 int tmem_bw_bench(int warps, int iters, int mode, unsigned long long* host_cycles);
@@ -166,6 +167,7 @@ size_t ngm_struct_size(int which) {
     case 10: return sizeof(NgmAdamArgs);
     case 11: return sizeof(NgmTargetVisArgs);
     case 12: return sizeof(NgmTargetRaysArgs);
+    case 13: return sizeof(NgmObservedArgs);
     default: return 0;
   }
 }
@@ -278,6 +280,16 @@ int ngm_target_rays(const NgmTargetRaysArgs* a, void* stream) {
                     a->term_probs && a->term_mask,
                 "missing output");
   return launch_target_rays(*a, (cudaStream_t)stream);
+}
+
+int ngm_observed_fields(const NgmObservedArgs* a, void* stream) {
+  NGM_CHECK_ARG(a != nullptr, "null args");
+  NGM_CHECK_ARG(a->num_fields >= 0 && a->num_points >= 0 && a->pixel_stride > 0, "bad field / point counts or stride");
+  NGM_CHECK_ARG(a->cam.fx != 0.f && a->cam.fy != 0.f && a->cam.width > 0 && a->cam.height > 0, "bad camera");
+  if (a->num_fields == 0) return NGM_OK;
+  NGM_CHECK_ARG(a->c2w && a->positions && a->observed, "missing pose / positions / output");
+  NGM_CHECK_ARG(a->num_points == 0 || (a->depth && a->pixel_ids), "missing depth image / pixel ids");
+  return launch_observed_fields(*a, (cudaStream_t)stream);
 }
 
 static int validate_encoding(const NgmFieldDesc& fd) {

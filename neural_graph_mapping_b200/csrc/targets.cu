@@ -128,7 +128,82 @@ __global__ void __launch_bounds__(128) target_rays_kernel(NgmTargetRaysArgs a) {
   a.term_mask[idx] = gt > near && valid_depth;                  // :1445
 }
 
+// NeuralGraphMap._get_observed_fields (ngm/run_mapping.py:1643-1670): which fields does the current depth image
+// observe?  A few hundred valid pixels are back-projected (Camera.depth_to_pointcloud, OpenGL; camera.py:372-385);
+// fields whose sphere's AABB misses the points' AABB are dropped (geometry.py:25-42); a remaining field is observed
+// if the segment camera -> point passes within field_radius of its centre for any point (geometry.py:67-103).
+// Every CTA back-projects the points into shared memory and reduces their AABB; each of its warps then owns one
+// field, lanes striding over the points.
+constexpr int kObservedWarps = 8;
+constexpr int kObservedMaxPoints = 2048;
+
+__global__ void __launch_bounds__(kObservedWarps * 32) observed_fields_kernel(NgmObservedArgs a) {
+  __shared__ float pts[kObservedMaxPoints][3];
+  __shared__ float red[kObservedWarps][6];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+  for (int p = threadIdx.x; p < a.num_points; p += blockDim.x) {
+    const long long pix = a.pixel_ids[p];
+    const float i = (float)(pix / a.cam.width), j = (float)(pix % a.cam.width);
+    const float d = __ldg(a.depth + pix * a.pixel_stride);
+    const float x = __fdiv_rn((j - a.cam.cx0) * d, a.cam.fx);        // camera.py:380
+    const float y = __fdiv_rn(-(i - a.cam.cy0) * d, a.cam.fy);       // :381
+    const float z = -d;                                              // :382
+    pts[p][0] = x; pts[p][1] = y; pts[p][2] = z;
+    mn[0] = fminf(mn[0], x); mn[1] = fminf(mn[1], y); mn[2] = fminf(mn[2], z);
+    mx[0] = fmaxf(mx[0], x); mx[1] = fmaxf(mx[1], y); mx[2] = fmaxf(mx[2], z);
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mn[c] = fminf(mn[c], __shfl_xor_sync(0xffffffffu, mn[c], o));
+      mx[c] = fmaxf(mx[c], __shfl_xor_sync(0xffffffffu, mx[c], o));
+    }
+    if (lane == 0) { red[warp][c] = mn[c]; red[warp][3 + c] = mx[c]; }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    mn[c] = red[0][c]; mx[c] = red[0][3 + c];
+    for (int w = 1; w < kObservedWarps; ++w) { mn[c] = fminf(mn[c], red[w][c]); mx[c] = fmaxf(mx[c], red[w][3 + c]); }
+  }
+  const int f = blockIdx.x * kObservedWarps + warp;
+  if (f >= a.num_fields) return;
+  const Pose pose = load_pose(a.c2w);
+  float c[3];
+  world_to_cam(pose, __ldg(a.positions + f * 3), __ldg(a.positions + f * 3 + 1), __ldg(a.positions + f * 3 + 2), c[0], c[1], c[2]);
+  const float r = a.field_radius;
+  bool in_box = true;  // sphere AABB [c - r, c + r] against the points' AABB (geometry.py:38-42)
+#pragma unroll
+  for (int k = 0; k < 3; ++k) in_box = in_box && (c[k] - r <= mx[k]) && (c[k] + r >= mn[k]);
+  bool hit = false;
+  if (in_box) {
+    const float r2 = r * r;
+    for (int p = lane; p < a.num_points; p += 32) {
+      const float x = pts[p][0], y = pts[p][1], z = pts[p][2];
+      float sq = x * x + y * y + z * z;
+      if (sq == 0.0f) sq = 1.0f;                                            // geometry.py:100
+      const float t = fminf(fmaxf(__fdiv_rn(c[0] * x + c[1] * y + c[2] * z, sq), 0.0f), 1.0f);  // :101-102
+      const float dx = c[0] - x * t, dy = c[1] - y * t, dz = c[2] - z * t;
+      hit = hit || (dx * dx + dy * dy + dz * dz <= r2);                     // :79-83
+    }
+  }
+  hit = __any_sync(0xffffffffu, hit);
+  if (lane == 0) a.observed[f] = hit ? 1 : 0;
+}
+
 }  // namespace
+
+int launch_observed_fields(const NgmObservedArgs& a, cudaStream_t stream) {
+  if (a.num_fields == 0) return NGM_OK;
+  if (a.num_points > kObservedMaxPoints) {
+    set_error("num_points %d exceeds %d", a.num_points, kObservedMaxPoints);
+    return NGM_ERR_UNSUPPORTED;
+  }
+  observed_fields_kernel<<<(a.num_fields + kObservedWarps - 1) / kObservedWarps, kObservedWarps * 32, 0, stream>>>(a);
+  return check_launch("observed_fields_kernel");
+}
 
 int launch_target_visibility(const NgmTargetVisArgs& a, cudaStream_t stream) {
   const long long n = (long long)a.num_fields * a.num_frames;

@@ -293,7 +293,8 @@ def install(driver_cls, optimizer: bool = True, targets: bool = True) -> None:
     SLAM driver, keyframe selection and loop-closure code stay untouched callers.  With ``optimizer`` the Adam
     update of the active fields (``_set_vmap_fields`` / ``_update_step``) runs as one in-place launch too;
     ``_init_optimizer``, ``_add_fields`` and ``_optim_state`` stay the driver's own.  With ``targets`` the
-    multi-view target sampling right before the render (``_sample_target_mv``) runs as two launches."""
+    multi-view target sampling right before the render (``_sample_target_mv``) runs as two launches and
+    ``_get_observed_fields`` as one."""
     driver_cls._render_ijs = render_rays
     driver_cls._quadrature = quadrature
     driver_cls.render_image = render_image
@@ -303,9 +304,10 @@ def install(driver_cls, optimizer: bool = True, targets: bool = True) -> None:
         driver_cls._set_vmap_fields = optim.set_vmap_fields
         driver_cls._update_step = optim.update_step
     if targets:
-        from .targets import sample_target_mv
+        from .targets import get_observed_fields, sample_target_mv
 
         driver_cls._sample_target_mv = sample_target_mv
+        driver_cls._get_observed_fields = get_observed_fields
 
 
 class RenderState:

@@ -136,3 +136,54 @@ def sample_target_mv(driver, current_field_ids: torch.Tensor, draws: Optional[di
         if uv is None:
             uv = torch.rand(len(field_ids), R, 2, device=dev)
         return target_rays(driver._camera, *store, field_ids, frame_cids, uv, lo, hi, train_radius)
+
+
+NUM_OBSERVED_POINTS = 500  # :1651
+
+
+def observed_fields(camera, depth_image: torch.Tensor, pixel_ids: torch.Tensor, c2w: torch.Tensor,
+                    positions: torch.Tensor, field_radius: float) -> torch.Tensor:
+    """``ngm_observed_fields``: bool (num_fields,) -- field observed by the back-projected pixels ``pixel_ids``
+    (row-major indices into ``depth_image``, which may be a strided channel view of an (H, W, 4) RGB-D image)."""
+    if not depth_image.is_cuda:
+        raise RuntimeError("depth image must be a CUDA tensor: neural_graph_mapping_b200 has no CPU path")
+    dev = depth_image.device
+    if depth_image.dtype != torch.float32 or depth_image.shape != (camera.height, camera.width):
+        raise ValueError(f"depth image must be fp32 ({camera.height}, {camera.width}), got {depth_image.dtype} {tuple(depth_image.shape)}")
+    sh, sw = depth_image.stride()
+    if sh != sw * camera.width:  # not a plain channel view: make it one
+        depth_image = depth_image.contiguous()
+        sh, sw = depth_image.stride()
+    pix = pixel_ids.to(device=dev, dtype=torch.int64).contiguous()
+    c2w = _lib.dev_f32(c2w, "c2w")
+    positions = _lib.dev_f32(positions, "positions")
+    out = torch.empty(positions.shape[0], dtype=torch.bool, device=dev)
+    a = _lib.NgmObservedArgs()
+    a.cam = camera_struct(camera)
+    a.depth, a.pixel_ids, a.c2w, a.positions = depth_image.data_ptr(), pix.data_ptr(), c2w.data_ptr(), positions.data_ptr()
+    a.pixel_stride, a.num_points, a.num_fields, a.field_radius = sw, pix.numel(), positions.shape[0], float(field_radius)
+    a.observed = out.data_ptr()
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib.ngm_observed_fields(C.byref(a), _lib.stream_ptr(dev)))
+    return out
+
+
+def get_observed_fields(driver, rgbd_image: torch.Tensor, c2w: torch.Tensor, draws: Optional[dict] = None) -> torch.Tensor:
+    """Drop-in for ``NeuralGraphMap._get_observed_fields`` (ngm/run_mapping.py:1643-1670).  The choice of pixels is
+    the reference's (``torch.nonzero`` of the depth channel, ``torch.multinomial`` of 500 of them -- same functions,
+    same generator); ``draws["subset"]`` injects it for parity runs."""
+    dev = driver._device
+    num_fields = getattr(driver, "_num_fields", None)
+    if num_fields is None:
+        num_fields = driver._global_map_dict["num"]
+    with torch.no_grad():
+        depth = rgbd_image[..., 3]
+        ijs = torch.nonzero(depth)  # camera.py:373
+        subset = (draws or {}).get("subset")
+        if subset is None:
+            subset = torch.multinomial(torch.ones(len(ijs), device=dev), NUM_OBSERVED_POINTS)
+        ijs = ijs[subset.to(dev)]
+        pix = ijs[:, 0] * driver._camera.width + ijs[:, 1]
+        observed = observed_fields(driver._camera, depth, pix, c2w, driver._global_map_dict["positions"][:num_fields],
+                                   driver._field_radius)
+        return torch.nonzero(observed)[:, 0]

@@ -94,6 +94,15 @@ def main():
                   current_field_ids=MG._np(current))
     arrays.update({"draw:" + k: MG._np(v) for k, v in draws.items()})
     arrays.update({"out:" + k: MG._np(getattr(t, k)) for k in t._fields})
+    # ---- _get_observed_fields (:1643-1670) on one stored frame, from the pose of keyframe 2
+    rgbd_image = rgbd[3]
+    with recorded_draws() as rec2:
+        obs = m._get_observed_fields(rgbd_image, c2ws[2])
+    assert [c[0] for c in rec2.calls] == ["multinomial"]
+    print("observed fields:", obs.tolist())
+    assert 0 < len(obs) < n
+    arrays.update({"observed:rgbd": MG._np(rgbd_image), "observed:c2w": MG._np(c2ws[2]),
+                   "observed:draw_subset": MG._np(rec2.calls[0][1]), "observed:out": MG._np(obs)})
     MG._save("target_mv", {"case": "target_mv", "camera": CAM, "num_fields": n, "num_train_fields": 8,
                            "num_rays_per_field": 32, "field_radius": cfg["field_radius"]}, arrays)
 

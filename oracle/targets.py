@@ -107,3 +107,23 @@ def sample_target_mv(cam: R.CameraSpec, c2ws, rgbds, frame_to_store, positions, 
     fm = mask.any(dim=-1)
     return rays(cam, c2ws, rgbds, frame_to_store, positions, ids[fm], draws["frame_cids"], draws["uv"], lo[fm], hi[fm],
                 train_radius)
+
+
+def observed_fields(cam: R.CameraSpec, depth, c2w, positions, field_radius, subset):
+    """``NeuralGraphMap._get_observed_fields`` (ngm/run_mapping.py:1643-1670) with its multinomial draw supplied:
+    ids of the fields (rows of ``positions``) the frame observes."""
+    pos_c = transform_points_inv(positions, c2w)
+    ids = torch.arange(positions.shape[0], device=positions.device)
+    cx0, cy0 = cam.cx - cam.pixel_center, cam.cy - cam.pixel_center
+    ijs = torch.nonzero(depth)  # Camera.depth_to_pointcloud, camera.py:372-385 (OpenGL)
+    d = depth[ijs[:, 0], ijs[:, 1]]
+    pts = torch.stack(((ijs[:, 1].to(d.dtype) - cx0) * d / cam.fx, -(ijs[:, 0].to(d.dtype) - cy0) * d / cam.fy, -d), -1)
+    pts = pts[subset]
+    lo, hi = pts.min(dim=0)[0], pts.max(dim=0)[0]
+    in_box = ((pos_c - field_radius <= hi).all(-1)) * ((pos_c + field_radius >= lo).all(-1))  # geometry.py:25-42
+    c, ids = pos_c[in_box], ids[in_box]
+    sq = (pts * pts).sum(-1, keepdim=True)  # segments from the origin: geometry.py:86-103
+    sq[sq == 0] = 1.0
+    t = ((c[:, None] * pts).sum(-1, keepdim=True) / sq).clamp(0.0, 1.0)
+    d2 = ((c[:, None] - pts * t) ** 2).sum(-1)
+    return ids[(d2 <= field_radius ** 2).any(-1)]

@@ -92,6 +92,14 @@ def test_target_argument_errors_without_gpu(lib_mod):
     assert b"missing" in lib_mod.lib.ngm_last_error()
     r.rays_per_field = 0
     assert lib_mod.lib.ngm_target_rays(ctypes.byref(r), None) == 0
+    o = lib_mod.NgmObservedArgs()
+    o.cam, o.num_fields, o.num_points, o.pixel_stride = v.cam, 3, 500, 0
+    assert lib_mod.lib.ngm_observed_fields(ctypes.byref(o), None) == -1  # stride
+    o.pixel_stride = 4
+    assert lib_mod.lib.ngm_observed_fields(ctypes.byref(o), None) == -1  # pointers missing
+    assert b"missing" in lib_mod.lib.ngm_last_error()
+    o.num_fields = 0
+    assert lib_mod.lib.ngm_observed_fields(ctypes.byref(o), None) == 0
 
 
 def test_no_cpu_fallback(lib_mod):

@@ -43,3 +43,15 @@ def test_fixture_is_not_on_a_rounding_edge():
     for k in ("ijs", "field_ids", "rgb_mask", "depth_mask", "term_mask"):
         assert torch.equal(getattr(t, k).to(a["out:" + k].dtype), a["out:" + k]), k
     assert torch.equal(t.term_probs.float(), a["out:term_probs"])
+
+
+def test_observed_fields_matches_reference():
+    """_get_observed_fields (ngm/run_mapping.py:1643-1670) on the fixture frame, in fp32 and (same answer) fp64."""
+    meta, a = G.load("target_mv")
+    cam = G.camera_spec(meta["camera"])
+    n = meta["num_fields"]
+    for dt in (torch.float32, torch.float64):
+        obs = T.observed_fields(cam, a["observed:rgbd"][..., 3].to(dt), a["observed:c2w"].to(dt),
+                                a["positions"][:n].to(dt), meta["field_radius"], a["observed:draw_subset"])
+        assert torch.equal(obs, a["observed:out"]), dt
+    assert 0 < len(a["observed:out"]) < n
