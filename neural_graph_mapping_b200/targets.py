@@ -21,9 +21,14 @@ Target = namedtuple("Target", ["ijs", "c2ws", "near_distances", "far_distances",
 NUM_FIELD_SAMPLES = 20  # :1291
 
 
+def _aligned(t: torch.Tensor, nbytes: int) -> torch.Tensor:
+    """The kernels read poses / pixels / boxes as 16- or 8-byte vectors; a view that starts off that grid is copied."""
+    return t if t.data_ptr() % nbytes == 0 else t.clone()
+
+
 def _store(c2ws, rgbds, frame_to_store, positions, camera):
-    c2ws = _lib.dev_f32(c2ws, "_c_c2w_tensor")
-    rgbds = _lib.dev_f32(rgbds, "_nc_rgbd_tensor")
+    c2ws = _aligned(_lib.dev_f32(c2ws, "_c_c2w_tensor"), 16)
+    rgbds = _aligned(_lib.dev_f32(rgbds, "_nc_rgbd_tensor"), 16)
     positions = _lib.dev_f32(positions, "positions")
     if c2ws.dim() != 3 or c2ws.shape[1:] != (4, 4):
         raise ValueError(f"keyframe poses must be (num_frames, 4, 4), got {tuple(c2ws.shape)}")
@@ -64,8 +69,8 @@ def target_rays(camera, c2ws, rgbds, frame_to_store, positions, field_ids, frame
     dev = c2ws.device
     ids = field_ids.to(device=dev, dtype=torch.int64).contiguous()
     cids = frame_cids.to(device=dev, dtype=torch.int64).contiguous()
-    uv = _lib.dev_f32(uv, "uv")
-    lo, hi = _lib.dev_f32(min_xys, "min_xys"), _lib.dev_f32(max_xys, "max_xys")
+    uv = _aligned(_lib.dev_f32(uv, "uv"), 8)
+    lo, hi = _aligned(_lib.dev_f32(min_xys, "min_xys"), 8), _aligned(_lib.dev_f32(max_xys, "max_xys"), 8)
     F, R, K = ids.numel(), cids.shape[1] if cids.dim() == 2 else 0, c2ws.shape[0]
     if cids.shape != (F, R) or uv.shape != (F, R, 2) or lo.shape != (F, K, 2) or hi.shape != (F, K, 2):
         raise ValueError("frame_cids (F,R), uv (F,R,2) and min/max_xys (F,K,2) disagree")
@@ -155,7 +160,7 @@ def observed_fields(camera, depth_image: torch.Tensor, pixel_ids: torch.Tensor, 
         depth_image = depth_image.contiguous()
         sh, sw = depth_image.stride()
     pix = pixel_ids.to(device=dev, dtype=torch.int64).contiguous()
-    c2w = _lib.dev_f32(c2w, "c2w")
+    c2w = _aligned(_lib.dev_f32(c2w, "c2w"), 16)
     positions = _lib.dev_f32(positions, "positions")
     out = torch.empty(positions.shape[0], dtype=torch.bool, device=dev)
     a = _lib.NgmObservedArgs()

@@ -1,13 +1,13 @@
 #!/bin/bash
-# One short gpurun call: the newest GPU tests first (fail fast), then the rest of the GPU suite, the optimizer
-# micro-benchmark and the bench line.  Outputs under gpurun_out/.
+# One short gpurun call: the newest GPU tests, then (unless "quick") the rest of the GPU suite, and the ncu launch
+# list of the training-side kernels.  Outputs under gpurun_out/.
 TAG=${1:-r1f}
-NEW="tests/test_gpu_targets.py tests/test_checkpoint.py"
+NEW="tests/test_gpu_targets.py::test_get_observed_fields_golden_and_random tests/test_gpu_fullsize.py::test_c5_loop_closure_rerender_invariance"
 mkdir -p gpurun_out
-timeout 300 python -m pytest $NEW -m gpu -x -q > gpurun_out/${TAG}_pytest_new.log 2>&1; echo "new tests rc=$?"; tail -15 gpurun_out/${TAG}_pytest_new.log
-DESEL=""; for t in $NEW; do DESEL="$DESEL --deselect $t"; done
-timeout 600 python -m pytest tests -m gpu -x -q $DESEL > gpurun_out/${TAG}_pytest_gpu.log 2>&1; echo "suite rc=$?"; tail -3 gpurun_out/${TAG}_pytest_gpu.log
-if [ "$2" != "nobench" ]; then
-timeout 120 python tools/bench_adam.py > gpurun_out/${TAG}_bench_adam.json 2> gpurun_out/${TAG}_bench_adam.err; echo "adam rc=$?"; cat gpurun_out/${TAG}_bench_adam.json; tail -3 gpurun_out/${TAG}_bench_adam.err
-timeout 300 python bench.py --no-cpu-baseline > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"; cut -c1-400 gpurun_out/${TAG}_bench.json; tail -3 gpurun_out/${TAG}_bench.err
+timeout 300 python -m pytest $NEW -x -q > gpurun_out/${TAG}_pytest_new.log 2>&1; echo "new tests rc=$?"; tail -15 gpurun_out/${TAG}_pytest_new.log
+if [ "$2" != "quick" ]; then
+timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest_gpu.log 2>&1; echo "suite rc=$?"; tail -3 gpurun_out/${TAG}_pytest_gpu.log
 fi
+timeout 200 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
+    -k regex:'adam|target|observed' --csv --log-file gpurun_out/${TAG}_train_kernels.csv python tools/prof_train.py > gpurun_out/${TAG}_prof_train.log 2>&1; echo "ncu rc=$?"; tail -2 gpurun_out/${TAG}_prof_train.log
+grep -c "adam\|target\|observed" gpurun_out/${TAG}_train_kernels.csv
