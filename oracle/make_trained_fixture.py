@@ -14,7 +14,6 @@ oracle's (= reference arithmetic) render, so that the GPU test can compare
 from __future__ import annotations
 
 import json
-import math
 import os
 import sys
 

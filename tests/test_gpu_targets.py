@@ -118,7 +118,7 @@ def test_mapping_iteration_end_to_end():
     """Target sampling -> render under autograd -> the reference's losses -> Adam, all through the drop-ins, twice
     with the same seed: bit-identical targets, a finite loss, parameters of exactly the target fields move."""
     import neural_graph_mapping_b200 as ngm
-    from neural_graph_mapping_b200 import optim, targets
+    from neural_graph_mapping_b200 import targets
     from tests_support import product_field_kwargs
 
     meta, a = G.load("target_mv")

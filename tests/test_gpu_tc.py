@@ -4,7 +4,6 @@ Tolerances (fp16 operands, fp32 accumulation; north_star: "PSNR within 0.1 dB", 
   per-pixel colour L1 (mean) <= 2e-3, depth L1 (mean) <= 5e-3 m against the fp32 reference
   golden vectors; the raw MLP output within 2% of its scale (max) / 0.3% (mean).
 """
-import ctypes as C
 
 import pytest
 import torch
