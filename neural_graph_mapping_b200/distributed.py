@@ -34,6 +34,15 @@ def shard_range(num_items: int, world: int, rank: int) -> Tuple[int, int]:
     return start, start + base + (1 if rank < rem else 0)
 
 
+def owned_fields(field_ids: torch.Tensor, num_fields: int, world: int, rank: int) -> torch.Tensor:
+    """Training at N > 1: rank r owns the contiguous rows ``shard_range(num_fields, world, r)`` of
+    the per-field tables (parameters AND Adam moments live only there), so of a global set of target fields it
+    renders, back-propagates and updates exactly the ones it owns -- the gradient of a field is local to its
+    rays, hence no all-reduce.  Returns the boolean mask of ``field_ids`` this rank owns."""
+    f0, f1 = shard_range(num_fields, world, rank)
+    return (field_ids >= f0) & (field_ids < f1)
+
+
 def packed_views(flat: torch.Tensor, n_rays: int):
     """Views of one rank's packed tile [rgbd 4n | colour var 3n | depth var n | term n]."""
     assert flat.numel() == FLOATS_PER_RAY * n_rays

@@ -66,3 +66,17 @@ def test_shard_range_uneven():
     assert [D.shard_range(10, 4, r) for r in range(4)] == [(0, 3), (3, 6), (6, 8), (8, 10)]
     assert D.shard_range(256, 8, 7) == (224, 256)
     assert D.world_info() == (1, 0)
+
+
+def test_owned_fields_partition_targets_exactly_once():
+    """Every target field of a training iteration is updated by exactly one rank (no gradient collective)."""
+    from neural_graph_mapping_b200 import distributed as D
+
+    g = torch.Generator().manual_seed(0)
+    for num_fields, world in ((256, 8), (37, 4), (5, 8)):
+        ids = torch.randperm(num_fields, generator=g)[: min(32, num_fields)]
+        owners = torch.stack([D.owned_fields(ids, num_fields, world, r) for r in range(world)]).long()
+        assert torch.equal(owners.sum(0), torch.ones(len(ids), dtype=torch.long))
+        for r in range(world):
+            f0, f1 = D.shard_range(num_fields, world, r)
+            assert all(f0 <= int(i) < f1 for i in ids[owners[r].bool()])
