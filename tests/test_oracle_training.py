@@ -74,3 +74,46 @@ def test_adam_update_on_reference_gradients():
 
     G.replay_training(meta, a, iteration, grow)
     assert a["training_iterations"].tolist() == [3, 2, 4, 2, 2, 3]  # how often each field was active
+
+
+def test_adam_update_vs_torch_optim_random_schedules():
+    """The Adam restatement against torch.optim.Adam itself driven the way the reference drives it (gather rows and
+    moments, step, scatter: ngm/run_mapping.py:679-707, 1191-1221) on random active sets, with tensors that skip
+    iterations, weight decay on and off, and gradients spanning ten orders of magnitude."""
+    for seed, wd, eps in ((0, 1e-5, 1e-15), (1, 0.0, 1e-8), (2, 1e-2, 1e-15)):
+        g = torch.Generator().manual_seed(seed)
+        shapes = {"w": (7, 5), "b": (7,), "s": ()}
+        n = 9
+        ours = {k: torch.randn(n, *s, generator=g) for k, s in shapes.items()}
+        ref = {k: v.clone() for k, v in ours.items()}
+        st = T.new_optim_state(ours)
+        rst = {k: {"step": torch.tensor(0.0), "exp_avg": torch.zeros_like(v), "exp_avg_sq": torch.zeros_like(v)}
+               for k, v in ref.items()}
+        for it in range(6):
+            ids = torch.randperm(n, generator=g)[: int(torch.randint(1, n + 1, (1,), generator=g))]
+            grads = {k: torch.randn(len(ids), *s, generator=g) * 10.0 ** float(torch.randint(-8, 2, (1,), generator=g))
+                     for k, s in shapes.items()}
+            if it % 3 == 1:
+                grads["s"] = None
+            vm = {k: v[ids].clone().requires_grad_(True) for k, v in ref.items()}
+            opt = torch.optim.Adam(list(vm.values()), lr=1e-3, eps=eps, weight_decay=wd)
+            for k, p in vm.items():
+                p.grad = grads[k]
+                if rst[k]["step"].item() > 0:
+                    opt.state[p] = {"step": rst[k]["step"], "exp_avg": rst[k]["exp_avg"][ids],
+                                    "exp_avg_sq": rst[k]["exp_avg_sq"][ids]}
+            opt.step()
+            with torch.no_grad():
+                for k, p in vm.items():
+                    ref[k][ids] = p
+                    if p in opt.state and len(opt.state[p]):
+                        rst[k]["step"] = opt.state[p]["step"]
+                        rst[k]["exp_avg"][ids] = opt.state[p]["exp_avg"]
+                        rst[k]["exp_avg_sq"][ids] = opt.state[p]["exp_avg_sq"]
+            T.adam_update(ours, st, ids, grads, 1e-3, eps, wd)
+            for k in shapes:
+                assert torch.allclose(ours[k], ref[k], atol=1e-7, rtol=2e-6), (seed, it, k)
+                for key in ("exp_avg", "exp_avg_sq"):
+                    r = rst[k][key]
+                    assert torch.allclose(st[k][key], r, atol=3e-7 * r.abs().max().item() + 1e-30, rtol=1e-5), (seed, it, k, key)
+                assert int(st[k]["step"]) == int(rst[k]["step"].item()), (seed, it, k)
