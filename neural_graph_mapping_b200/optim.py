@@ -106,6 +106,25 @@ def set_vmap_fields(driver, field_ids: torch.Tensor) -> None:
             p.requires_grad_()
 
 
+def adam_hyper(driver) -> dict:
+    """Hyper-parameters of the driver's optimizer.  The reference builds ``torch.optim.Adam(lr=_learning_rate,
+    eps=_adam_eps, weight_decay=_adam_weight_decay)`` with default betas (ngm/run_mapping.py:347-362); if the driver
+    holds that object its (possibly re-scheduled) ``param_groups[0]`` wins, and anything but plain Adam is refused
+    rather than silently replaced."""
+    opt = getattr(driver, "_optimizer", None)
+    if opt is not None:
+        if type(opt) is not torch.optim.Adam:
+            raise NotImplementedError(f"the CUDA update step implements torch.optim.Adam, not {type(opt).__name__}; "
+                                      "use install(..., optimizer=False)")
+        g = opt.param_groups[0]
+        if g.get("amsgrad") or g.get("maximize"):
+            raise NotImplementedError("amsgrad / maximize are not implemented by the CUDA update step")
+        return dict(lr=float(g["lr"]), eps=float(g["eps"]), weight_decay=float(g["weight_decay"]),
+                    betas=tuple(float(b) for b in g["betas"]))
+    return dict(lr=float(driver._learning_rate), eps=float(driver._adam_eps),
+                weight_decay=float(driver._adam_weight_decay), betas=(0.9, 0.999))
+
+
 def update_step(driver, loss_dict: dict, field_ids: torch.Tensor) -> None:
     """Drop-in for ``NeuralGraphMap._update_step`` (ngm/run_mapping.py:1183-1221)."""
     if getattr(driver, "_single_field_id", None) is not None:
@@ -117,5 +136,4 @@ def update_step(driver, loss_dict: dict, field_ids: torch.Tensor) -> None:
     driver._global_map_dict["training_iterations"][field_ids] += 1  # :1188
     if driver._optim_state is None:
         driver._optim_state = new_optim_state(model.all_fields_params)
-    adam_step(model.all_fields_params, model.vmap_fields_params, driver._optim_state, field_ids,
-              lr=driver._learning_rate, eps=driver._adam_eps, weight_decay=driver._adam_weight_decay)
+    adam_step(model.all_fields_params, model.vmap_fields_params, driver._optim_state, field_ids, **adam_hyper(driver))

@@ -75,3 +75,43 @@ def test_adam_step_has_no_cpu_path():
     st = optim.new_optim_state(p)
     optim.adam_step(p, v, st, torch.tensor([0, 1]), 1e-3)
     assert all(s["step"].item() == 0 for s in st.values())
+
+
+def test_adam_hyper_follows_the_drivers_optimizer():
+    d = _Driver(_params(2, torch.Generator().manual_seed(3)))
+    d._learning_rate, d._adam_eps, d._adam_weight_decay = 1e-3, 1e-15, 1e-5
+    assert optim.adam_hyper(d) == dict(lr=1e-3, eps=1e-15, weight_decay=1e-5, betas=(0.9, 0.999))
+    # the reference's own throw-away optimizer object (run_mapping.py:357-362), re-scheduled by the user
+    d._optimizer = torch.optim.Adam([torch.zeros((), requires_grad=True)], lr=1e-3, eps=1e-15, weight_decay=1e-5)
+    d._optimizer.param_groups[0]["lr"] = 2.5e-4
+    assert optim.adam_hyper(d) == dict(lr=2.5e-4, eps=1e-15, weight_decay=1e-5, betas=(0.9, 0.999))
+    d._optimizer = torch.optim.RMSprop([torch.zeros((), requires_grad=True)], lr=1e-3)
+    with pytest.raises(NotImplementedError, match="RMSprop"):
+        optim.adam_hyper(d)
+    d._optimizer = torch.optim.Adam([torch.zeros((), requires_grad=True)], amsgrad=True)
+    with pytest.raises(NotImplementedError, match="amsgrad"):
+        optim.adam_hyper(d)
+
+
+def test_update_step_host_sequence(monkeypatch):
+    """zero_grad -> backward -> training_iterations -> one adam_step call with the driver's hyper-parameters
+    (ngm/run_mapping.py:1183-1193); the kernel call itself is covered by the GPU tests."""
+    p = _params(4, torch.Generator().manual_seed(4))
+    d = _Driver(p)
+    d._learning_rate, d._adam_eps, d._adam_weight_decay, d._optim_state = 1e-3, 1e-15, 1e-5, None
+    d._global_map_dict = {"training_iterations": torch.zeros(4, dtype=torch.long)}
+    ids = torch.tensor([2, 0])
+    optim.set_vmap_fields(d, ids)
+    vm = d._model.vmap_fields_params
+    vm["_neus_sd"].grad = torch.ones(2)  # stale gradient from an earlier iteration: must be cleared
+    calls = []
+    monkeypatch.setattr(optim, "adam_step", lambda *a, **k: calls.append((a, k)))
+    loss = (vm["_linears.0.weight"] ** 2).sum() + vm["_linears.0.bias"].sum()
+    optim.update_step(d, {"combined": loss}, ids)
+    assert d._global_map_dict["training_iterations"].tolist() == [1, 0, 1, 0]
+    assert vm["_neus_sd"].grad is None and torch.equal(vm["_linears.0.bias"].grad, torch.ones(2, 8))
+    assert torch.allclose(vm["_linears.0.weight"].grad, 2 * p["_linears.0.weight"][ids])
+    (a, k), = calls
+    assert a[0] is p and a[1] is vm and a[2] is d._optim_state and a[3] is ids
+    assert k == dict(lr=1e-3, eps=1e-15, weight_decay=1e-5, betas=(0.9, 0.999))
+    assert set(d._optim_state) == set(p)  # created on first use in the reference's layout
