@@ -1,8 +1,8 @@
 """Precision study (CPU emulation, no GPU needed): what would fp16 ACCUMULATORS cost the tcgen05 render path?
 
-TEST INFRASTRUCTURE ONLY (see ``oracle/__init__.py``).  The fused kernel keeps fp32 accumulators in TMEM
-(128 columns per tile slot); fp16 accumulators would halve both the TMEM footprint (a third full tile slot fits)
-and the epilogue's TMEM traffic.  This script renders golden fixtures through the oracle with
+TEST INFRASTRUCTURE ONLY (see ``oracle/__init__.py``).  The fused kernel keeps fp32 accumulators in TMEM; fp16
+accumulators (read back with ``tcgen05.ld ... .pack::16b``, two columns per register) would halve the epilogue's
+registers per load and drop its fp32->fp16 convert.  This script renders golden fixtures through the oracle with
 the per-field MLP evaluated under three arithmetic models and reports the error against the reference's outputs:
 
   fp32          the reference arithmetic
