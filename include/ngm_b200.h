@@ -164,6 +164,10 @@ typedef struct NgmCompositeArgs {
   int32_t geometry_mode;    /* NgmGeometryMode */
   float geometry_factor, color_factor, truncation;
   int32_t overwrite_behind_camera; /* geometry := fill where depth < 0 (run_mapping.py:614-622) */
+  /* device flag gating the overwrite, or NULL = unconditional: the reference switches the overwrite off when
+   * every near distance is >= 0 (run_mapping.py:494-495) -- the caller evaluates `(near < 0).any()` on the
+   * device and passes its address, so the gate costs no host synchronisation */
+  const int32_t* overwrite_gate;
   /* outputs; rgbd is required, the others may be NULL */
   float* rgbd;       /* (num_rays, 4): colour(3), depth */
   float* color_var;  /* (num_rays, 3) */
@@ -338,6 +342,8 @@ typedef struct NgmRenderArgs {
   int32_t num_fields;
   int32_t scale_mode, geometry_mode, precision;
   int32_t overwrite_behind_camera;
+  int32_t _pad1;
+  const int32_t* overwrite_gate; /* see NgmCompositeArgs.overwrite_gate (run_mapping.py:494-495); NULL = unconditional */
   /* outputs: Prediction (run_mapping.py:59-69); aux ones may be NULL */
   float* rgbd;       /* (num_fields, rays_per_field, 4) */
   float* color_var;  /* (..., 3) */
@@ -394,22 +400,6 @@ int ngm_observed_fields(const NgmObservedArgs* args, void* stream);    /* run_ma
 int ngm_render_rays_fwd(const NgmRenderArgs* args, void* stream); /* run_mapping.py:440-666 (use_vmap=True) */
 int ngm_fieldset_knn_fwd(const NgmKnnFwdArgs* args, void* stream); /* models.py:347-405 (use_vmap=False) */
 int ngm_fieldset_knn_workspace_bytes(const NgmKnnFwdArgs* args, size_t* out);
-
-/* diagnostics: out(rows,n) = A(rows,k; fp16) x weight(n,k; fp32 -> fp16)^T + bias through the production
- * tcgen05 plumbing (weight packing, SWIZZLE_128B descriptors, A operand in TMEM, TMEM epilogue).
- * k % 16 == 0, 16 <= k <= 128, n <= 128; workspace >= 64 KiB. */
-int ngm_debug_tc_gemm(const float* weight, const float* bias, int n, int k, const void* a_half, int64_t rows, float* out,
-                      void* workspace, size_t workspace_bytes, void* stream);
-
-/* diagnostics: with NGM_TC_TRACE=1 in the environment, CTA 0 of every tcgen05 launch records (event, clock)
- * pairs; this copies them to HOST memory (synchronises the device); returns the event count. */
-int ngm_debug_tc_trace(uint64_t* host_out, int max_events);
-/* same without synchronising the device (reads the trace of a still-running kernel; deadlock diagnosis) */
-int ngm_debug_tc_trace_peek(uint64_t* host_out, int max_events);
-/* diagnostics: TMEM load/store micro-benchmark (the only entry point that allocates a scratch buffer itself):
- * `warps` warps per CTA issue `iters` tcgen05.ld/st (mode 0: ld.x32, 1: 2x ld.x32 in flight, 2: st.x16,
- * 3: ld.x16); writes the cycle count of CTA 0 to *host_cycles. */
-int ngm_debug_tmem_bw(int warps, int iters, int mode, uint64_t* host_cycles);
 
 int ngm_field_fwd_workspace_bytes(const NgmFieldFwdArgs* args, size_t* out);
 int ngm_render_workspace_bytes(const NgmRenderArgs* args, size_t* out);

@@ -11,8 +11,12 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 INCLUDE = os.path.join(os.path.dirname(PKG_DIR), "include")
 LIB_PATH = os.path.join(PKG_DIR, "libngm_b200.so")
 STAMP = os.path.join(PKG_DIR, ".libngm_b200.stamp")
+# the same sources with -DNGM_DEBUG_EXPORTS: adds the ngm_debug_* entry points (include/ngm_b200_debug.h) and the
+# traced twin of the tcgen05 kernel; used by tests/tools only, never by the package
+DEBUG_LIB_PATH = os.path.join(PKG_DIR, "libngm_b200_debug.so")
+DEBUG_STAMP = os.path.join(PKG_DIR, ".libngm_b200_debug.stamp")
 
-SOURCES = ["abi.cu", "sampler.cu", "composite.cu", "composite_bwd.cu", "encode.cu", "adam.cu", "targets.cu", "field_simt.cu", "field_tc.cu", "knn.cu", "tmem_bench.cu"]
+SOURCES = ["abi.cu", "sampler.cu", "composite.cu", "composite_bwd.cu", "encode.cu", "adam.cu", "targets.cu", "field_simt.cu", "field_tc.cu", "knn.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",
@@ -26,9 +30,10 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found")
 
 
-def _source_hash() -> str:
+def _source_hash(extra: str = "") -> str:
     h = hashlib.sha256()
-    files = sorted(os.listdir(CSRC)) + [os.path.join(INCLUDE, "ngm_b200.h")]
+    h.update(extra.encode())
+    files = sorted(os.listdir(CSRC)) + [os.path.join(INCLUDE, "ngm_b200.h"), os.path.join(INCLUDE, "ngm_b200_debug.h")]
     for f in files:
         path = f if os.path.isabs(f) else os.path.join(CSRC, f)
         if os.path.isfile(path):
@@ -38,18 +43,21 @@ def _source_hash() -> str:
     return h.hexdigest()
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every CUDA source to objects and link libngm_b200.so next to the package."""
-    want = _source_hash()
-    if not force and os.path.exists(LIB_PATH) and os.path.exists(STAMP) and open(STAMP).read() == want:
-        return LIB_PATH
+def build(force: bool = False, verbose: bool = False, debug: bool = False) -> str:
+    """Compile every CUDA source to objects and link libngm_b200.so next to the package
+    (``debug``: libngm_b200_debug.so, the same sources with -DNGM_DEBUG_EXPORTS)."""
+    lib_path, stamp = (DEBUG_LIB_PATH, DEBUG_STAMP) if debug else (LIB_PATH, STAMP)
+    defines = ["-DNGM_DEBUG_EXPORTS"] if debug else []
+    want = _source_hash(" ".join(defines))
+    if not force and os.path.exists(lib_path) and os.path.exists(stamp) and open(stamp).read() == want:
+        return lib_path
     nvcc = _nvcc()
-    objdir = os.path.join(PKG_DIR, "build")
+    objdir = os.path.join(PKG_DIR, "build_debug" if debug else "build")
     os.makedirs(objdir, exist_ok=True)
     procs = []
     for src in SOURCES:
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-I", INCLUDE, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *defines, "-I", INCLUDE, "-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     objs, log = [], []
     for src, obj, p in procs:
@@ -58,16 +66,16 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if p.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}:\n{out}")
         objs.append(obj)
-    link = [nvcc, "-shared", "-o", LIB_PATH, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+    link = [nvcc, "-shared", "-o", lib_path, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}")
     open(os.path.join(objdir, "build.log"), "w").write("\n".join(log))
-    open(STAMP, "w").write(want)
+    open(stamp, "w").write(want)
     if verbose:
         print("\n".join(log))
-    return LIB_PATH
+    return lib_path
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    print(build(force="--force" in sys.argv, verbose=True, debug="--debug" in sys.argv))

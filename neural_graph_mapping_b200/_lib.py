@@ -77,7 +77,7 @@ class NgmCompositeArgs(C.Structure):
         ("neus_isd", _fp), ("gt", _fp), ("color_stride", C.c_int64), ("geometry_stride", C.c_int64),
         ("rays_per_isd", C.c_int64), ("num_samples", C.c_int32), ("geometry_mode", C.c_int32),
         ("geometry_factor", C.c_float), ("color_factor", C.c_float), ("truncation", C.c_float),
-        ("overwrite_behind_camera", C.c_int32),
+        ("overwrite_behind_camera", C.c_int32), ("overwrite_gate", _fp),
         ("rgbd", _fp), ("color_var", _fp), ("depth_var", _fp), ("term_prob", _fp), ("weights", _fp),
         ("freespace", _fp), ("freespace_mask", _fp), ("tsdf", _fp), ("tsdf_mask", _fp),
     ]
@@ -143,6 +143,7 @@ class NgmRenderArgs(C.Structure):
         ("truncation", C.c_float), ("c2w_per_ray", C.c_int32), ("num_samples", C.c_int32),
         ("num_samples_guided", C.c_int32), ("num_fields", C.c_int32), ("scale_mode", C.c_int32),
         ("geometry_mode", C.c_int32), ("precision", C.c_int32), ("overwrite_behind_camera", C.c_int32),
+        ("_pad1", C.c_int32), ("overwrite_gate", _fp),
         ("rgbd", _fp), ("color_var", _fp), ("depth_var", _fp), ("term_prob", _fp),
         ("freespace", _fp), ("freespace_mask", _fp), ("tsdf", _fp), ("tsdf_mask", _fp),
         ("workspace", _fp), ("workspace_bytes", C.c_size_t),
@@ -164,7 +165,7 @@ STRUCTS = [NgmCamera, NgmFieldDesc, NgmSampleArgs, NgmFieldFwdArgs, NgmComposite
            NgmTargetVisArgs, NgmTargetRaysArgs, NgmObservedArgs]
 EXPORTS = [
     "ngm_abi_version", "ngm_last_error", "ngm_struct_size", "ngm_launch_count", "ngm_sample_rays", "ngm_field_fwd", "ngm_composite", "ngm_composite_bwd", "ngm_encode_fwd", "ngm_encode_bwd", "ngm_adam_step", "ngm_target_visibility", "ngm_target_rays", "ngm_observed_fields",
-    "ngm_render_rays_fwd", "ngm_debug_tc_gemm", "ngm_debug_tc_trace", "ngm_debug_tc_trace_peek", "ngm_debug_tmem_bw", "ngm_fieldset_knn_fwd", "ngm_fieldset_knn_workspace_bytes", "ngm_field_fwd_workspace_bytes", "ngm_render_workspace_bytes",
+    "ngm_render_rays_fwd", "ngm_fieldset_knn_fwd", "ngm_fieldset_knn_workspace_bytes", "ngm_field_fwd_workspace_bytes", "ngm_render_workspace_bytes",
 ]
 
 if not os.path.exists(LIB_PATH):
@@ -189,15 +190,6 @@ for _name, _arg in [("ngm_sample_rays", NgmSampleArgs), ("ngm_field_fwd", NgmFie
     getattr(lib, _name).argtypes = [C.POINTER(_arg), C.c_void_p]
 lib.ngm_fieldset_knn_workspace_bytes.restype = C.c_int
 lib.ngm_fieldset_knn_workspace_bytes.argtypes = [C.POINTER(NgmKnnFwdArgs), C.POINTER(C.c_size_t)]
-lib.ngm_debug_tmem_bw.restype = C.c_int
-lib.ngm_debug_tmem_bw.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p]
-lib.ngm_debug_tc_trace_peek.restype = C.c_int
-lib.ngm_debug_tc_trace_peek.argtypes = [C.c_void_p, C.c_int]
-lib.ngm_debug_tc_trace.restype = C.c_int
-lib.ngm_debug_tc_trace.argtypes = [C.c_void_p, C.c_int]
-lib.ngm_debug_tc_gemm.restype = C.c_int
-lib.ngm_debug_tc_gemm.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p,
-                                  C.c_void_p, C.c_size_t, C.c_void_p]
 lib.ngm_field_fwd_workspace_bytes.restype = C.c_int
 lib.ngm_field_fwd_workspace_bytes.argtypes = [C.POINTER(NgmFieldFwdArgs), C.POINTER(C.c_size_t)]
 lib.ngm_render_workspace_bytes.restype = C.c_int
@@ -208,6 +200,24 @@ if lib.ngm_abi_version() != NGM_ABI_VERSION:
 for _i, _s in enumerate(STRUCTS):
     if lib.ngm_struct_size(_i) != C.sizeof(_s):
         raise ImportError(f"{_s.__name__}: C sizeof {lib.ngm_struct_size(_i)} != ctypes {C.sizeof(_s)}")
+
+
+def load_debug_lib():
+    """The diagnostics build (libngm_b200_debug.so, include/ngm_b200_debug.h): tests and tools only.  The package
+    itself never loads it."""
+    path = os.path.join(_PKG, "libngm_b200_debug.so")
+    if not os.path.exists(path):
+        raise ImportError(f"{path} is missing: build it with `python -m neural_graph_mapping_b200._build --debug`")
+    dbg = C.CDLL(path)
+    dbg.ngm_last_error.restype = C.c_char_p
+    dbg.ngm_debug_tc_trace_peek.restype = C.c_int
+    dbg.ngm_debug_tc_trace_peek.argtypes = [C.c_void_p, C.c_int]
+    dbg.ngm_debug_tc_trace.restype = C.c_int
+    dbg.ngm_debug_tc_trace.argtypes = [C.c_void_p, C.c_int]
+    dbg.ngm_debug_tc_gemm.restype = C.c_int
+    dbg.ngm_debug_tc_gemm.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p,
+                                      C.c_void_p, C.c_size_t, C.c_void_p]
+    return dbg
 
 
 class NgmError(RuntimeError):

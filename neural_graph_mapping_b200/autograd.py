@@ -238,6 +238,7 @@ def _fill_composite_args(a, pk, isd, dist, depth, gt, cfg) -> None:
     a.geometry_factor, a.color_factor = cfg["geometry_factor"], cfg["color_factor"]
     a.truncation = cfg["truncation"]
     a.overwrite_behind_camera = int(cfg["overwrite"])
+    a.overwrite_gate = _lib.ptr(cfg.get("overwrite_gate"))  # device flag of run_mapping.py:494-495
     if isd is not None:
         a.neus_isd, a.rays_per_isd = isd.data_ptr(), cfg["rays_per_isd"]
     a.gt = _lib.ptr(gt)
@@ -247,7 +248,7 @@ def _fill_composite_args(a, pk, isd, dist, depth, gt, cfg) -> None:
 # the training-time _render_ijs (use_vmap=True)
 # ------------------------------------------------------------------------------------------
 def render_rays_vmap(driver, camera, ijs, c2ws, params, positions, orientations, near, far, gt, overwrite,
-                     jitter, jitter_guided, seed, precision="fp32"):
+                     jitter, jitter_guided, seed, precision="fp32", sample_offset=0):
     """Differentiable twin of the fused renderer; returns the six ``Prediction`` members."""
     from .camera import sample_rays
 
@@ -262,7 +263,7 @@ def render_rays_vmap(driver, camera, ijs, c2ws, params, positions, orientations,
             camera, ijs, S, near if near is not None else float(driver._near_distance),
             far if far is not None else float(driver._far_distance), gt=gt, num_samples_guided=G,
             range_guided=float(driver._range_depth_guided or 0.0), c2ws=c2ws, jitter=jitter, jitter_guided=jitter_guided,
-            seed=seed, want_world=True, want_depth=True)
+            seed=seed, offset=sample_offset, want_world=True, want_depth=True, want_cam=False)
         local = world_to_local(world.view(F, R * St, 3), _lib.dev_f32(positions, "positions"),
                                _lib.dev_f32(orientations, "orientations"), model._scale_mode, model._field_radius)
     outs = field_forward(proto, params, local)  # (F, R*St, 4), differentiable in params (fp32 whatever `precision`)
@@ -274,7 +275,9 @@ def render_rays_vmap(driver, camera, ijs, c2ws, params, positions, orientations,
     want_ts = driver._tsdf_weight != 0.0 and gt is not None       # :632
     cfg = dict(geometry_mode=mode, geometry_factor=float(driver._geometry_factor), color_factor=float(driver._color_factor),
                truncation=float(driver._truncation_distance or 0.0), overwrite=bool(overwrite), rays_per_isd=R,
-               want_freespace=want_fs, want_tsdf=want_ts)
+               want_freespace=want_fs, want_tsdf=want_ts,
+               overwrite_gate=((_lib.dev_f32(near, "near") < 0).any().to(torch.int32).reshape(1)
+                               if overwrite and torch.is_tensor(near) else None))
     gt_flat = None if gt is None else _lib.dev_f32(gt, "gt_distances").expand(F, R).reshape(-1).contiguous()
     rgbd, cvar, dvar, term, fs, ts, fs_m, ts_m = _CompositeFn.apply(
         outs.reshape(F * R, St, 4), isd, dist.view(F * R, St), depth.view(F * R, St), gt_flat, cfg)

@@ -81,7 +81,8 @@ def _per_ray(x, leading, device, name):
 
 
 def sample_rays_args(camera, ijs, num_samples, near, far, gt=None, num_samples_guided=0, range_guided=0.0,
-                     c2ws=None, jitter=None, jitter_guided=None, seed=0, offset=0, want_world=False, want_depth=False):
+                     c2ws=None, jitter=None, jitter_guided=None, seed=0, offset=0, want_world=False, want_depth=False,
+                     want_cam=True):
     """The ``NgmSampleArgs`` of one ``ngm_sample_rays`` call: (args, outputs, tensors the args point into)."""
     if not ijs.is_cuda:
         raise RuntimeError("ijs must be a CUDA tensor: neural_graph_mapping_b200 has no CPU path")
@@ -119,9 +120,11 @@ def sample_rays_args(camera, ijs, num_samples, near, far, gt=None, num_samples_g
             c2w_t = c2w_t.expand(*leading, 4, 4).contiguous()
             a.c2w_per_ray = 1
     a.c2ws = c2w_t.data_ptr()
-    pts = torch.empty(*leading, St, 3, device=dev)
+    # points_cam is what Camera.sample_ijs_uniform returns; the renderer itself only needs world points, distances
+    # and depths (24 + 20 St bytes per ray), so its callers pass want_cam=False and get None here
+    pts = torch.empty(*leading, St, 3, device=dev) if want_cam else None
     dist = torch.empty(*leading, St, device=dev)
-    a.points_cam, a.distances = pts.data_ptr(), dist.data_ptr()
+    a.points_cam, a.distances = _lib.ptr(pts), dist.data_ptr()
     outs = [pts, dist]
     if want_world:
         pw = torch.empty(*leading, St, 3, device=dev)

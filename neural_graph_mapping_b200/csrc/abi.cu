@@ -48,8 +48,12 @@ int launch_render_fused_tc(const NgmRenderArgs& a, void* tc_ws, float* isd_ws, c
                            const float* depth, cudaStream_t stream);
 bool render_tc_precoded(const NgmRenderArgs& a);
 int launch_permuto_rows_half(const PermutoRowsArgs& a, cudaStream_t stream);
+#ifdef NGM_DEBUG_EXPORTS
 int launch_tc_gemm_debug(const NgmFieldDesc& fd, const void* a_half, long long rows, float* out, void* workspace,
                          cudaStream_t stream);
+int tc_trace_read(unsigned long long* out, int max_events);
+int tc_trace_peek(unsigned long long* out, int max_events);
+#endif
 
 size_t knn_workspace_bytes(const NgmKnnFwdArgs& a);
 int launch_fieldset_knn(const NgmKnnFwdArgs& a, cudaStream_t stream);
@@ -61,9 +65,6 @@ int launch_adam_step(const NgmAdamArgs& a, cudaStream_t stream);
 int launch_target_visibility(const NgmTargetVisArgs& a, cudaStream_t stream);
 int launch_target_rays(const NgmTargetRaysArgs& a, cudaStream_t stream);
 int launch_observed_fields(const NgmObservedArgs& a, cudaStream_t stream);
-int tc_trace_read(unsigned long long* out, int max_events);
-int tc_trace_peek(unsigned long long* out, int max_events);
-int tmem_bw_bench(int warps, int iters, int mode, unsigned long long* host_cycles);
 
 static int validate_field(const NgmFieldDesc& fd) {
   NGM_CHECK_ARG(fd.num_layers >= 0 && fd.num_layers + 1 <= NGM_MAX_LINEARS, "num_layers=%d out of range [0,%d]",
@@ -370,14 +371,11 @@ int ngm_fieldset_knn_fwd(const NgmKnnFwdArgs* a, void* stream) {
   return launch_fieldset_knn(*a, (cudaStream_t)stream);
 }
 
+#ifdef NGM_DEBUG_EXPORTS
+/* diagnostics: only in libngm_b200_debug.so (include/ngm_b200_debug.h) */
 int ngm_debug_tc_trace_peek(uint64_t* host_out, int max_events) {
   NGM_CHECK_ARG(host_out && max_events > 0, "null args");
   return tc_trace_peek(reinterpret_cast<unsigned long long*>(host_out), max_events);
-}
-
-int ngm_debug_tmem_bw(int warps, int iters, int mode, uint64_t* host_cycles) {
-  NGM_CHECK_ARG(warps >= 1 && warps <= 16 && iters > 0 && host_cycles, "bad args");
-  return tmem_bw_bench(warps, iters, mode, reinterpret_cast<unsigned long long*>(host_cycles));
 }
 
 int ngm_debug_tc_trace(uint64_t* host_out, int max_events) {
@@ -400,6 +398,7 @@ int ngm_debug_tc_gemm(const float* weight, const float* bias, int n, int k, cons
   NGM_CHECK_ARG(workspace_bytes >= (size_t)((k + 63) / 64) * ((n + 15) / 16 * 16) * 128 + 1024, "workspace too small");
   return launch_tc_gemm_debug(fd, a_half, rows, out, workspace, (cudaStream_t)stream);
 }
+#endif  // NGM_DEBUG_EXPORTS
 
 int ngm_render_workspace_bytes(const NgmRenderArgs* a, size_t* out) {
   NGM_CHECK_ARG(a && out, "null args");
@@ -417,6 +416,7 @@ int ngm_render_rays_fwd(const NgmRenderArgs* a, void* stream_) {
   const long long num_rays = (long long)a->num_fields * a->rays_per_field;
   if (num_rays == 0) return NGM_OK;
   NGM_CHECK_ARG(a->ijs && a->c2ws && a->positions && a->orientations && a->rgbd, "missing input/output");
+  NGM_CHECK_ARG(((uintptr_t)a->rgbd & 15) == 0, "rgbd must be 16-byte aligned");
   NGM_CHECK_ARG(a->geometry_mode >= NGM_GEOM_DENSITY && a->geometry_mode <= NGM_GEOM_NRGBD, "unknown geometry_mode %d",
                 a->geometry_mode);
   if (a->geometry_mode == NGM_GEOM_NEUS) NGM_CHECK_ARG(a->neus_sd != nullptr, "neus mode needs the _neus_sd table");
@@ -497,6 +497,7 @@ int ngm_render_rays_fwd(const NgmRenderArgs* a, void* stream_) {
   c.geometry_mode = a->geometry_mode;
   c.geometry_factor = a->geometry_factor; c.color_factor = a->color_factor; c.truncation = a->truncation;
   c.overwrite_behind_camera = a->overwrite_behind_camera;
+  c.overwrite_gate = a->overwrite_gate;
   c.rgbd = a->rgbd; c.color_var = a->color_var; c.depth_var = a->depth_var; c.term_prob = a->term_prob;
   c.freespace = a->freespace; c.freespace_mask = a->freespace_mask;
   c.tsdf = a->tsdf; c.tsdf_mask = a->tsdf_mask;

@@ -50,6 +50,12 @@ inline int check_launch(const char* what) {
 
 int num_sms();
 
+// behind-camera overwrite (run_mapping.py:614-622) with the reference's gate (:494-495): on only when requested AND
+// (no gate given, or the device flag "some near distance is negative" is set)
+__device__ __forceinline__ int overwrite_enabled(int requested, const int32_t* gate) {
+  return requested && (gate == nullptr || __ldg(gate) != 0);
+}
+
 // internal: fp16 A-operand rows of the permutohedral encoding for the tcgen05 renderer (encode.cu)
 struct PermutoRowsArgs {
   NgmFieldDesc field;

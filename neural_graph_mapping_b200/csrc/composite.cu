@@ -143,7 +143,9 @@ __device__ __forceinline__ SampleTerms eval_block(const RayCtx& c, int blk, cons
 // ahead), then nine warp reductions.  The variances use  Sum w (m - x)^2 = Sum w x^2 - m^2 (2 - Sum w)
 // (exact algebra; the fp32 cancellation error is ~1e-7 of the colour / depth scale).
 template <bool PACKED>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, 5) composite_kernel(NgmCompositeArgs a) {
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 5) composite_kernel(NgmCompositeArgs a_in) {
+  NgmCompositeArgs a = a_in;
+  a.overwrite_behind_camera = overwrite_enabled(a_in.overwrite_behind_camera, a_in.overwrite_gate);
   const int lane = threadIdx.x & 31;
   // broadcast -> provably warp-uniform ray index, so the shuffles below are emitted without
   // per-instruction WARPSYNC / ENDCOLLECTIVE convergence wrappers
@@ -230,7 +232,9 @@ __device__ __forceinline__ void accumulate(Moments& a, float occ, float z, float
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(kStagedWarps * 32) composite_staged_kernel(NgmCompositeArgs a) {
+__global__ void __launch_bounds__(kStagedWarps * 32) composite_staged_kernel(NgmCompositeArgs a_in) {
+  NgmCompositeArgs a = a_in;
+  a.overwrite_behind_camera = overwrite_enabled(a_in.overwrite_behind_camera, a_in.overwrite_gate);
   extern __shared__ __align__(16) uint8_t staged_smem[];
   const int lane = threadIdx.x & 31;
   const int warp_in_block = threadIdx.x >> 5;

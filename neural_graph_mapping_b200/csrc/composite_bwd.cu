@@ -42,7 +42,9 @@ struct BwdRay {
   }
 };
 
-__global__ void __launch_bounds__(128) composite_bwd_kernel(NgmCompositeBwdArgs b) {
+__global__ void __launch_bounds__(128) composite_bwd_kernel(NgmCompositeBwdArgs b_in) {
+  NgmCompositeBwdArgs b = b_in;
+  b.fwd.overwrite_behind_camera = overwrite_enabled(b_in.fwd.overwrite_behind_camera, b_in.fwd.overwrite_gate);
   const NgmCompositeArgs& a = b.fwd;
   const long long ray = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (ray >= a.num_rays) return;

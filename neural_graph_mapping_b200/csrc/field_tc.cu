@@ -169,6 +169,7 @@ struct TcParams {
   float inv_S;  // 1 / S (torch.linspace step)
   long long rays_per_field;
   int geometry_mode, overwrite;
+  const int* overwrite_gate;  // device flag of run_mapping.py:494-495 (some near < 0), or nullptr
   float geometry_factor, color_factor, truncation;
   const float* neus_isd;  // (num_fields)
   float* rgbd;
@@ -386,7 +387,8 @@ __device__ __forceinline__ void comp_stage1(const TcParams& p, Smem& sm, int s, 
   const bool ray_ok = sm.comp[s][7][row] != 0.0f;
   const bool valid = ray_ok && k < St;
   const bool has_gt = p.gt != nullptr;
-  if (p.overwrite && z < 0.0f) g = (mode == NGM_GEOM_OCCUPANCY || mode == NGM_GEOM_DENSITY) ? -100.0f : 1.0f;
+  if (p.overwrite && z < 0.0f && (p.overwrite_gate == nullptr || __ldg(p.overwrite_gate) != 0))
+    g = (mode == NGM_GEOM_OCCUPANCY || mode == NGM_GEOM_DENSITY) ? -100.0f : 1.0f;
   if (valid && (p.freespace || p.tsdf)) {
     const long long ray_global = f * p.rays_per_field + tile_in_field * p.rpt + (row >> p.sp_shift);
     const long long idx = ray_global * St + k;
@@ -981,10 +983,15 @@ int tc_grid(long long total_tiles) {
   return (int)(total_tiles < g ? total_tiles : g);
 }
 
+// the traced twin of the kernel exists only in the debug build (libngm_b200_debug.so, -DNGM_DEBUG_EXPORTS)
 int tc_trace_enabled() {
+#ifdef NGM_DEBUG_EXPORTS
   static int v = -1;
   if (v < 0) { const char* e = getenv("NGM_TC_TRACE"); v = (e && e[0] == '1') ? 1 : 0; }
   return v;
+#else
+  return 0;
+#endif
 }
 
 template <int MODE>
@@ -1002,11 +1009,13 @@ int launch_tc(const TcParams& p_in, int octaves, size_t smem, int grid, cudaStre
   };
   switch (octaves * 2 + (p.trace ? 1 : 0)) {  // octaves == 0: permutohedral
     case 0: return go(tc_kernel<MODE, 0, false>);
-    case 1: return go(tc_kernel<MODE, 0, true>);
     case 8: return go(tc_kernel<MODE, 4, false>);
-    case 9: return go(tc_kernel<MODE, 4, true>);
     case 16: return go(tc_kernel<MODE, 8, false>);
+#ifdef NGM_DEBUG_EXPORTS
+    case 1: return go(tc_kernel<MODE, 0, true>);
+    case 9: return go(tc_kernel<MODE, 4, true>);
     case 17: return go(tc_kernel<MODE, 8, true>);
+#endif
     default: set_error("tcgen05 path: unsupported num_octaves %d", octaves); return NGM_ERR_UNSUPPORTED;
   }
 }
@@ -1052,8 +1061,6 @@ size_t tc_smem_bytes(const TcImage& im) {
                       (tc_trace_enabled() == 1 ? (size_t)kTraceRoles * kTraceN * sizeof(uint2) : 0);
   return need < 120 * 1024 ? 120 * 1024 : need;
 }
-
-#include "field_tc3.cuh"
 
 }  // namespace
 
@@ -1124,7 +1131,6 @@ int launch_field_fwd_tc(const NgmFieldFwdArgs& a, cudaStream_t stream) {
     p.raw_a = reinterpret_cast<const __half*>(e.out);
   }
   const int grid = tc_grid(p.total_tiles);
-  if (tc3_enabled() && tc3_supported(a.field, p.im)) return launch_tc3(p, a.field.nerf_num_octaves, grid, stream);
   return launch_tc<1>(p, tc_oct(a.field), tc_smem_bytes(p.im), grid, stream);
 }
 
@@ -1150,6 +1156,7 @@ int launch_field_fwd_tc_gather(const NgmFieldFwdArgs& a, const int* entries, con
   return launch_tc<1>(p, tc_oct(a.field), tc_smem_bytes(p.im), grid, stream);
 }
 
+#ifdef NGM_DEBUG_EXPORTS
 // debug / unit-test entry: D = A (fp16, given) x W^T with the production weight packing, smem
 // descriptors, TMEM A operand and epilogue -- isolates the tcgen05 plumbing from the renderer.
 int launch_tc_gemm_debug(const NgmFieldDesc& fd, const void* a_half, long long rows, float* out, void* workspace,
@@ -1196,6 +1203,8 @@ int tc_trace_peek(unsigned long long* out, int max_events) {
   cudaStreamDestroy(st);
   return rc;
 }
+
+#endif  // NGM_DEBUG_EXPORTS
 
 int launch_neus_isd(const float* sd, const int64_t* slots, int num_fields, float* out, cudaStream_t stream);
 
@@ -1246,6 +1255,7 @@ int launch_render_fused_tc(const NgmRenderArgs& a, void* tc_ws, float* isd_ws, c
   p.rays_per_field = a.rays_per_field;
   p.geometry_mode = a.geometry_mode;
   p.overwrite = a.overwrite_behind_camera;
+  p.overwrite_gate = a.overwrite_gate;
   p.geometry_factor = a.geometry_factor; p.color_factor = a.color_factor; p.truncation = a.truncation;
   if (a.geometry_mode == NGM_GEOM_NEUS) {
     if (int rc = launch_neus_isd(a.neus_sd, a.field_slots, a.num_fields, isd_ws, stream)) return rc;

@@ -4,14 +4,24 @@ The reference is single-GPU (no collective anywhere).  Rays never interact and f
 only read-only, so the path shards with NO data-path collective; the one exchange step is a
 single all-gather of the rendered tiles (9 fp32 = 36 B per ray: rgbd 4, colour var 3, depth var
 1, term prob 1) so every rank ends with the full Prediction.
+
+Three partitions of a render batch:
+
+* ``render_rays_gathered``: every rank renders ITS OWN (F, R) batch (its keyframe) -- weak scaling;
+* ``render_rays_sharded``:  the GLOBAL (F, R) batch split by FIELD, rank r gets fields [f0, f1) and therefore only
+  ever touches its own fields' parameters (the training / BASELINE config 4 shape);
+* ``render_rays_split``:    the GLOBAL (F, R) batch split by RAY inside every field (one keyframe over N GPUs).
+
+The all-gather can be left in flight (``async_gather=True`` returns a :class:`PendingTiles`): NCCL runs on its own
+stream, so step i's collective overlaps step i+1's render and the caller waits only when it needs the tiles.
 """
 from __future__ import annotations
 
-from typing import Tuple
+from typing import Optional, Tuple
 
 import torch
 
-from .renderer import Prediction, render_rays
+from .renderer import Prediction, _next_seed, render_rays
 
 FLOATS_PER_RAY = 9
 
@@ -54,29 +64,53 @@ def packed_views(flat: torch.Tensor, n_rays: int):
     return rgbd, cvar, dvar, term
 
 
-def gather_tiles(local_flat: torch.Tensor, group=None) -> torch.Tensor:
-    """All-gather equally sized packed tiles -> (world, len(local_flat))."""
+class PendingTiles:
+    """An all-gather of rendered tiles that may still be in flight.  ``wait()`` orders the current CUDA stream
+    after the collective (no host block) and returns the (world, 9 n) buffer; ``local`` is this rank's own tile,
+    valid in stream order right after the render (e.g. for a device-to-host copy that need not wait)."""
+
+    def __init__(self, buffer: torch.Tensor, local: torch.Tensor, work=None) -> None:
+        self.buffer, self.local, self._work = buffer, local, work
+
+    def wait(self) -> torch.Tensor:
+        if self._work is not None:
+            self._work.wait()
+            self._work = None
+        return self.buffer
+
+
+def gather_tiles(local_flat: torch.Tensor, group=None, out: Optional[torch.Tensor] = None, async_op: bool = False):
+    """All-gather equally sized packed tiles -> (world, len(local_flat)); with ``async_op`` a PendingTiles."""
     d = _dist()
     world, _ = world_info(group)
     if d is None or world == 1:
-        return local_flat.view(1, -1)
-    out = torch.empty(world, local_flat.numel(), device=local_flat.device, dtype=local_flat.dtype)
-    d.all_gather_into_tensor(out.view(-1), local_flat.contiguous(), group=group)
-    return out
+        buf = local_flat.view(1, -1)
+        return PendingTiles(buf, local_flat) if async_op else buf
+    if out is None:
+        out = torch.empty(world, local_flat.numel(), device=local_flat.device, dtype=local_flat.dtype)
+    work = d.all_gather_into_tensor(out.view(-1), local_flat.contiguous(), group=group, async_op=async_op)
+    return PendingTiles(out, local_flat, work) if async_op else out
 
 
 def render_rays_gathered(driver, ijs, c2ws, camera, field_ids, near=None, far=None, gt=None,
-                         return_packed: bool = False, group=None, **kw):
+                         return_packed: bool = False, group=None, async_gather: bool = False,
+                         buffers: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, **kw):
     """Each rank renders ITS OWN (F, R) ray batch (e.g. its keyframe / its pixel tiles); the packed
-    tiles of all ranks are all-gathered.  Returns the packed (world, 9*F*R) buffer or a list of
-    per-rank ``Prediction`` views into it."""
+    tiles of all ranks are all-gathered.  Returns the packed (world, 9*F*R) buffer, a PendingTiles
+    (``async_gather``), or a list of per-rank ``Prediction`` views.  ``buffers`` = (local 9n, gathered world x 9n)
+    preallocated tensors to reuse (a step loop double-buffers them)."""
     F, R = ijs.shape[0], ijs.shape[1]
     n = F * R
-    local = torch.empty(FLOATS_PER_RAY * n, device=ijs.device, dtype=torch.float32)
+    if buffers is not None:
+        local, out = buffers
+    else:
+        local, out = torch.empty(FLOATS_PER_RAY * n, device=ijs.device, dtype=torch.float32), None
     rgbd, cvar, dvar, term = packed_views(local, n)
     render_rays(driver, ijs, c2ws, camera, field_ids, True, near, far, gt,
                 out=(rgbd.view(F, R, 4), cvar.view(F, R, 3), dvar.view(F, R), term.view(F, R)), **kw)
-    buf = gather_tiles(local, group)
+    if async_gather:
+        return gather_tiles(local, group, out, async_op=True)
+    buf = gather_tiles(local, group, out)
     if return_packed:
         return buf
     preds = []
@@ -86,25 +120,84 @@ def render_rays_gathered(driver, ijs, c2ws, camera, field_ids, near=None, far=No
     return preds
 
 
-def render_rays_sharded(driver, ijs, c2ws, camera, field_ids, near=None, far=None, gt=None, group=None, **kw):
+def shared_seed(device, group=None) -> int:
+    """One jitter seed for all ranks: rank 0 draws it (torch's CPU generator, like every render), an 8-byte
+    broadcast hands it out."""
+    d = _dist()
+    world, rank = world_info(group)
+    seed = _next_seed()
+    if d is None or world == 1:
+        return seed
+    t = torch.tensor([seed], dtype=torch.int64, device=device)
+    src = d.get_global_rank(group, 0) if group is not None else 0
+    d.broadcast(t, src=src, group=group)
+    return int(t.item())
+
+
+def _leading_slice(x, lead_shape, sl):
+    """Slice a per-ray input by ``sl`` along its leading dims if it carries them; scalars / shared values pass."""
+    if x is None or not torch.is_tensor(x) or x.dim() < len(lead_shape) or tuple(x.shape[:len(lead_shape)]) != lead_shape:
+        return x
+    return x[sl]
+
+
+def render_rays_sharded(driver, ijs, c2ws, camera, field_ids, near=None, far=None, gt=None, group=None,
+                        jitter=None, jitter_guided=None, seed: Optional[int] = None, **kw):
     """Training-batch shape (SURVEY.md 8e, C4): the GLOBAL (F, R) batch is known on every rank;
     rank r renders fields [f0, f1) -- so it only ever touches its own fields' parameters -- and
-    the tiles are all-gathered into the full (F, R) Prediction on every rank."""
+    the tiles are all-gathered into the full (F, R) Prediction on every rank.
+
+    Per-ray inputs given for the whole batch (``near``/``far``/``gt``, per-ray ``c2ws``, ``jitter`` /
+    ``jitter_guided``) are sliced to the shard; a shared (4, 4) ``c2ws`` is passed through.  Without injected
+    jitter all ranks use ONE seed (``seed`` or a broadcast from rank 0) and every shard's samples keep their global
+    indices, so the sharded render is bit-identical to the same batch rendered on one GPU with that seed."""
     world, rank = world_info(group)
     F, R = ijs.shape[0], ijs.shape[1]
     if F % world != 0:
         raise ValueError(f"num_fields={F} must be divisible by the world size {world}")
     f0, f1 = shard_range(F, world, rank)
-
-    def sl(x, per_ray=True):
-        if x is None:
-            return None
-        return x[f0:f1] if (per_ray and torch.is_tensor(x) and x.dim() >= 2 and x.shape[0] == F) else x
-
-    c2 = c2ws if c2ws.dim() == 2 else c2ws[f0:f1]
-    buf = render_rays_gathered(driver, ijs[f0:f1], c2, camera, field_ids[f0:f1], sl(near), sl(far), sl(gt),
-                               return_packed=True, group=group, **kw)
+    sl = slice(f0, f1)
+    lead = (F, R)
+    c2 = c2ws if c2ws.numel() == 16 else _leading_slice(c2ws, lead, sl)
+    gt_s = _leading_slice(gt, lead, sl)
+    S = int(driver._num_samples)
+    St = S + (int(driver._num_samples_depth_guided) if gt is not None else 0)
+    if jitter is None and seed is None:
+        seed = shared_seed(ijs.device, group)
+    buf = render_rays_gathered(
+        driver, ijs[sl], c2, camera, field_ids[sl], _leading_slice(near, lead, sl), _leading_slice(far, lead, sl), gt_s,
+        return_packed=True, group=group, jitter=_leading_slice(jitter, lead, sl),
+        jitter_guided=_leading_slice(jitter_guided, lead, sl), seed=seed, sample_offset=f0 * R * St, **kw)
     n = (f1 - f0) * R
     parts = [packed_views(buf[r], n) for r in range(buf.shape[0])]
     cat = lambda i, shape: torch.cat([p[i] for p in parts]).view(*shape)  # noqa: E731
     return Prediction(cat(0, (F, R, 4)), cat(1, (F, R, 3)), cat(2, (F, R)), cat(3, (F, R)), None, None)
+
+
+def render_rays_split(driver, ijs, c2ws, camera, field_ids, near=None, far=None, gt=None, group=None,
+                      jitter=None, jitter_guided=None, return_packed: bool = False, async_gather: bool = False,
+                      buffers=None, **kw):
+    """ONE batch over N GPUs by RAY (strong scaling of a keyframe render): rank r renders rays
+    [r0, r1) of EVERY field, so all ranks need all fields' parameters (replicated, ~9 MB fp16 for 75 fields) and the
+    per-rank kernel time drops by N.  R must be divisible by the world size.  The result is the full (F, R)
+    Prediction on every rank (or the packed (world, 9 F R/N) buffer / a PendingTiles).  In-kernel jitter of a split
+    render is a valid stratified draw but not the single-GPU stream (ray indices restart per shard); inject
+    ``jitter`` for bit-identity."""
+    world, rank = world_info(group)
+    F, R = ijs.shape[0], ijs.shape[1]
+    if R % world != 0:
+        raise ValueError(f"rays_per_field={R} must be divisible by the world size {world}")
+    r0, r1 = shard_range(R, world, rank)
+    sl = (slice(None), slice(r0, r1))
+    lead = (F, R)
+    c2 = c2ws if c2ws.numel() == 16 else _leading_slice(c2ws, lead, sl)
+    res = render_rays_gathered(
+        driver, ijs[sl], c2, camera, field_ids, _leading_slice(near, lead, sl), _leading_slice(far, lead, sl),
+        _leading_slice(gt, lead, sl), return_packed=True, group=group, async_gather=async_gather, buffers=buffers,
+        jitter=_leading_slice(jitter, lead, sl), jitter_guided=_leading_slice(jitter_guided, lead, sl), **kw)
+    if async_gather or return_packed:
+        return res
+    Rs = r1 - r0
+    parts = [packed_views(res[r], F * Rs) for r in range(res.shape[0])]
+    cat = lambda i, tail: torch.cat([p[i].view(F, Rs, *tail) for p in parts], 1)  # noqa: E731
+    return Prediction(cat(0, (4,)), cat(1, (3,)), cat(2, ()), cat(3, ()), None, None)

@@ -57,7 +57,7 @@ def fieldset_forward_knn(model, query_points, field_positions, field_orientation
 def render_rays_knn(driver, ijs, c2ws, camera, field_ids, near, far, gt, overwrite, jitter):
     """``_render_ijs`` with use_vmap=False (ngm/run_mapping.py:586-595): sampler stage -> kNN
     field set (in blocks of ``_block_size`` points, like utils.batched_evaluation) -> compositor."""
-    from .renderer import Prediction, _next_seed, _precision, composite
+    from .renderer import Prediction, _next_seed, _overwrite_gate, _precision, composite
 
     model = driver._model
     dev = ijs.device
@@ -76,7 +76,7 @@ def render_rays_knn(driver, ijs, c2ws, camera, field_ids, near, far, gt, overwri
             camera, ijs, S, driver._near_distance if near is None else near,
             driver._far_distance if far is None else far, gt=gt, num_samples_guided=G,
             range_guided=float(driver._range_depth_guided or 0.0), c2ws=c2ws, jitter=jitter,
-            seed=0 if jitter is not None else _next_seed(), want_world=True, want_depth=True)
+            seed=0 if jitter is not None else _next_seed(), want_world=True, want_depth=True, want_cam=False)
         St = dist.shape[-1]
         pts = world.reshape(-1, 3)
         outs = []
@@ -88,10 +88,12 @@ def render_rays_knn(driver, ijs, c2ws, camera, field_ids, near, far, gt, overwri
         gt_t = None if gt is None else _lib.dev_f32(gt, "gt").expand(leading).reshape(-1).contiguous()
         want_fs = driver._freespace_weight != 0.0 and gt is not None
         want_ts = driver._tsdf_weight != 0.0 and gt is not None
+        gate = _overwrite_gate(_lib.dev_f32(near, "near")) if overwrite and torch.is_tensor(near) else None
         rgbd, cvar, dvar, term, _, aux = composite(
             o, o[:, 3], dist.reshape(n, St), depth.reshape(n, St), driver._geometry_mode, driver._geometry_factor,
             driver._color_factor, gt=gt_t, truncation=float(driver._truncation_distance or 0.0),
-            overwrite_behind_camera=overwrite, want_aux=(want_fs, want_ts), color_stride=4, geometry_stride=4)
+            overwrite_behind_camera=overwrite, want_aux=(want_fs, want_ts), color_stride=4, geometry_stride=4,
+            overwrite_gate=gate)
         fs, fs_m, ts, ts_m = aux
         freespace = fs[fs_m] if fs is not None else None
         tsdf = ts[ts_m] if ts is not None else None

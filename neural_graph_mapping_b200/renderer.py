@@ -28,10 +28,41 @@ Prediction = namedtuple(
 )
 
 
+_SEED_POOL: list = []
+_SEED_EPOCH = None
+
+
 def _next_seed() -> int:
-    """Philox seed for in-kernel jitter, drawn from torch's CPU generator (so torch.manual_seed
-    makes renders reproducible, like the reference's torch.rand)."""
-    return int(torch.randint(0, 2**62, (1,), dtype=torch.int64).item())
+    """Philox seed for in-kernel jitter, drawn from torch's CPU generator (so torch.manual_seed makes renders
+    reproducible, like the reference's torch.rand).  Seeds are drawn 256 at a time -- one torch call per 256
+    renders instead of one per render -- and the pool is dropped when the generator is re-seeded."""
+    global _SEED_EPOCH
+    epoch = torch.initial_seed()
+    if not _SEED_POOL or epoch != _SEED_EPOCH:
+        _SEED_EPOCH = epoch
+        _SEED_POOL[:] = torch.randint(0, 2**62, (256,), dtype=torch.int64).tolist()[::-1]
+    return _SEED_POOL.pop()
+
+
+_WORKSPACES: dict = {}
+
+
+def _workspace(dev: torch.device, nbytes: int) -> torch.Tensor:
+    """Per-(device, stream) scratch buffer, grown on demand and reused by every render call on that stream
+    (stream order makes the reuse safe; calls on different streams get different buffers)."""
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(),
+           torch.cuda.current_stream(dev).cuda_stream)
+    ws = _WORKSPACES.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(int(nbytes * 1.25), 1 << 16), device=dev, dtype=torch.uint8)
+        _WORKSPACES[key] = ws
+    return ws
+
+
+def _overwrite_gate(near_t: torch.Tensor) -> torch.Tensor:
+    """Device flag of ngm/run_mapping.py:494-495: the behind-camera overwrite stays on only if SOME near distance
+    is negative.  Evaluated on the device (the reference synchronises the host with ``.all()`` here)."""
+    return (near_t < 0).any().to(torch.int32).reshape(1)
 
 
 def _precision(driver) -> str:
@@ -53,13 +84,18 @@ def render_rays(
     jitter: Optional[torch.Tensor] = None,
     jitter_guided: Optional[torch.Tensor] = None,
     out: Optional[tuple] = None,
+    seed: Optional[int] = None,
+    sample_offset: int = 0,
 ) -> Prediction:
     """Drop-in for ``NeuralGraphMap._render_ijs`` (ngm/run_mapping.py:440-666).
 
     Extra keyword-only-in-practice arguments ``jitter`` / ``jitter_guided`` inject the
     stratified-sampling noise (parity runs); by default it is generated in-kernel (Philox).
     ``out`` = preallocated (rgbds, color_vars, depth_vars, term_probs) to render into (used by the
-    multi-GPU all-gather so the tiles land directly in the send buffer).
+    multi-GPU all-gather so the tiles land directly in the send buffer).  ``seed`` / ``sample_offset`` pin the
+    in-kernel jitter stream: sample k of ray r draws element ``sample_offset + r * St + k`` of stream ``seed``, so
+    a shard of a batch rendered with the batch's seed and its first sample's global index as offset draws
+    exactly what the whole batch would (multi-GPU field sharding).
     """
     if use_vmap and field_ids is None:
         raise ValueError("field_ids=None only supported for use_vmap=False")  # run_mapping.py:497-498
@@ -67,8 +103,9 @@ def render_rays(
         raise NotImplementedError("single_field_id debugging mode is not implemented by the CUDA path")
     if not ijs.is_cuda:
         raise RuntimeError("render_rays needs CUDA tensors: neural_graph_mapping_b200 has no CPU path")
-    # run_mapping.py:494-495 decides this with a host-synchronising `.all()`; samples behind the
-    # camera exist only if some near < 0, so the kernel's per-sample test gives the same result.
+    # run_mapping.py:494-495: no overwrite without near distances, or when all of them are >= 0 -- the second half
+    # is a device flag (`_overwrite_gate`) the kernels read, so the decision costs no host synchronisation.  (It is
+    # not implied by the per-sample test: depth-guided samples can lie behind the camera although near >= 0.)
     overwrite = bool(overwrite_samples_behind_camera) and near_distances is not None
     if not use_vmap:
         from .knn import render_rays_knn
@@ -110,7 +147,9 @@ def render_rays(
             raise ValueError("out= is not supported on the differentiable path")
         return Prediction(*ag.render_rays_vmap(
             driver, camera, ijs, c2ws, params, positions, orientations, near_distances, far_distances, gt_distances,
-            overwrite, jitter, jitter_guided, 0 if jitter is not None else _next_seed(), _precision(driver)))
+            overwrite, jitter, jitter_guided,
+            0 if jitter is not None else (_next_seed() if seed is None else int(seed)), _precision(driver),
+            sample_offset=int(sample_offset)))
     with torch.no_grad(), torch.cuda.device(dev):
         a.field, k2 = proto.field_desc(params, True)
         keep += k2
@@ -142,7 +181,8 @@ def render_rays(
         jt = None if jitter is None else _lib.dev_f32(jitter, "jitter")
         jg = None if jitter_guided is None else _lib.dev_f32(jitter_guided, "jitter_guided")
         a.jitter, a.jitter_guided = _lib.ptr(jt), _lib.ptr(jg)
-        a.seed = 0 if jt is not None else _next_seed()
+        a.seed = 0 if jt is not None else (_next_seed() if seed is None else int(seed))
+        a.offset = int(sample_offset)
         pos = _lib.dev_f32(positions, "positions")
         ori = _lib.dev_f32(orientations, "orientations")
         a.positions, a.orientations, a.field_slots = pos.data_ptr(), ori.data_ptr(), _lib.ptr(slots)
@@ -152,6 +192,10 @@ def render_rays(
         a.geometry_factor, a.color_factor = float(driver._geometry_factor), float(driver._color_factor)
         a.truncation = float(driver._truncation_distance or 0.0)
         a.overwrite_behind_camera = int(overwrite)
+        if overwrite:
+            gate = _overwrite_gate(near_t)
+            keep.append(gate)
+            a.overwrite_gate = gate.data_ptr()
         a.precision = _lib.PREC[_precision(driver)]
         if driver._geometry_mode == "neus":
             sd = _lib.dev_f32(params["_neus_sd"], "_neus_sd")
@@ -162,6 +206,8 @@ def render_rays(
             for t_, shp in ((rgbd, (F, R, 4)), (cvar, (F, R, 3)), (dvar, (F, R)), (term, (F, R))):
                 if tuple(t_.shape) != shp or not t_.is_contiguous() or t_.dtype != torch.float32:
                     raise ValueError("out tensors must be contiguous fp32 of the Prediction shapes")
+            if rgbd.data_ptr() % 16 != 0:  # the kernels store a ray's rgbd as one 16-byte vector
+                raise ValueError("out[0] (rgbds) must be 16-byte aligned")
         else:
             rgbd = torch.empty(F, R, 4, device=dev)
             cvar = torch.empty(F, R, 3, device=dev)
@@ -179,7 +225,7 @@ def render_rays(
             a.tsdf, a.tsdf_mask = ts.data_ptr(), ts_m.data_ptr()
         need = C.c_size_t(0)
         _lib.check(_lib.lib.ngm_render_workspace_bytes(C.byref(a), C.byref(need)))
-        ws = torch.empty(max(need.value, 16), device=dev, dtype=torch.uint8)
+        ws = _workspace(dev, need.value)
         a.workspace, a.workspace_bytes = ws.data_ptr(), need.value
         _lib.check(_lib.lib.ngm_render_rays_fwd(C.byref(a), _lib.stream_ptr(dev)))
         # the reference returns 1-D masked tensors (data-dependent length, :628,637)
@@ -190,7 +236,8 @@ def render_rays(
 
 def composite_args(colors, geometries, distances, depths, geometry_mode, geometry_factor, color_factor=1.0,
                    neus_isd=None, rays_per_isd=1, gt=None, truncation=0.0, overwrite_behind_camera=False,
-                   want_weights=False, want_aux=(False, False), color_stride=None, geometry_stride=None):
+                   want_weights=False, want_aux=(False, False), color_stride=None, geometry_stride=None,
+                   overwrite_gate=None):
     """The ``NgmCompositeArgs`` of one ``ngm_composite`` call and its freshly allocated outputs."""
     dev = distances.device
     N, S = distances.shape
@@ -203,6 +250,7 @@ def composite_args(colors, geometries, distances, depths, geometry_mode, geometr
     a.geometry_mode = _lib.GEOM[geometry_mode]
     a.geometry_factor, a.color_factor, a.truncation = float(geometry_factor), float(color_factor), float(truncation)
     a.overwrite_behind_camera = int(overwrite_behind_camera)
+    a.overwrite_gate = _lib.ptr(overwrite_gate)  # device int32 flag (run_mapping.py:494-495) or None = unconditional
     if neus_isd is not None:
         a.neus_isd, a.rays_per_isd = neus_isd.data_ptr(), rays_per_isd
     a.gt = _lib.ptr(gt)
@@ -270,10 +318,18 @@ def quadrature(driver, sample_colors, sample_geometries, sample_distances, sampl
 
 # render_image pixel blocks: the reference cuts the image into `pixel_block_size` (8,192) pixel blocks to bound the
 # memory of its PyTorch intermediates (ngm/run_mapping.py:424-435).  Pixels are independent, so the block size only
-# changes memory and launch count; the CUDA path needs ~200 B of workspace per sample and renders a 640x480x64 frame
-# in 11.1 ms as one block against 12.9 ms as 38 blocks (tools/bench_knn.py).  Blocks are therefore at least this
-# many pixels (0 = exactly the reference's blocks).
-IMAGE_BLOCK_PIXELS = 1 << 19
+# changes memory and launch count (a 640x480x64 frame: 11.1 ms as one block, 12.9 ms as 38 blocks, tools/bench_knn.py).
+# The CUDA path therefore renders blocks as large as a transient-memory budget allows -- never smaller than the
+# configured `pixel_block_size` -- counting samples, not pixels: the kNN path holds ~320 B per SAMPLE in flight
+# (world point, distance, depth, K = 2 fp16 feature rows, bucketing tables, raw outputs), so with the reference's
+# default eval setting of 640 samples per ray a block is ~40k pixels, with 64 samples a whole 640x480 frame.
+IMAGE_BLOCK_BYTES = 8 << 30
+IMAGE_BYTES_PER_SAMPLE = 320
+
+
+def image_block_pixels(driver) -> int:
+    samples = max(int(driver._num_samples), 1)
+    return max(int(driver._pixel_block_size), IMAGE_BLOCK_BYTES // (samples * IMAGE_BYTES_PER_SAMPLE))
 
 
 @torch.no_grad()
@@ -283,7 +339,7 @@ def render_image(driver, c2w: torch.Tensor, camera, progressbar: bool = False):
     dev = driver._device
     ijs = torch.cartesian_prod(torch.arange(h, device=dev), torch.arange(w, device=dev))
     rgbds, _, d_vars, _, _, _ = batched_evaluation(
-        lambda x: driver._render_ijs(x, c2w, camera), ijs, block_size=max(int(driver._pixel_block_size), IMAGE_BLOCK_PIXELS),
+        lambda x: driver._render_ijs(x, c2w, camera), ijs, block_size=image_block_pixels(driver),
         progressbar=progressbar)
     return rgbds.reshape(h, w, 4), d_vars.reshape(h, w)
 
@@ -387,7 +443,10 @@ class RenderState:
     def save_model(self, path: str) -> None:
         """The checkpoint half of ``NeuralGraphMap.save_model`` (ngm/run_mapping.py:2147-2156): same three keys,
         same tensors (stacked per-field parameters in the reference's state-dict names, the over-allocated map
-        tables with their ``num``), so either side loads the other's file."""
+        tables with their ``num``), so either side loads the other's file.  Verified with a checkpoint written by the
+        reference for the in-tree encodings (tests/test_checkpoint.py); for the permutohedral encoding the key names
+        and tensor kinds of the third-party module (``_encoding.*``) are assumed, not verified -- its source is not
+        in the reference tree (parity unpinned)."""
         torch.save({"map_dict": self._global_map_dict, "all_fields_params": self._model.all_fields_params,
                     "state_dict": self._model.state_dict()}, path)
 

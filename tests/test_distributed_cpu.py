@@ -44,6 +44,16 @@ def _worker(rank, world, port, F, R):
         a, b, c, d = D.packed_views(buf[r], n)
         assert torch.all(a == r + 0.25) and torch.all(b == r + 0.5) and torch.all(c == r + 0.75)
         assert torch.equal(d, torch.arange(n, dtype=torch.float32) + 1000 * r)
+    # the asynchronous form: this rank's tile at once, the full buffer after wait()
+    pend = D.gather_tiles(local, async_op=True)
+    assert torch.equal(pend.local, local)
+    assert torch.equal(pend.wait(), buf) and torch.equal(pend.wait(), buf)  # wait() is idempotent
+    # one jitter seed for all ranks (rank 0's draw)
+    torch.manual_seed(100 + rank)
+    seed = D.shared_seed("cpu")
+    seeds = [None] * world
+    dist.all_gather_object(seeds, seed)
+    assert len(set(seeds)) == 1
     # balanced contiguous field shards cover [0, F) exactly once
     cover = []
     for r in range(world):
@@ -66,6 +76,26 @@ def test_shard_range_uneven():
     assert [D.shard_range(10, 4, r) for r in range(4)] == [(0, 3), (3, 6), (6, 8), (8, 10)]
     assert D.shard_range(256, 8, 7) == (224, 256)
     assert D.world_info() == (1, 0)
+
+
+def test_leading_slice_only_touches_whole_batch_inputs():
+    """render_rays_sharded / render_rays_split slice per-ray inputs given for the WHOLE batch and pass everything
+    else through (scalars, a shared (4, 4) pose, inputs the caller already sliced)."""
+    from neural_graph_mapping_b200 import distributed as D
+
+    F, R = 6, 10
+    near = torch.arange(F * R, dtype=torch.float32).view(F, R)
+    jit = torch.rand(F, R, 8)
+    c2ws = torch.eye(4).repeat(F, R, 1, 1)
+    sl = slice(2, 4)
+    assert torch.equal(D._leading_slice(near, (F, R), sl), near[2:4])
+    assert torch.equal(D._leading_slice(jit, (F, R), sl), jit[2:4])
+    assert D._leading_slice(c2ws, (F, R), sl).shape == (2, R, 4, 4)
+    assert D._leading_slice(None, (F, R), sl) is None and D._leading_slice(1.5, (F, R), sl) == 1.5
+    pre = jit[2:4]
+    assert D._leading_slice(pre, (F, R), sl) is pre            # already a shard: untouched
+    rays = (slice(None), slice(5, 10))
+    assert torch.equal(D._leading_slice(near, (F, R), rays), near[:, 5:10])
 
 
 def test_owned_fields_partition_targets_exactly_once():

@@ -53,10 +53,28 @@ def _worker(rank, world, port, tmpdir):
             full = st._render_ijs(ijs.to(dev), c2w, cam, fid.to(dev), True, near.to(dev), far.to(dev), jitter=jit.to(dev))
             f0, f1 = D.shard_range(F, world, rank)
             shard = D.render_rays_sharded(st, ijs.to(dev), c2w, cam, fid.to(dev), near.to(dev), far.to(dev),
-                                          jitter=jit[f0:f1].to(dev))
-        for x, y in zip(full[:4], shard[:4]):
-            assert x.shape == y.shape
-            assert torch.equal(x, y), (prec, (x - y).abs().max().item())
+                                          jitter=jit[f0:f1].to(dev))       # pre-sliced jitter
+            shard2 = D.render_rays_sharded(st, ijs.to(dev), c2w, cam, fid.to(dev), near.to(dev), far.to(dev),
+                                           jitter=jit.to(dev))             # whole-batch jitter: sliced by the library
+            split = D.render_rays_split(st, ijs.to(dev), c2w, cam, fid.to(dev), near.to(dev), far.to(dev),
+                                        jitter=jit.to(dev))                # the same batch split by ray
+            seed = D.shared_seed(torch.device(dev))
+            full_s = st._render_ijs(ijs.to(dev), c2w, cam, fid.to(dev), True, near.to(dev), far.to(dev), seed=seed)
+            shard_s = D.render_rays_sharded(st, ijs.to(dev), c2w, cam, fid.to(dev), near.to(dev), far.to(dev), seed=seed)
+            shard_auto = D.render_rays_sharded(st, ijs.to(dev), c2w, cam, fid.to(dev), near.to(dev), far.to(dev))
+        for other in (shard, shard2, split):
+            for x, y in zip(full[:4], other[:4]):
+                assert x.shape == y.shape
+                assert torch.equal(x, y), (prec, (x - y).abs().max().item())
+        for x, y in zip(full_s[:4], shard_s[:4]):  # in-kernel jitter: one seed, global sample indices
+            assert torch.equal(x, y), (prec, "seeded", (x - y).abs().max().item())
+        assert torch.isfinite(shard_auto.rgbds).all()
+        # an asynchronous gather returns this rank's tile at once and the full buffer after wait()
+        pend = D.render_rays_gathered(st, ijs[f0:f1].to(dev), c2w, cam, fid[f0:f1].to(dev), near[f0:f1].to(dev),
+                                      far[f0:f1].to(dev), async_gather=True, jitter=jit[f0:f1].to(dev))
+        buf = pend.wait()
+        torch.cuda.synchronize()
+        assert buf.shape[0] == world and torch.equal(buf[rank], pend.local)
     dist.barrier()
     dist.destroy_process_group()
 

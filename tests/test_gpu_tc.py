@@ -26,7 +26,7 @@ def _gemm(n, k, rows, seed):
     ad, wd, bd = a.to(DEV), w.to(DEV), b.to(DEV)
     out = torch.full((rows, n), float("nan"), device=DEV)
     ws = torch.zeros(256 * 1024, dtype=torch.uint8, device=DEV)
-    rc = _lib.lib.ngm_debug_tc_gemm(wd.data_ptr(), bd.data_ptr(), n, k, ad.data_ptr(), rows, out.data_ptr(),
+    rc = _lib.load_debug_lib().ngm_debug_tc_gemm(wd.data_ptr(), bd.data_ptr(), n, k, ad.data_ptr(), rows, out.data_ptr(),
                                     ws.data_ptr(), ws.numel(), _lib.stream_ptr(torch.device(DEV)))
     _lib.check(rc)
     torch.cuda.synchronize()
@@ -58,7 +58,7 @@ def test_tc_gemm_one_hot_layout():
         ad, wd, bd = a.to(DEV), w.contiguous().to(DEV), b.to(DEV)
         out = torch.empty(rows, n, device=DEV)
         ws = torch.zeros(256 * 1024, dtype=torch.uint8, device=DEV)
-        _lib.check(_lib.lib.ngm_debug_tc_gemm(wd.data_ptr(), bd.data_ptr(), n, k, ad.data_ptr(), rows, out.data_ptr(),
+        _lib.check(_lib.load_debug_lib().ngm_debug_tc_gemm(wd.data_ptr(), bd.data_ptr(), n, k, ad.data_ptr(), rows, out.data_ptr(),
                                               ws.data_ptr(), ws.numel(), _lib.stream_ptr(torch.device(DEV))))
         ref = w.T[torch.arange(rows) % k]  # out[r, n] = W[n, r]
         assert torch.equal(out.cpu(), ref), \
@@ -127,7 +127,11 @@ def test_render_fused_fp16_golden(name):
     dep = (p.rgbds[..., 3].cpu() - a["out_rgbds"][..., 3]).abs()
     assert col.mean().item() < 2e-3, f"colour L1 {col.mean().item():.2e} (max {col.max().item():.2e})"
     assert dep.mean().item() < 5e-3, f"depth L1 {dep.mean().item():.2e} (max {dep.max().item():.2e})"
+    # per-pixel bounds: a single badly wrong pixel must fail, not vanish in the mean
+    assert col.max().item() < 3e-2, f"colour max error {col.max().item():.2e} (mean {col.mean().item():.2e})"
+    assert dep.max().item() < 8e-2, f"depth max error {dep.max().item():.2e} (mean {dep.mean().item():.2e})"
     assert (p.term_probs.cpu() - a["out_term_probs"]).abs().mean().item() < 3e-3
+    assert (p.term_probs.cpu() - a["out_term_probs"]).abs().max().item() < 5e-2
     assert (p.color_vars.cpu() - a["out_color_vars"]).abs().mean().item() < 3e-3
     assert (p.depth_vars.cpu() - a["out_depth_vars"]).abs().mean().item() < 5e-3
     if "out_freespace" in a:
@@ -330,40 +334,6 @@ def test_render_knn_fp16_golden(name):
     assert col.mean().item() < 2e-3, f"colour L1 {col.mean().item():.2e} (max {col.max().item():.2e})"
     assert dep.mean().item() < 5e-3, f"depth L1 {dep.mean().item():.2e} (max {dep.max().item():.2e})"
     assert (p.term_probs.cpu() - a["out_term_probs"]).abs().mean().item() < 3e-3
-
-
-@pytest.mark.parametrize("slots", ["3", "2", "1"])
-def test_three_slot_field_kernel_experiment(slots, monkeypatch):
-    """csrc/field_tc3.cuh (NGM_TC3=1): static round-robin schedule over three tile slots, the third with its A operand
-    in shared memory (SS-mode tcgen05.mma).  Slower than the production kernel (see its header) but kept correct:
-    multi-segment tile ranges, partial last rounds, several fields."""
-    import neural_graph_mapping_b200 as ngm
-
-    monkeypatch.setenv("NGM_TC3", "1")
-    monkeypatch.setenv("NGM_TC3_SLOTS", slots)
-    monkeypatch.setenv("NGM_TC_MAX_CTAS", "3")  # few CTAs: every CTA walks several fields and rounds
-    g = torch.Generator().manual_seed(3)
-    F, n, W, L, O = 7, 128 * 11 + 50, 128, 4, 8
-    spec = R.FieldSpec("nerf", {"dim_in": 3, "num_octaves": O}, L, 4, W, "no")
-    params = R.stack_params([R.init_field_params(spec, g) for _ in range(F)])
-    pos = torch.randn(F, 3, generator=g)
-    q = torch.randn(F, 4, generator=g)
-    ori = q / q.norm(dim=-1, keepdim=True)
-    pts = pos[:, None] + torch.rand(F, n, 3, generator=g) * 1.6 - 0.8
-    rs = R.RenderSpec(field_radius=1.0, scale_mode="unit_cube")
-    ref = R.fieldset_forward_vmap(pts, pos, ori, spec, params, rs)
-    model = ngm.NeuralFieldSet(3, "neural_graph_mapping_b200.models.NeuralField",
-                               {"encoding_type": "neural_graph_mapping_b200.positional_encodings.PositionalEncodingNeRF",
-                                "encoding_kwargs": {"dim_in": 3, "num_octaves": O}, "num_layers": L, "dim_out": 4,
-                                "dim_mlp_out": W}, 2, 10.0, 1.0, field_radius=1.0, scale_mode="unit_cube",
-                               precision="fp16").to(DEV)
-    model.all_fields_params = {k: v.to(DEV) for k, v in params.items()}
-    model.set_vmap_fields(None)
-    with torch.no_grad():
-        y = model(pts.to(DEV), pos.to(DEV), ori.to(DEV), None, True)
-    scale = ref.abs().max().item()
-    e = (y.cpu() - ref).abs()
-    assert e.max().item() < 2e-2 * scale and e.mean().item() < 3e-3 * scale, (e.max().item(), e.mean().item(), scale)
 
 
 @pytest.mark.parametrize("prec", ["fp32", "fp16"])

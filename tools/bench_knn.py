@@ -59,8 +59,8 @@ cfg["eval_near_distance"], cfg["eval_far_distance"], cfg["eval_num_samples"] = 1
 st = ngm.RenderState(cfg)
 st.set_fields(sc["params"], sc["positions"], sc["orientations"])
 st.eval()
-for blk in (0, renderer.IMAGE_BLOCK_PIXELS):
-    renderer.IMAGE_BLOCK_PIXELS = blk
+for blk in (0, renderer.IMAGE_BLOCK_BYTES):  # 0: exactly the reference's 8,192-pixel blocks
+    renderer.IMAGE_BLOCK_BYTES = blk
     ts = []
     for i in range(4):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -70,5 +70,5 @@ for blk in (0, renderer.IMAGE_BLOCK_PIXELS):
         torch.cuda.synchronize()
         if i > 0:
             ts.append(e0.elapsed_time(e1))
-    print(json.dumps({"call": "render_image 640x480, eval samples", "min_block_pixels": blk,
+    print(json.dumps({"call": "render_image 640x480, eval samples", "block_budget_bytes": blk, "block_pixels": renderer.image_block_pixels(st),
                       "ms_per_frame": round(sum(ts) / len(ts), 3)}), flush=True)

@@ -8,6 +8,8 @@ import sys
 
 os.environ["NGM_TC_TRACE"] = "1"
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# the traced twin of the kernel and the ngm_debug_* entry points live in the diagnostics build only
+os.environ.setdefault("NGM_B200_LIB", os.path.join(ROOT, "neural_graph_mapping_b200", "libngm_b200_debug.so"))
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
@@ -26,7 +28,7 @@ with torch.no_grad():
         st._render_ijs(dz["ijs"], dz["c2w"], cam, dz["field_ids"], True, dz["near"], dz["far"])
 torch.cuda.synchronize()
 buf = (C.c_uint64 * 16384)()
-n = _lib.lib.ngm_debug_tc_trace(buf, 16384)
+n = _lib.load_debug_lib().ngm_debug_tc_trace(buf, 16384)
 ev = sorted(((buf[i] & 0xFFFFFFFFFFFF), buf[i] >> 48) for i in range(n))
 print("events", n)
 PH = {0: "FE start", 1: "sample ready (pre-encode)", 2: "A0 stored+arrived", 3: "d_ready (hidden)",
