@@ -145,7 +145,29 @@ typedef struct NgmFieldFwdArgs {
   int32_t num_fields;
   int32_t scale_mode; /* NgmScaleMode */
   int32_t precision;  /* NgmPrecision */
+  /* optional (fp16 path only): the encoding already evaluated by the caller as fp16 rows
+   * (num_fields * points_per_field, EP) with EP = dim_encoding rounded up to 16 and zero padding -- the layer-0
+   * operand of the MLP.  `points` / poses are then not read.  NULL: the library evaluates the encoding. */
+  const void* rows_half;
 } NgmFieldFwdArgs;
+
+/* ---- stage: field evaluation, backward ------------------------------------------------
+ * What torch.autograd derives from NeuralField.forward under vmap (ngm/models.py:143-182, :342) when the
+ * training step calls loss.backward() (ngm/run_mapping.py:1186): given d_out = dLoss/d out of the forward call
+ * `fwd`, the gradients of every `_linears.{i}.weight` / `.bias` of the num_fields evaluated fields, in the layout
+ * of the gathered tables (vmap_fields_params: (num_fields, out, in) / (num_fields, out)).  The forward is
+ * recomputed inside the kernel; nothing is stored by ngm_field_fwd.  precision FP16: tcgen05 (fp16 operands, the
+ * upstream gradient scaled by a per-call power of two, fp32 accumulation); FP32: FFMA kernel, reference arithmetic.
+ * Outputs are overwritten (not accumulated).  d_encoding, when given, receives dLoss/d encoding(x)
+ * (num_fields, points_per_field, dim_encoding) for the gradient of the encoding's own parameters
+ * (ngm_encode_bwd). */
+typedef struct NgmFieldBwdArgs {
+  NgmFieldFwdArgs fwd;   /* the forward call (its `out` is not read); workspace from ngm_field_bwd_workspace_bytes */
+  const float* d_out;    /* (num_fields, points_per_field, dim_out) */
+  float* d_weights[NGM_MAX_LINEARS];
+  float* d_biases[NGM_MAX_LINEARS];
+  float* d_encoding;     /* optional */
+} NgmFieldBwdArgs;
 
 /* ---- stage: compositor ---------------------------------------------------------------
  * Replaces the post-MLP split + masks (ngm/run_mapping.py:610-639) and
@@ -382,13 +404,15 @@ const char* ngm_last_error(void);
 /* sizeof() of the structs above as compiled, so a binding can verify its mirror:
  * which = 0 NgmCamera, 1 NgmFieldDesc, 2 NgmSampleArgs, 3 NgmFieldFwdArgs, 4 NgmCompositeArgs, 5 NgmRenderArgs,
  * 6 NgmKnnFwdArgs, 7 NgmCompositeBwdArgs, 8 NgmEncodeArgs, 9 NgmAdamParam, 10 NgmAdamArgs,
- * 11 NgmTargetVisArgs, 12 NgmTargetRaysArgs, 13 NgmObservedArgs */
+ * 11 NgmTargetVisArgs, 12 NgmTargetRaysArgs, 13 NgmObservedArgs, 14 NgmFieldBwdArgs */
 size_t ngm_struct_size(int which);
 /* number of CUDA kernels this library has launched in this process (bench.py's gpu_launches) */
 uint64_t ngm_launch_count(void);
 
 int ngm_sample_rays(const NgmSampleArgs* args, void* stream);   /* camera.py:215-292, run_mapping.py:521-547 */
 int ngm_field_fwd(const NgmFieldFwdArgs* args, void* stream);   /* models.py:143-182, 329-345 */
+int ngm_field_bwd(const NgmFieldBwdArgs* args, void* stream);   /* autograd of models.py:143-182 under :342 (run_mapping.py:1186) */
+int ngm_field_bwd_workspace_bytes(const NgmFieldBwdArgs* args, size_t* out);
 int ngm_composite(const NgmCompositeArgs* args, void* stream);  /* run_mapping.py:610-639, 709-799 */
 int ngm_composite_bwd(const NgmCompositeBwdArgs* args, void* stream); /* autograd of run_mapping.py:610-639, 709-799 */
 int ngm_encode_fwd(const NgmEncodeArgs* args, void* stream);    /* positional_encodings.py forward()s */

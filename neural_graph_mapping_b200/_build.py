@@ -16,7 +16,7 @@ STAMP = os.path.join(PKG_DIR, ".libngm_b200.stamp")
 DEBUG_LIB_PATH = os.path.join(PKG_DIR, "libngm_b200_debug.so")
 DEBUG_STAMP = os.path.join(PKG_DIR, ".libngm_b200_debug.stamp")
 
-SOURCES = ["abi.cu", "sampler.cu", "composite.cu", "composite_bwd.cu", "encode.cu", "adam.cu", "targets.cu", "field_simt.cu", "field_tc.cu", "knn.cu"]
+SOURCES = ["abi.cu", "sampler.cu", "composite.cu", "composite_bwd.cu", "encode.cu", "adam.cu", "targets.cu", "field_simt.cu", "field_tc.cu", "field_tc_bwd.cu", "knn.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",

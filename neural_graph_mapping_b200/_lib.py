@@ -67,7 +67,14 @@ class NgmFieldFwdArgs(C.Structure):
         ("field", NgmFieldDesc), ("points_per_field", C.c_int64), ("points", _fp), ("positions", _fp),
         ("orientations", _fp), ("field_slots", _fp), ("out", _fp), ("workspace", _fp),
         ("workspace_bytes", C.c_size_t), ("field_radius", C.c_float), ("num_fields", C.c_int32),
-        ("scale_mode", C.c_int32), ("precision", C.c_int32),
+        ("scale_mode", C.c_int32), ("precision", C.c_int32), ("rows_half", _fp),
+    ]
+
+
+class NgmFieldBwdArgs(C.Structure):
+    _fields_ = [
+        ("fwd", NgmFieldFwdArgs), ("d_out", _fp), ("d_weights", _fp * NGM_MAX_LINEARS),
+        ("d_biases", _fp * NGM_MAX_LINEARS), ("d_encoding", _fp),
     ]
 
 
@@ -162,9 +169,9 @@ class NgmKnnFwdArgs(C.Structure):
 
 STRUCTS = [NgmCamera, NgmFieldDesc, NgmSampleArgs, NgmFieldFwdArgs, NgmCompositeArgs, NgmRenderArgs, NgmKnnFwdArgs,
            NgmCompositeBwdArgs, NgmEncodeArgs, NgmAdamParam, NgmAdamArgs,
-           NgmTargetVisArgs, NgmTargetRaysArgs, NgmObservedArgs]
+           NgmTargetVisArgs, NgmTargetRaysArgs, NgmObservedArgs, NgmFieldBwdArgs]
 EXPORTS = [
-    "ngm_abi_version", "ngm_last_error", "ngm_struct_size", "ngm_launch_count", "ngm_sample_rays", "ngm_field_fwd", "ngm_composite", "ngm_composite_bwd", "ngm_encode_fwd", "ngm_encode_bwd", "ngm_adam_step", "ngm_target_visibility", "ngm_target_rays", "ngm_observed_fields",
+    "ngm_abi_version", "ngm_last_error", "ngm_struct_size", "ngm_launch_count", "ngm_sample_rays", "ngm_field_fwd", "ngm_field_bwd", "ngm_field_bwd_workspace_bytes", "ngm_composite", "ngm_composite_bwd", "ngm_encode_fwd", "ngm_encode_bwd", "ngm_adam_step", "ngm_target_visibility", "ngm_target_rays", "ngm_observed_fields",
     "ngm_render_rays_fwd", "ngm_fieldset_knn_fwd", "ngm_fieldset_knn_workspace_bytes", "ngm_field_fwd_workspace_bytes", "ngm_render_workspace_bytes",
 ]
 
@@ -181,6 +188,7 @@ lib.ngm_struct_size.restype = C.c_size_t
 lib.ngm_struct_size.argtypes = [C.c_int]
 lib.ngm_launch_count.restype = C.c_uint64
 for _name, _arg in [("ngm_sample_rays", NgmSampleArgs), ("ngm_field_fwd", NgmFieldFwdArgs),
+                    ("ngm_field_bwd", NgmFieldBwdArgs),
                     ("ngm_composite", NgmCompositeArgs), ("ngm_render_rays_fwd", NgmRenderArgs),
                     ("ngm_fieldset_knn_fwd", NgmKnnFwdArgs), ("ngm_composite_bwd", NgmCompositeBwdArgs),
                     ("ngm_encode_fwd", NgmEncodeArgs), ("ngm_encode_bwd", NgmEncodeArgs), ("ngm_adam_step", NgmAdamArgs),
@@ -190,6 +198,8 @@ for _name, _arg in [("ngm_sample_rays", NgmSampleArgs), ("ngm_field_fwd", NgmFie
     getattr(lib, _name).argtypes = [C.POINTER(_arg), C.c_void_p]
 lib.ngm_fieldset_knn_workspace_bytes.restype = C.c_int
 lib.ngm_fieldset_knn_workspace_bytes.argtypes = [C.POINTER(NgmKnnFwdArgs), C.POINTER(C.c_size_t)]
+lib.ngm_field_bwd_workspace_bytes.restype = C.c_int
+lib.ngm_field_bwd_workspace_bytes.argtypes = [C.POINTER(NgmFieldBwdArgs), C.POINTER(C.c_size_t)]
 lib.ngm_field_fwd_workspace_bytes.restype = C.c_int
 lib.ngm_field_fwd_workspace_bytes.argtypes = [C.POINTER(NgmFieldFwdArgs), C.POINTER(C.c_size_t)]
 lib.ngm_render_workspace_bytes.restype = C.c_int

@@ -11,13 +11,13 @@ grad; evaluation (``torch.no_grad``) keeps the fused tcgen05 kernel.  Stage stru
                         (ngm/positional_encodings.py:245-272, 197-212, 132-161);
                         permutohedral: ``ngm_encode_fwd`` / ``ngm_encode_bwd`` (CUDA, table
                         gradient by atomics)
-* MLP                -- batched library GEMMs (``torch.baddbmm``) over the stacked per-field
-                        parameters, all four skip modes (ngm/models.py:143-182); autograd
-                        derives the weight gradients
+* MLP                -- precision "fp16" (skip mode "no", 1-4 hidden layers of width <= 128):
+                        ``ngm_field_fwd`` / ``ngm_field_bwd`` -- the tcgen05 forward kernel and the
+                        tcgen05 backward kernel (csrc/field_tc_bwd.cu: forward recomputed per tile,
+                        weight gradients accumulated in TMEM, NeRF encoding inside the kernel);
+                        otherwise batched GEMMs over the stacked per-field parameters
+                        (ngm/models.py:143-182, all four skip modes; autograd derives the gradients)
 * compositor         -- ``ngm_composite`` forward, ``ngm_composite_bwd`` backward (CUDA)
-
-The MLP is the one stage still on library GEMMs here; a tcgen05 backward is the next row of
-SURVEY.md 8(f).
 """
 from __future__ import annotations
 
@@ -156,6 +156,123 @@ def field_forward(proto, params: Dict[str, torch.Tensor], local: torch.Tensor) -
 
 
 # ------------------------------------------------------------------------------------------
+# MLP on tcgen05: ngm_field_fwd / ngm_field_bwd
+# ------------------------------------------------------------------------------------------
+def _rows_half(enc: torch.Tensor, ep: int) -> torch.Tensor:
+    """(F, N, E) fp32 features -> (F * N, EP) fp16 rows, zero padded to the K multiple of 16."""
+    F, N, E = enc.shape
+    rows = torch.zeros(F * N, ep, device=enc.device, dtype=torch.float16)
+    rows[:, :E] = enc.reshape(F * N, E)
+    return rows
+
+
+class _FieldTcFn(torch.autograd.Function):
+    """``NeuralField.forward`` of F stacked fields on the tensor cores, differentiable in the linears' weights and
+    biases (and in the encoding output when it is given as rows).  args: the L + 1 weights, then the L + 1 biases."""
+
+    @staticmethod
+    def forward(ctx, proto, geom, points, enc, *wb):
+        nl = proto._num_layers + 1
+        params = {f"_linears.{i}.weight": wb[i].detach() for i in range(nl)}
+        params.update({f"_linears.{i}.bias": wb[nl + i].detach() for i in range(nl)})
+        params.update(geom["enc_params"])
+        dev = points.device
+        F, N = points.shape[0], points.shape[1]
+        a = _lib.NgmFieldFwdArgs()
+        with torch.cuda.device(dev):
+            a.field, keep = proto.field_desc(params, True)
+            out = torch.empty(F, N, proto._dim_out, device=dev)
+            a.points_per_field, a.num_fields = N, F
+            pts = _lib.dev_f32(points, "points")
+            a.points = pts.data_ptr()
+            if geom["positions"] is not None:
+                a.positions, a.orientations = geom["positions"].data_ptr(), geom["orientations"].data_ptr()
+            a.out = out.data_ptr()
+            a.scale_mode = _lib.SCALE[geom["scale_mode"]]
+            a.field_radius = float(geom["field_radius"] or 0.0)
+            a.precision = _lib.PREC["fp16"]
+            rows = None
+            if enc is not None:
+                rows = _rows_half(enc.detach(), (proto._dim_encoding + 15) // 16 * 16)
+                a.rows_half = rows.data_ptr()
+            need = C.c_size_t(0)
+            _lib.check(_lib.lib.ngm_field_fwd_workspace_bytes(C.byref(a), C.byref(need)))
+            ws = torch.empty(max(need.value, 16), device=dev, dtype=torch.uint8)
+            a.workspace, a.workspace_bytes = ws.data_ptr(), need.value
+            _lib.check(_lib.lib.ngm_field_fwd(C.byref(a), _lib.stream_ptr(dev)))
+        ctx.proto, ctx.geom, ctx.nl = proto, geom, nl
+        ctx.enc_grad = enc is not None and enc.requires_grad
+        ctx.enc_shape = None if enc is None else tuple(enc.shape)
+        ctx.save_for_backward(pts, rows, *[t.detach() for t in wb])
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        pts, rows, *wb = ctx.saved_tensors
+        proto, geom, nl = ctx.proto, ctx.geom, ctx.nl
+        params = {f"_linears.{i}.weight": wb[i] for i in range(nl)}
+        params.update({f"_linears.{i}.bias": wb[nl + i] for i in range(nl)})
+        params.update(geom["enc_params"])
+        dev = pts.device
+        F, N = pts.shape[0], pts.shape[1]
+        b = _lib.NgmFieldBwdArgs()
+        with torch.cuda.device(dev):
+            b.fwd.field, keep = proto.field_desc(params, True)
+            b.fwd.points_per_field, b.fwd.num_fields = N, F
+            b.fwd.points = pts.data_ptr()
+            if geom["positions"] is not None:
+                b.fwd.positions, b.fwd.orientations = geom["positions"].data_ptr(), geom["orientations"].data_ptr()
+            b.fwd.scale_mode = _lib.SCALE[geom["scale_mode"]]
+            b.fwd.field_radius = float(geom["field_radius"] or 0.0)
+            b.fwd.precision = _lib.PREC["fp16"]
+            if rows is not None:
+                b.fwd.rows_half = rows.data_ptr()
+            g = _lib.dev_f32(g_out, "d_out")
+            b.d_out = g.data_ptr()
+            grads = [torch.empty_like(t) for t in wb]
+            for i in range(nl):
+                b.d_weights[i], b.d_biases[i] = grads[i].data_ptr(), grads[nl + i].data_ptr()
+            d_enc = None
+            if ctx.enc_grad:
+                d_enc = torch.empty(ctx.enc_shape, device=dev)
+                b.d_encoding = d_enc.data_ptr()
+            need = C.c_size_t(0)
+            _lib.check(_lib.lib.ngm_field_bwd_workspace_bytes(C.byref(b), C.byref(need)))
+            ws = torch.empty(max(need.value, 16), device=dev, dtype=torch.uint8)
+            b.fwd.workspace, b.fwd.workspace_bytes = ws.data_ptr(), need.value
+            _lib.check(_lib.lib.ngm_field_bwd(C.byref(b), _lib.stream_ptr(dev)))
+        return (None, None, None, d_enc, *grads)
+
+
+def tc_training_supported(proto) -> bool:
+    """Shapes the tcgen05 backward handles (csrc/field_tc_bwd.cu: field_bwd_tc_supported)."""
+    w = proto._dim_mlp_out
+    return (proto._skip_mode == "no" and 1 <= proto._num_layers <= 4 and w % 32 == 0 and 32 <= w <= 128
+            and proto._dim_out <= 8 and proto._dim_encoding <= 64)
+
+
+def field_forward_tc(proto, params: Dict[str, torch.Tensor], points_world: torch.Tensor, positions, orientations,
+                     scale_mode: str, field_radius) -> torch.Tensor:
+    """(F, N, 3) WORLD points -> (F, N, dim_out) through the tcgen05 kernels; differentiable in ``params``.
+    NeRF encodings are evaluated inside the kernels; the permutohedral encoding through ``ngm_encode_fwd`` /
+    ``ngm_encode_bwd`` and Fourier / Triplane through their PyTorch expressions, handed over as fp16 rows."""
+    enc = None
+    kind = proto._encoding.KIND
+    enc_params = {k: v.detach() for k, v in params.items() if k.startswith("_encoding.")}
+    pos = None if positions is None else _lib.dev_f32(positions, "positions")
+    ori = None if orientations is None else _lib.dev_f32(orientations, "orientations")
+    if kind != "nerf":
+        with torch.no_grad():
+            local = world_to_local(points_world, pos, ori, scale_mode, field_radius) if pos is not None else points_world
+        enc = encode(proto, params, local)
+    geom = dict(positions=pos, orientations=ori, scale_mode=scale_mode, field_radius=field_radius,
+                enc_params=enc_params)
+    nl = proto._num_layers + 1
+    wb = [params[f"_linears.{i}.weight"] for i in range(nl)] + [params[f"_linears.{i}.bias"] for i in range(nl)]
+    return _FieldTcFn.apply(proto, geom, points_world, enc, *wb)
+
+
+# ------------------------------------------------------------------------------------------
 # compositor
 # ------------------------------------------------------------------------------------------
 class _CompositeFn(torch.autograd.Function):
@@ -264,9 +381,15 @@ def render_rays_vmap(driver, camera, ijs, c2ws, params, positions, orientations,
             far if far is not None else float(driver._far_distance), gt=gt, num_samples_guided=G,
             range_guided=float(driver._range_depth_guided or 0.0), c2ws=c2ws, jitter=jitter, jitter_guided=jitter_guided,
             seed=seed, offset=sample_offset, want_world=True, want_depth=True, want_cam=False)
-        local = world_to_local(world.view(F, R * St, 3), _lib.dev_f32(positions, "positions"),
-                               _lib.dev_f32(orientations, "orientations"), model._scale_mode, model._field_radius)
-    outs = field_forward(proto, params, local)  # (F, R*St, 4), differentiable in params (fp32 whatever `precision`)
+    if precision == "fp16" and tc_training_supported(proto):
+        # tensor-core training path: tcgen05 forward + tcgen05 backward (weight gradients accumulated in TMEM)
+        outs = field_forward_tc(proto, params, world.view(F, R * St, 3), positions, orientations, model._scale_mode,
+                                model._field_radius)
+    else:
+        with torch.no_grad():
+            local = world_to_local(world.view(F, R * St, 3), _lib.dev_f32(positions, "positions"),
+                                   _lib.dev_f32(orientations, "orientations"), model._scale_mode, model._field_radius)
+        outs = field_forward(proto, params, local)  # (F, R*St, 4), differentiable in params, fp32 arithmetic
     mode = driver._geometry_mode
     isd = None
     if mode == "neus":

@@ -43,6 +43,9 @@ size_t field_tc_workspace_bytes(const NgmFieldDesc& fd, int num_fields);
 size_t field_tc_fwd_workspace_bytes(const NgmFieldFwdArgs& a);
 bool tc_rows_required(const NgmFieldDesc& fd);
 int launch_field_fwd_tc(const NgmFieldFwdArgs& a, cudaStream_t stream);
+bool field_bwd_tc_supported(const NgmFieldDesc& fd, const char** why);
+size_t field_bwd_tc_workspace_bytes(const NgmFieldBwdArgs& b);
+int launch_field_bwd_tc(const NgmFieldBwdArgs& b, cudaStream_t stream);
 bool render_fused_tc_ok(const NgmRenderArgs& a);
 int launch_render_fused_tc(const NgmRenderArgs& a, void* tc_ws, float* isd_ws, const void* rows_half, const float* dist,
                            const float* depth, cudaStream_t stream);
@@ -169,6 +172,7 @@ size_t ngm_struct_size(int which) {
     case 11: return sizeof(NgmTargetVisArgs);
     case 12: return sizeof(NgmTargetRaysArgs);
     case 13: return sizeof(NgmObservedArgs);
+    case 14: return sizeof(NgmFieldBwdArgs);
     default: return 0;
   }
 }
@@ -211,6 +215,41 @@ int ngm_field_fwd(const NgmFieldFwdArgs* a, void* stream) {
   }
   NGM_CHECK_ARG(a->precision == NGM_PREC_FP32, "unknown precision %d", a->precision);
   return launch_field_fwd_simt(*a, (cudaStream_t)stream);
+}
+
+static int validate_field_bwd(const NgmFieldBwdArgs* b) {
+  NGM_CHECK_ARG(b != nullptr, "null args");
+  const NgmFieldFwdArgs* a = &b->fwd;
+  if (int rc = validate_field(a->field)) return rc;
+  NGM_CHECK_ARG(a->num_fields >= 0 && a->points_per_field >= 0, "negative sizes");
+  NGM_CHECK_ARG((a->positions == nullptr) == (a->orientations == nullptr),
+                "positions and orientations must be given together");
+  NGM_CHECK_ARG(a->scale_mode >= NGM_SCALE_NO && a->scale_mode <= NGM_SCALE_UNIT_CUBE, "scale_mode=%d is not available.",
+                a->scale_mode);
+  return NGM_OK;
+}
+
+int ngm_field_bwd_workspace_bytes(const NgmFieldBwdArgs* b, size_t* out) {
+  NGM_CHECK_ARG(b && out, "null args");
+  NGM_UNSUPPORTED(b->fwd.precision != NGM_PREC_FP16, "ngm_field_bwd: only the fp16 tensor-core path is built");
+  *out = field_bwd_tc_workspace_bytes(*b);
+  return NGM_OK;
+}
+
+int ngm_field_bwd(const NgmFieldBwdArgs* b, void* stream) {
+  if (int rc = validate_field_bwd(b)) return rc;
+  const NgmFieldFwdArgs* a = &b->fwd;
+  if (a->num_fields == 0) return NGM_OK;
+  NGM_CHECK_ARG((a->points || a->rows_half) && b->d_out, "points / d_out missing");
+  NGM_UNSUPPORTED(a->precision != NGM_PREC_FP16, "ngm_field_bwd: only the fp16 tensor-core path is built");
+  const char* why = nullptr;
+  NGM_UNSUPPORTED(!field_bwd_tc_supported(a->field, &why), "fp16 tensor-core backward unsupported: %s", why);
+  const size_t need = field_bwd_tc_workspace_bytes(*b);
+  if (need > a->workspace_bytes || !a->workspace) {
+    set_error("workspace too small: need %zu B, have %zu B", need, a->workspace_bytes);
+    return NGM_ERR_WORKSPACE;
+  }
+  return launch_field_bwd_tc(*b, (cudaStream_t)stream);
 }
 
 int ngm_composite(const NgmCompositeArgs* a, void* stream) {

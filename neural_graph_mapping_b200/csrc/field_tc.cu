@@ -27,6 +27,7 @@
 #include "common.cuh"
 #include "encodings.cuh"
 #include "tc_ptx.cuh"
+#include "field_tc_common.cuh"
 
 namespace ngm {
 
@@ -38,87 +39,6 @@ constexpr int kTmemCols = 512;
 constexpr int kSlotCols = 256;
 constexpr int kACol = 128;
 constexpr int kStageCol = 192;  // layer-0 A operand of the slot's NEXT tile (<= 32 columns: K <= 64)
-constexpr uint32_t kMaxImageBytes = 200 * 1024;
-
-struct TcLayer {
-  int n_pad, k_pad, atoms;
-  uint32_t off;  // byte offset of the layer's B image inside the field image
-};
-
-struct TcImage {
-  int num_linears;
-  TcLayer layer[NGM_MAX_LINEARS];
-  uint32_t bias_h2_off;    // uint32 half2 biases of the hidden layers: [L][W/2]
-  uint32_t bias_last_off;  // fp32 biases of the last layer: [n_last_pad]
-  uint32_t total_bytes;    // multiple of 16
-};
-
-TcImage make_image(const NgmFieldDesc& fd, int EP) {
-  TcImage im{};
-  const int L = fd.num_layers, W = fd.dim_mlp_out;
-  im.num_linears = L + 1;
-  uint32_t off = 0;
-  for (int l = 0; l <= L; ++l) {
-    TcLayer& y = im.layer[l];
-    y.n_pad = l == L ? (fd.dim_out + 15) / 16 * 16 : W;
-    y.k_pad = l == 0 ? EP : W;
-    y.atoms = (y.k_pad + 63) / 64;
-    y.off = off;
-    off += (uint32_t)y.atoms * y.n_pad * 128;
-  }
-  im.bias_h2_off = off;
-  off += (uint32_t)L * (W / 2) * 4;
-  off = (off + 15) / 16 * 16;
-  im.bias_last_off = off;
-  off += (uint32_t)im.layer[L].n_pad * 4;
-  im.total_bytes = (off + 15) / 16 * 16;
-  return im;
-}
-
-// ---- weight packing: fp32 (out,in) tables -> per-field fp16 image in the UMMA K-major SWIZZLE_128B layout ----
-struct PackParams {
-  NgmFieldDesc fd;
-  TcImage im;
-  const long long* field_slots;
-  uint8_t* images;
-  int E;
-};
-
-__global__ void __launch_bounds__(256) pack_weights_kernel(PackParams p) {
-  const int f = blockIdx.x;
-  const long long slot = p.field_slots ? p.field_slots[f] : f;
-  uint8_t* img = p.images + (size_t)f * p.im.total_bytes;
-  const int L = p.fd.num_layers, W = p.fd.dim_mlp_out;
-  for (int l = 0; l <= L; ++l) {
-    const TcLayer y = p.im.layer[l];
-    const int N = l == L ? p.fd.dim_out : W;
-    const int K = l == 0 ? p.E : W;
-    const float* Wg = p.fd.weights[l] + slot * p.fd.weight_stride[l];
-    const int chunks = y.atoms * y.n_pad * 8;  // 16-byte chunks (8 halves)
-    for (int c = threadIdx.x; c < chunks; c += blockDim.x) {
-      const int atom = c / (y.n_pad * 8);
-      const int n = (c / 8) % y.n_pad;
-      const int ck = c % 8;
-      __half h[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int k = atom * 64 + ck * 8 + i;
-        h[i] = __float2half_rn((n < N && k < K) ? __ldg(Wg + (size_t)n * K + k) : 0.0f);
-      }
-      uint8_t* dst = img + y.off + (size_t)atom * y.n_pad * 128 + (size_t)n * 128 + ((ck ^ (n & 7)) * 16);
-      *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(h);
-    }
-  }
-  uint32_t* bh = reinterpret_cast<uint32_t*>(img + p.im.bias_h2_off);
-  for (int l = 0; l < L; ++l) {
-    const float* Bg = p.fd.biases[l] + slot * p.fd.bias_stride[l];
-    for (int j = threadIdx.x; j < W / 2; j += blockDim.x)
-      bh[l * (W / 2) + j] = ptx::pack_half2(__ldg(Bg + 2 * j), __ldg(Bg + 2 * j + 1));
-  }
-  float* bl = reinterpret_cast<float*>(img + p.im.bias_last_off);
-  const float* Bg = p.fd.biases[L] + slot * p.fd.bias_stride[L];
-  for (int j = threadIdx.x; j < p.im.layer[L].n_pad; j += blockDim.x) bl[j] = j < p.fd.dim_out ? __ldg(Bg + j) : 0.0f;
-}
 
 // ---- main kernel ---------------------------------------------------------------------------------
 struct TcParams {
@@ -205,49 +125,6 @@ struct Smem {
 };
 
 __device__ __forceinline__ float fast_sigmoid(float x) { return __frcp_rn(1.0f + __expf(-x)); }
-
-// sin(pi t), cos(pi t) with exact range reduction to [-1, 1], MUFU evaluation
-__device__ __forceinline__ void sincospi_fast(float t, float& s, float& c) {
-  const float r = fmaf(-2.0f, rintf(0.5f * t), t);
-  const float a = 3.14159265358979f * r;
-  s = __sinf(a);
-  c = __cosf(a);
-}
-
-// NeRF features of one row -> fp16 -> TMEM A operand (one thread per row).  Octaves 0 and 4 are
-// evaluated directly (exact range reduction + MUFU), the others by the double-angle recurrence: the
-// error at most doubles per octave, 3 steps -> < 1e-5, far below fp16 resolution.
-template <int OCT>
-__device__ __forceinline__ void encode_nerf_to_tmem(uint32_t a_addr, float3 x, int start_octave) {
-  constexpr int E = 6 * OCT;
-  constexpr int EP = (E + 15) / 16 * 16;
-  const float base = exp2f((float)start_octave);
-  const float xs[3] = {x.x, x.y, x.z};
-  float fe[EP];
-#pragma unroll
-  for (int i = E; i < EP; ++i) fe[i] = 0.0f;
-#pragma unroll
-  for (int d = 0; d < 3; ++d) {
-    const float t0 = xs[d] * base;
-    float s = 0.f, c = 1.f;
-#pragma unroll
-    for (int o = 0; o < OCT; ++o) {
-      if (o % 4 == 0) {
-        sincospi_fast(t0 * (float)(1 << o), s, c);
-      } else {
-        const float s2 = 2.0f * s * c;
-        c = fmaf(-2.0f * s, s, 1.0f);
-        s = s2;
-      }
-      fe[d * OCT + o] = s;
-      fe[3 * OCT + d * OCT + o] = c;
-    }
-  }
-  uint32_t w[EP / 2];
-#pragma unroll
-  for (int j = 0; j < EP / 2; ++j) w[j] = ptx::pack_half2(fe[2 * j], fe[2 * j + 1]);
-  ptx::tmem_store_n<EP / 2>(a_addr, w);
-}
 
 // Permutohedral features (2 per level) of lattice levels [l0, l1) of one row -> fp16 -> TMEM A-operand words
 // [l0, l1) (one word per level).  The table stays in global memory (L2-resident: 512 KB per field).
@@ -971,8 +848,6 @@ __global__ void __launch_bounds__(threads_of(MODE), 1) tc_kernel(const TcParams 
   tev.dump();
 }
 
-int nerf_octaves_supported(int o) { return o == 4 || o == 8; }
-
 // one persistent CTA per SM; NGM_TC_MAX_CTAS (tests) caps the grid so that small problems exercise the
 // multi-round / multi-segment paths of a CTA
 int tc_grid(long long total_tiles) {
@@ -1019,8 +894,6 @@ int launch_tc(const TcParams& p_in, int octaves, size_t smem, int grid, cudaStre
     default: set_error("tcgen05 path: unsupported num_octaves %d", octaves); return NGM_ERR_UNSUPPORTED;
   }
 }
-
-int ep_of(const NgmFieldDesc& fd) { return (fd.dim_encoding + 15) / 16 * 16; }
 
 // kernel variant: 4 / 8 = NeRF front end in the kernel; 0 = permutohedral front end or pre-encoded rows
 int tc_oct(const NgmFieldDesc& fd) {
@@ -1095,10 +968,22 @@ size_t field_tc_workspace_bytes(const NgmFieldDesc& fd, int num_fields) {
   return (size_t)make_image(fd, ep_of(fd)).total_bytes * (size_t)(num_fields > 0 ? num_fields : 1);
 }
 
-// dense field evaluation: weight images, then (for encodings without an in-kernel front end) one fp16 row per point
+// Dense field evaluation reads its layer-0 operand as fp16 rows when the caller supplies them, when the encoding has
+// no in-kernel front end, and for the permutohedral encoding (its 64 table gathers per point run ~2x faster from a
+// whole-GPU row encoder than from the 8 front-end warps of the persistent MMA kernel; NGM_TC_PERMUTO_INKERNEL=1
+// keeps the in-kernel front end).
+static bool fwd_rows_from_encoder(const NgmFieldFwdArgs& a) {
+  if (a.rows_half) return false;
+  if (tc_rows_required(a.field)) return true;
+  const char* e = getenv("NGM_TC_PERMUTO_INKERNEL");
+  return a.field.encoding == NGM_ENC_PERMUTO && !(e && e[0] == '1') &&
+         (long long)a.num_fields * a.points_per_field < (1ll << 31);
+}
+
+// workspace: weight images, then (when the library encodes the rows itself) one fp16 row per point
 size_t field_tc_fwd_workspace_bytes(const NgmFieldFwdArgs& a) {
   size_t n = (field_tc_workspace_bytes(a.field, a.num_fields) + 255) / 256 * 256;
-  if (tc_rows_required(a.field)) n += (size_t)a.num_fields * (size_t)a.points_per_field * (size_t)ep_of(a.field) * 2;
+  if (fwd_rows_from_encoder(a)) n += (size_t)a.num_fields * (size_t)a.points_per_field * (size_t)ep_of(a.field) * 2;
   return n;
 }
 
@@ -1114,7 +999,9 @@ int launch_field_fwd_tc(const NgmFieldFwdArgs& a, cudaStream_t stream) {
   p.out = a.out;
   p.tiles_per_field = (a.points_per_field + 127) / 128;
   p.total_tiles = p.tiles_per_field * a.num_fields;
-  if (tc_rows_required(a.field)) {
+  if (a.rows_half) {
+    p.raw_a = static_cast<const __half*>(a.rows_half);
+  } else if (fwd_rows_from_encoder(a)) {
     PermutoRowsArgs e{};
     e.field = a.field;
     e.points_world = a.points;
@@ -1131,7 +1018,7 @@ int launch_field_fwd_tc(const NgmFieldFwdArgs& a, cudaStream_t stream) {
     p.raw_a = reinterpret_cast<const __half*>(e.out);
   }
   const int grid = tc_grid(p.total_tiles);
-  return launch_tc<1>(p, tc_oct(a.field), tc_smem_bytes(p.im), grid, stream);
+  return launch_tc<1>(p, p.raw_a ? 0 : tc_oct(a.field), tc_smem_bytes(p.im), grid, stream);
 }
 
 // kNN path: every tile is 128 (point, neighbour) entries of ONE field; the tile count lives in tile_offsets[F]

@@ -167,6 +167,16 @@ __device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uin
       ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// D[tmem] (+)= A[smem desc] * B[smem desc]   (kind::f16), one thread issues
+__device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // arrive on an mbarrier when all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -180,6 +190,30 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int n) {
          | (0u << 15) | (0u << 16)      // a_major = b_major = K
          | ((uint32_t)(n >> 3) << 17)   // n_dim
          | ((uint32_t)(128 >> 4) << 24);  // m_dim
+}
+
+// general instruction descriptor, kind::f16: fp16 operands, fp32 accumulate; a_mn / b_mn = 1 selects an MN-major
+// (transposed) shared-memory operand (cute/arch/mma_sm100_desc.hpp InstrDescriptor: a_major bit 15, b_major bit 16)
+__host__ __device__ constexpr uint32_t make_idesc_f16_mn(int m, int n, int a_mn, int b_mn) {
+  return (1u << 4) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(m >> 4) << 24);
+}
+
+// SWIZZLE_128B shared-memory descriptor with explicit leading / stride byte offsets.
+//   K-major operand : rows of 128 B (64 halves of K), 8-row groups `sbo` bytes apart (lbo unused)
+//   MN-major operand: rows of 128 B hold 64 consecutive MN elements of ONE k index; 8 k rows form a 1024-B group,
+//                     groups `sbo` bytes apart, the next 64 MN elements `lbo` bytes apart
+//                     (canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units, cute/atom/mma_traits_sm100.hpp)
+// The same [row][128 B] swizzled tile is therefore readable as K-major (K = its 64 columns) and as MN-major
+// (MN = its 64 columns, K = its rows).
+__device__ __forceinline__ uint64_t make_smem_desc_sw128_ex(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
 }
 
 // shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart
@@ -265,6 +299,25 @@ __device__ __forceinline__ void tmem_store_n(uint32_t addr, const uint32_t* r) {
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
+}
+// x + bias on packed half2 (no activation: the sign bits are the ReLU mask)
+__device__ __forceinline__ uint32_t bias_half2(uint32_t x, uint32_t bias) {
+  uint32_t d;
+  const uint32_t one = 0x3C003C00u;
+  asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(x), "r"(one), "r"(bias));
+  return d;
+}
+__device__ __forceinline__ uint32_t relu_half2(uint32_t x) {
+  uint32_t d;
+  const uint32_t zero = 0u;
+  asm("max.f16x2 %0, %1, %2;" : "=r"(d) : "r"(x), "r"(zero));
+  return d;
+}
+// 0xFFFF in every 16-bit half of x whose sign bit is set, 0 elsewhere (byte permute with sign replication)
+__device__ __forceinline__ uint32_t sign_mask_half2(uint32_t x) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(x), "r"(0u), "r"(0xBB99u));
+  return d;
 }
 // relu(x + bias) on packed half2
 __device__ __forceinline__ uint32_t bias_relu_half2(uint32_t x, uint32_t bias) {

@@ -28,20 +28,13 @@ Prediction = namedtuple(
 )
 
 
-_SEED_POOL: list = []
-_SEED_EPOCH = None
+_SEED_BOX = torch.empty((), dtype=torch.int64)
 
 
 def _next_seed() -> int:
-    """Philox seed for in-kernel jitter, drawn from torch's CPU generator (so torch.manual_seed makes renders
-    reproducible, like the reference's torch.rand).  Seeds are drawn 256 at a time -- one torch call per 256
-    renders instead of one per render -- and the pool is dropped when the generator is re-seeded."""
-    global _SEED_EPOCH
-    epoch = torch.initial_seed()
-    if not _SEED_POOL or epoch != _SEED_EPOCH:
-        _SEED_EPOCH = epoch
-        _SEED_POOL[:] = torch.randint(0, 2**62, (256,), dtype=torch.int64).tolist()[::-1]
-    return _SEED_POOL.pop()
+    """Seed of the in-kernel jitter stream, drawn from torch's CPU generator (so torch.manual_seed makes renders
+    reproducible, like the reference's torch.rand): one in-place draw into a preallocated CPU scalar, no device work."""
+    return int(_SEED_BOX.random_(0, 2**62))
 
 
 _WORKSPACES: dict = {}

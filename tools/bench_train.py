@@ -71,9 +71,10 @@ def run_cpu(F, R, S, G):
 for name, (F, R, S, G) in {"default training batch (32 x 512 x 8+16)": (32, 512, 8, 16),
                            "config-4 shard (32 x 4096 x 64)": (32, 4096, 64, 0)}.items():
     row = {"shape": name, "rays": F * R, "points": F * R * (S + G)}
-    ms = run(F, R, S, G, "fp32")
-    row["gpu_ms"] = round(ms, 3)
-    row["gpu_rays_per_s"] = round(F * R / ms * 1e3)
+    for prec in ("fp16", "fp32"):  # fp16: tcgen05 forward + tcgen05 backward; fp32: reference arithmetic
+        ms = run(F, R, S, G, prec)
+        row[f"gpu_{prec}_ms"] = round(ms, 3)
+        row[f"gpu_{prec}_rays_per_s"] = round(F * R / ms * 1e3)
     if F * R * (S + G) <= 500000:
         torch.set_num_threads(os.cpu_count() or 1)
         row["cpu_oracle_ms"] = round(min(run_cpu(F, R, S, G) for _ in range(2)), 1)
