@@ -370,7 +370,8 @@ def main():
     tile_floats = distributed.FLOATS_PER_RAY * rays_per_step
 
     # ---- multi-GPU parity inside the bench (runs under torch.distributed.run on the multi-GPU box) ----
-    parity = multi_gpu_parity(st, cam, dev, world, rank, precision) if world > 1 else None
+    # (on a scene that is the same on every rank: the timed scenes below differ per rank)
+    parity = multi_gpu_parity(make_state(precision, synthetic_scene(4321)), cam, dev, world, rank, precision) if world > 1 else None
 
     # ---- device-timed step, inputs resident: render + all-gather of the rendered tiles ----
     # The all-gather of step i is left in flight (NCCL's own stream) and overlaps step i+1's render; its buffers are
@@ -624,6 +625,24 @@ def run_extras(ngm, distributed, make_state, cam, dev, world, rank, precision, f
                                  "forward render of the batch (the training step's fwd+bwd is `train`)",
                      "value": n4 / (ms / 1e3), "unit": "rays/s", "ms_per_step": ms, "n_gpus": world, "scaling": "strong",
                      "rays_per_step": n4, "steps": steps}
+    # ---- the training step on the C4 batch: fields sharded over the GPUs, NO collective (a field's gradient is local) ----
+    if C4_FIELDS % world == 0 and precision == "fp16":
+        f0, f1 = distributed.shard_range(C4_FIELDS, world, rank)
+        st4._reference_flow = True  # the driver's flow: _render_ijs gathers the active fields into leaves (:500)
+        sl = {k: d4[k][f0:f1].contiguous() for k in ("ijs", "c2ws", "near", "far", "field_ids")}
+
+        def step_train():
+            p = st4._render_ijs(sl["ijs"], sl["c2ws"], cam, sl["field_ids"], True, sl["near"], sl["far"])
+            loss = p.rgbds.square().mean() + p.depth_vars.mean() + p.term_probs.mean()
+            st4._update_step({"combined": loss}, sl["field_ids"])
+
+        tsteps = max(3, steps // 4)
+        ms = timed(step_train, tsteps, 2) / tsteps
+        out["train_c4"] = {"workload": "configs[3] training step: render under autograd (tcgen05 forward) -> loss -> backward "
+                                       "(tcgen05 MLP backward, compositor backward) -> Adam on the rank's own fields; "
+                                       f"{C4_FIELDS // world} fields x {C4_RAYS} rays x {S} samples per GPU, no collective",
+                           "value": n4 / (ms / 1e3), "unit": "rays/s", "ms_per_step": ms, "n_gpus": world, "scaling": "strong",
+                           "rays_per_step": n4, "steps": tsteps}
     del st4, d4, c4
     # ---- strong scaling of the headline keyframe ----
     if world > 1 and R_RAYS % world == 0:

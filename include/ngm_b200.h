@@ -98,6 +98,11 @@ typedef struct NgmFieldDesc {
   int64_t enc_param1_stride;
   /* permuto: per-level, per-axis scale factors (levels,3), shared by all fields */
   const float* permuto_scale;
+  /* optional (fp16 path): persistent pre-swizzled fp16 weight images of the table rows, written by
+   * ngm_pack_weights and indexed like the tables (image of row r at packed_weights + r * ngm_packed_weights_bytes).
+   * When non-NULL the tensor-core kernels read these instead of re-packing the active rows on every call; the
+   * caller re-packs the rows it changes (e.g. the rows an Adam step touched). */
+  const void* packed_weights;
 } NgmFieldDesc;
 
 /* ---- stage: ray sampler --------------------------------------------------------------
@@ -426,6 +431,11 @@ int ngm_fieldset_knn_fwd(const NgmKnnFwdArgs* args, void* stream); /* models.py:
 int ngm_fieldset_knn_workspace_bytes(const NgmKnnFwdArgs* args, size_t* out);
 
 int ngm_field_fwd_workspace_bytes(const NgmFieldFwdArgs* args, size_t* out);
+/* persistent kernel-friendly layout of the stacked per-field linears (the tables of
+ * models.py:254-264 stay the source of truth): bytes of one row's image, and packing of `num_rows` table rows
+ * `rows[i]` (NULL: 0..num_rows-1) into images + rows[i] * bytes. */
+int ngm_packed_weights_bytes(const NgmFieldDesc* field, size_t* bytes_per_row);
+int ngm_pack_weights(const NgmFieldDesc* field, const int64_t* rows, int32_t num_rows, void* images, void* stream);
 int ngm_render_workspace_bytes(const NgmRenderArgs* args, size_t* out);
 
 #ifdef __cplusplus

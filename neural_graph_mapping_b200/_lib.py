@@ -48,7 +48,7 @@ class NgmFieldDesc(C.Structure):
         ("rezero", _fp), ("rezero_stride", C.c_int64),
         ("enc_param0", _fp), ("enc_param0_stride", C.c_int64),
         ("enc_param1", _fp), ("enc_param1_stride", C.c_int64),
-        ("permuto_scale", _fp),
+        ("permuto_scale", _fp), ("packed_weights", _fp),
     ]
 
 
@@ -172,7 +172,7 @@ STRUCTS = [NgmCamera, NgmFieldDesc, NgmSampleArgs, NgmFieldFwdArgs, NgmComposite
            NgmTargetVisArgs, NgmTargetRaysArgs, NgmObservedArgs, NgmFieldBwdArgs]
 EXPORTS = [
     "ngm_abi_version", "ngm_last_error", "ngm_struct_size", "ngm_launch_count", "ngm_sample_rays", "ngm_field_fwd", "ngm_field_bwd", "ngm_field_bwd_workspace_bytes", "ngm_composite", "ngm_composite_bwd", "ngm_encode_fwd", "ngm_encode_bwd", "ngm_adam_step", "ngm_target_visibility", "ngm_target_rays", "ngm_observed_fields",
-    "ngm_render_rays_fwd", "ngm_fieldset_knn_fwd", "ngm_fieldset_knn_workspace_bytes", "ngm_field_fwd_workspace_bytes", "ngm_render_workspace_bytes",
+    "ngm_render_rays_fwd", "ngm_fieldset_knn_fwd", "ngm_fieldset_knn_workspace_bytes", "ngm_field_fwd_workspace_bytes", "ngm_render_workspace_bytes", "ngm_packed_weights_bytes", "ngm_pack_weights",
 ]
 
 if not os.path.exists(LIB_PATH):
@@ -200,6 +200,10 @@ lib.ngm_fieldset_knn_workspace_bytes.restype = C.c_int
 lib.ngm_fieldset_knn_workspace_bytes.argtypes = [C.POINTER(NgmKnnFwdArgs), C.POINTER(C.c_size_t)]
 lib.ngm_field_bwd_workspace_bytes.restype = C.c_int
 lib.ngm_field_bwd_workspace_bytes.argtypes = [C.POINTER(NgmFieldBwdArgs), C.POINTER(C.c_size_t)]
+lib.ngm_packed_weights_bytes.restype = C.c_int
+lib.ngm_packed_weights_bytes.argtypes = [C.POINTER(NgmFieldDesc), C.POINTER(C.c_size_t)]
+lib.ngm_pack_weights.restype = C.c_int
+lib.ngm_pack_weights.argtypes = [C.POINTER(NgmFieldDesc), C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
 lib.ngm_field_fwd_workspace_bytes.restype = C.c_int
 lib.ngm_field_fwd_workspace_bytes.argtypes = [C.POINTER(NgmFieldFwdArgs), C.POINTER(C.c_size_t)]
 lib.ngm_render_workspace_bytes.restype = C.c_int

@@ -404,6 +404,8 @@ def render_rays_vmap(driver, camera, ijs, c2ws, params, positions, orientations,
     gt_flat = None if gt is None else _lib.dev_f32(gt, "gt_distances").expand(F, R).reshape(-1).contiguous()
     rgbd, cvar, dvar, term, fs, ts, fs_m, ts_m = _CompositeFn.apply(
         outs.reshape(F * R, St, 4), isd, dist.view(F * R, St), depth.view(F * R, St), gt_flat, cfg)
-    freespace = fs[fs_m] if want_fs else None  # 1-D, data-dependent length (:628)
-    tsdf = ts[ts_m] if want_ts else None       # (:637)
+    # 1-D tensors of data-dependent length (:628, :637).  masked_select = the reference's boolean-mask indexing, but
+    # its backward is one masked_scatter instead of index_put's sort + accumulate (18 radix-sort launches per step)
+    freespace = torch.masked_select(fs, fs_m) if want_fs else None
+    tsdf = torch.masked_select(ts, ts_m) if want_ts else None
     return rgbd.view(F, R, 4), cvar.view(F, R, 3), dvar.view(F, R), term.view(F, R), freespace, tsdf

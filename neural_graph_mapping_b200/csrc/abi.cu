@@ -46,6 +46,8 @@ int launch_field_fwd_tc(const NgmFieldFwdArgs& a, cudaStream_t stream);
 bool field_bwd_tc_supported(const NgmFieldDesc& fd, const char** why);
 size_t field_bwd_tc_workspace_bytes(const NgmFieldBwdArgs& b);
 int launch_field_bwd_tc(const NgmFieldBwdArgs& b, cudaStream_t stream);
+size_t packed_weights_bytes(const NgmFieldDesc& fd);
+int launch_pack_weights(const NgmFieldDesc& fd, const int64_t* rows, int num_rows, void* images, cudaStream_t stream);
 bool render_fused_tc_ok(const NgmRenderArgs& a);
 int launch_render_fused_tc(const NgmRenderArgs& a, void* tc_ws, float* isd_ws, const void* rows_half, const float* dist,
                            const float* depth, cudaStream_t stream);
@@ -250,6 +252,25 @@ int ngm_field_bwd(const NgmFieldBwdArgs* b, void* stream) {
     return NGM_ERR_WORKSPACE;
   }
   return launch_field_bwd_tc(*b, (cudaStream_t)stream);
+}
+
+int ngm_packed_weights_bytes(const NgmFieldDesc* fd, size_t* out) {
+  NGM_CHECK_ARG(fd && out, "null args");
+  if (int rc = validate_field(*fd)) return rc;
+  const char* why = nullptr;
+  NGM_UNSUPPORTED(!field_tc_supported(*fd, &why), "fp16 tensor-core path unsupported: %s", why);
+  *out = packed_weights_bytes(*fd);
+  return NGM_OK;
+}
+
+int ngm_pack_weights(const NgmFieldDesc* fd, const int64_t* rows, int32_t num_rows, void* images, void* stream) {
+  NGM_CHECK_ARG(fd && images, "null args");
+  NGM_CHECK_ARG(num_rows >= 0, "negative num_rows");
+  if (int rc = validate_field(*fd)) return rc;
+  const char* why = nullptr;
+  NGM_UNSUPPORTED(!field_tc_supported(*fd, &why), "fp16 tensor-core path unsupported: %s", why);
+  NGM_CHECK_ARG(((uintptr_t)images & 15) == 0, "images must be 16-byte aligned");
+  return launch_pack_weights(*fd, rows, num_rows, images, (cudaStream_t)stream);
 }
 
 int ngm_composite(const NgmCompositeArgs* a, void* stream) {

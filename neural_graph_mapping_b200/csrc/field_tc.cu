@@ -44,6 +44,7 @@ constexpr int kStageCol = 192;  // layer-0 A operand of the slot's NEXT tile (<=
 struct TcParams {
   TcImage im;
   const uint8_t* images;
+  int images_by_slot;  // persistent images (NgmFieldDesc.packed_weights): indexed by table row, not by field of the call
   int num_fields;
   int E, EP, W, L, dim_out;
   int nerf_start;
@@ -517,7 +518,8 @@ __global__ void __launch_bounds__(threads_of(MODE), 1) tc_kernel(const TcParams 
 
     // ---- stage this field's weight image (TMA engine) ----
     if (tid == 0) {
-      const uint8_t* src = p.images + (size_t)f * p.im.total_bytes;
+      const long long img = p.images_by_slot ? (p.field_slots ? p.field_slots[f] : f) : f;
+      const uint8_t* src = p.images + (size_t)img * p.im.total_bytes;
       ptx::mbar_arrive_expect_tx(&sm.w_ready, p.im.total_bytes);
       for (uint32_t o = 0; o < p.im.total_bytes; o += 32768) {
         const uint32_t n = p.im.total_bytes - o < 32768 ? p.im.total_bytes - o : 32768;
@@ -916,14 +918,16 @@ int fill_common(TcParams& p, const NgmFieldDesc& fd, int num_fields, const float
     p.pm_concat = fd.permuto_concat_points; p.pm_concat_scale = fd.permuto_concat_scaling;
   }
   p.im = make_image(fd, p.EP);
-  p.images = static_cast<const uint8_t*>(workspace);
+  p.images = static_cast<const uint8_t*>(fd.packed_weights ? fd.packed_weights : workspace);
+  p.images_by_slot = fd.packed_weights ? 1 : 0;
   p.num_fields = num_fields;
   p.positions = positions;
   p.orientations = orientations;
   p.field_slots = reinterpret_cast<const long long*>(slots);
   p.scale_mode = scale_mode;
   p.field_radius = radius;
-  PackParams pk{fd, p.im, p.field_slots, static_cast<uint8_t*>(workspace), fd.dim_encoding};
+  if (fd.packed_weights) return NGM_OK;  // persistent images: nothing to pack per call
+  PackParams pk{fd, p.im, p.field_slots, static_cast<uint8_t*>(workspace), fd.dim_encoding, 0};
   pack_weights_kernel<<<num_fields, 256, 0, stream>>>(pk);
   return check_launch("pack_weights_kernel");
 }
@@ -962,9 +966,24 @@ bool field_tc_supported(const NgmFieldDesc& fd, const char** why) {
   return w == nullptr;
 }
 
+size_t packed_weights_bytes(const NgmFieldDesc& fd) {
+  const char* why;
+  if (!field_tc_supported(fd, &why)) return 0;
+  return make_image(fd, ep_of(fd)).total_bytes;
+}
+
+int launch_pack_weights(const NgmFieldDesc& fd, const int64_t* rows, int num_rows, void* images, cudaStream_t stream) {
+  if (num_rows <= 0) return NGM_OK;
+  PackParams pk{fd, make_image(fd, ep_of(fd)), reinterpret_cast<const long long*>(rows), static_cast<uint8_t*>(images),
+                fd.dim_encoding, 1};
+  pack_weights_kernel<<<num_rows, 256, 0, stream>>>(pk);
+  return check_launch("pack_weights_kernel");
+}
+
 size_t field_tc_workspace_bytes(const NgmFieldDesc& fd, int num_fields) {
   const char* why;
   if (!field_tc_supported(fd, &why)) return 0;
+  if (fd.packed_weights) return 0;
   return (size_t)make_image(fd, ep_of(fd)).total_bytes * (size_t)(num_fields > 0 ? num_fields : 1);
 }
 

@@ -23,7 +23,7 @@
 //
 // The upstream gradient is scaled by a per-call power of two s (max |g_out| * s in (4, 8]) before the conversion
 // to fp16 -- mean-reduced losses give |g_out| ~ 1e-7, far below the fp16 range -- and the accumulators are unscaled
-// by 1/s when they are flushed.  ReLU masks are the sign bits of the pre-activation, kept as bit masks in registers.
+// by 1/s when they are flushed.  The ReLU mask of a layer is re-derived from its stored activation (h > 0).
 //
 // TMEM (512 columns): [0,128) chain/forward accumulator, [128,192) fp16 A operand, the rest weight / bias gradient
 // accumulators.  Three 128x128 fp32 accumulators do not fit next to those, so a 4-layer x 128 field is processed in
@@ -55,11 +55,14 @@ struct BwdPlan {
   uint32_t gt_off, ones_off;          // g_out^T tile (16 x 128 K-major) and the ones tile, from the activation area
   uint32_t acts_bytes;                // activation area size (buffers + the two small tiles)
   int want_denc;                      // also emit dLoss/d h_0 (lo == 0 only)
+  int emit_g;                         // lo >= 1: also produce g_lo and spill it (fp16 rows) for the next launch
+  int g_in;                           // hi < L: the chain starts from the spilled g_{hi+1} (forward only up to h_hi)
 };
 
 struct BwdParams {
   TcImage im;
   const uint8_t* images;
+  int images_by_slot;  // persistent images (NgmFieldDesc.packed_weights), indexed by table row
   int num_fields;
   int E, EP, W, WP, L, dim_out, nerf_start;
   const float* positions;
@@ -75,6 +78,8 @@ struct BwdParams {
   float* d_w[NGM_MAX_LINEARS];  // (F, out, in) fp32, zeroed by the host side
   float* d_b[NGM_MAX_LINEARS];  // (F, out)
   float* d_enc;                 // (F, N, E) or nullptr
+  uint32_t* g_spill;            // (total_tiles, 128, WP / 2) packed fp16 rows of the spilled gradient
+  long long field_base;         // first field of this launch group (row of positions / orientations / field_slots)
   long long tiles_per_field, total_tiles;
   BwdPlan plan;
 };
@@ -140,49 +145,102 @@ __device__ __forceinline__ void store_row_words16(uint8_t* buf, int row, int fea
     *reinterpret_cast<uint4*>(base + (((ch0 + k) ^ (row & 7)) << 4)) = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
 }
 
-// forward epilogue: columns [c0, c0 + CPT) of the accumulator -> h = relu(z + b) as fp16; sign bits -> mk
+// load the 16 packed words (32 features starting at `feat`) of row `row` back from such a buffer
+__device__ __forceinline__ void load_row_words16(const uint8_t* buf, int row, int feat, uint32_t* w) {
+  const uint8_t* base = buf + (size_t)(feat >> 6) * 16384 + (size_t)row * 128;
+  const int ch0 = (feat & 63) >> 3;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint4 u = *reinterpret_cast<const uint4*>(base + (((ch0 + k) ^ (row & 7)) << 4));
+    w[4 * k] = u.x; w[4 * k + 1] = u.y; w[4 * k + 2] = u.z; w[4 * k + 3] = u.w;
+  }
+}
+
+// 0xFFFF in every half of x that is > 0 (ReLU derivative of the stored activation)
+__device__ __forceinline__ uint32_t positive_mask_half2(uint32_t x) {
+  return __hgt2_mask(*reinterpret_cast<const __half2*>(&x), __half2{});
+}
+
+// forward epilogue: columns [c0, c0 + CPT) of the accumulator -> h = relu(z + b) as fp16 (one fused fma.relu per pair).
+// One 32-column load at a time: two in flight were measured slower (64 more live registers spill at the
+// 168-register cap of a 9-warp CTA).  W % 32 == 0, so a 32-column chunk is entirely inside or outside the layer.
 template <int CPT>
 __device__ __forceinline__ void fwd_epilogue(uint32_t d_addr, uint32_t a_addr, const uint32_t* bias2, int c0, int W, bool to_tmem,
-                                             uint8_t* sbuf, int row, uint32_t (&mk)[2]) {
+                                             uint8_t* sbuf, int row) {
 #pragma unroll
   for (int c = 0; c < CPT / 32; ++c) {
     const int col = c0 + 32 * c;
-    uint32_t v[32];
-    ptx::tmem_ld32(d_addr + col, v);
-    ptx::tc_wait_ld();
     uint32_t w[16];
-    uint32_t m = 0;
+    if (col < W) {
+      uint32_t v[32];
+      ptx::tmem_ld32(d_addr + col, v);
+      ptx::tc_wait_ld();
+      const uint4* b4 = reinterpret_cast<const uint4*>(bias2 + col / 2);
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const uint32_t r = ptx::bias_half2(ptx::pack_half2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), bias2[col / 2 + j]);
-      m |= (r & 0x80008000u) >> j;
-      w[j] = (col + 2 * j < W) ? ptx::relu_half2(r) : 0u;
+      for (int q4 = 0; q4 < 4; ++q4) {
+        const uint4 bb = b4[q4];
+        const uint32_t b[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int j = 4 * q4 + i;
+          w[j] = ptx::bias_relu_half2(ptx::pack_half2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), b[i]);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) w[j] = 0u;
     }
-    mk[c] = m;
     if (to_tmem) ptx::tmem_st16(a_addr + col / 2, w);
     if (sbuf) store_row_words16(sbuf, row, col, w);
   }
 }
 
-// chain epilogue: g = D .* [pre-activation >= 0] as fp16 words
+// chain epilogue: g = D .* [h > 0] as fp16 words; h is read back from its shared-memory buffer (the same
+// locations this thread wrote in the forward epilogue and will overwrite with g)
 template <int CPT>
-__device__ __forceinline__ void chain_epilogue(uint32_t d_addr, int c0, int W, const uint32_t (&mk)[2], uint32_t (&w)[CPT / 2]) {
+__device__ __forceinline__ void chain_epilogue(uint32_t d_addr, int c0, int W, const uint8_t* hbuf, int row, uint32_t (&w)[CPT / 2]) {
 #pragma unroll
   for (int c = 0; c < CPT / 32; ++c) {
     const int col = c0 + 32 * c;
-    uint32_t v[32];
-    ptx::tmem_ld32(d_addr + col, v);
-    ptx::tc_wait_ld();
+    if (col < W) {
+      uint32_t hw[16];
+      load_row_words16(hbuf, row, col, hw);
+      uint32_t v[32];
+      ptx::tmem_ld32(d_addr + col, v);
+      ptx::tc_wait_ld();
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const uint32_t x = ptx::pack_half2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
-      const uint32_t neg = ptx::sign_mask_half2((mk[c] << j) & 0x80008000u);
-      w[16 * c + j] = (col + 2 * j < W) ? (x & ~neg) : 0u;
+      for (int j = 0; j < 16; ++j)
+        w[16 * c + j] = ptx::pack_half2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])) & positive_mask_half2(hw[j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) w[16 * c + j] = 0u;
     }
   }
 }
 
 __device__ __forceinline__ void red_add(float* addr, float v) { atomicAdd(addr, v); }
+
+// spilled gradient rows (written by the previous launch of the group): this thread's CPT / 2 packed words
+__device__ __forceinline__ void fetch_spill(const uint32_t* src_words, uint32_t (&gin)[32], int cpt) {
+  const uint4* src = reinterpret_cast<const uint4*>(src_words);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    if (k < cpt / 8) {
+      const uint4 u = __ldcs(src + k);
+      gin[4 * k] = u.x; gin[4 * k + 1] = u.y; gin[4 * k + 2] = u.z; gin[4 * k + 3] = u.w;
+    }
+  }
+}
+// ... -> A operand of the first chain step (TMEM) and operand of dW_top (shared memory)
+__device__ __forceinline__ void place_spill(const uint32_t (&gin)[32], int cpt, bool to_tmem, uint32_t a_words_addr, uint8_t* sbuf,
+                                            int row, int c0) {
+  if (to_tmem) {
+    ptx::tmem_st16(a_words_addr, gin);
+    if (cpt == 64) ptx::tmem_st16(a_words_addr + 16, gin + 16);
+  }
+  store_row_words16(sbuf, row, c0, gin);
+  if (cpt == 64) store_row_words16(sbuf, row, c0 + 32, gin + 16);
+}
 
 template <int OCT, int L>
 __global__ void __launch_bounds__(kBwdThreads, 1) bwd_kernel(const BwdParams p) {
@@ -197,6 +255,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_kernel(const BwdParams p) 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int lo = p.plan.lo, hi = p.plan.hi;
+  const int top = p.plan.g_in ? hi : L;          // first backward step
+  const int fwd_layers = p.plan.g_in ? hi : L;   // forward layers recomputed per tile
   const int W = p.W, WP = p.WP;
   const int MW = WP == 128 ? 128 : 64;  // M of the weight-gradient GEMMs (rows = features of the A buffer)
 
@@ -251,7 +311,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_kernel(const BwdParams p) 
     const long long tile0_in_field = t - seg_begin;
 
     if (tid == 0) {  // stage this field's weight image (TMA engine)
-      const uint8_t* src = p.images + (size_t)f * p.im.total_bytes;
+      const long long img = p.images_by_slot ? (p.field_slots ? p.field_slots[p.field_base + f] : p.field_base + f) : f;
+      const uint8_t* src = p.images + (size_t)img * p.im.total_bytes;
       ptx::mbar_arrive_expect_tx(&sm.w_ready, p.im.total_bytes);
       for (uint32_t o = 0; o < p.im.total_bytes; o += 32768) {
         const uint32_t n = p.im.total_bytes - o < 32768 ? p.im.total_bytes - o : 32768;
@@ -269,23 +330,25 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_kernel(const BwdParams p) 
       for (int ti = 0; ti < ntiles; ++ti) {
         const uint32_t first_acc = ti > 0 ? 1u : 0u;  // the first tile of a field segment overwrites the accumulators
 #pragma unroll
-        for (int l = 0; l < L; ++l) {  // forward recompute
-          ptx::mbar_wait_lean(&sm.a_ready, pa);
-          pa ^= 1;
-          ptx::tc_fence_after();
-          if (ptx::elect_one()) {
-            issue_forward(d_work, a_tm, wsm_u, p.im.layer[l]);
-            ptx::mma_commit(&sm.d_ready);
+        for (int l = 0; l < L; ++l) {  // forward recompute (only up to h_hi when the chain starts from a spilled gradient)
+          if (l < fwd_layers) {
+            ptx::mbar_wait_spin(&sm.a_ready, pa);
+            pa ^= 1;
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) {
+              issue_forward(d_work, a_tm, wsm_u, p.im.layer[l]);
+              ptx::mma_commit(&sm.d_ready);
+            }
+            __syncwarp();
           }
-          __syncwarp();
         }
 #pragma unroll
         for (int l = L; l >= 0; --l) {  // backward step l: chain to g_l, weight gradient of linear l
-          if (l >= lo) {
-            ptx::mbar_wait_lean(&sm.a_ready, pa);
+          if (l >= lo && l <= top) {
+            ptx::mbar_wait_spin(&sm.a_ready, pa);
             pa ^= 1;
             ptx::tc_fence_after();
-            const bool chain = l > lo || (l == 0 && p.plan.want_denc);
+            const bool chain = l > lo || (l == lo && lo >= 1 && p.plan.emit_g) || (l == 0 && p.plan.want_denc);
             const bool dw = l <= hi;
             if (ptx::elect_one()) {
               if (chain) {
@@ -316,7 +379,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_kernel(const BwdParams p) 
       const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
       const uint32_t d_addr = lane_base + kColWork, a_addr = lane_base + kColA;
       const uint32_t* bias2 = reinterpret_cast<const uint32_t*>(wsm + p.im.bias_h2_off);
-      const long long slot = p.field_slots ? p.field_slots[f] : f;
+      const long long slot = p.field_slots ? p.field_slots[p.field_base + f] : p.field_base + f;
       const int CPT = WP / 2;   // columns per thread
       const int c0 = h * CPT;
       float dbl[8];             // db_L partial sums (lane 0 of the h == 1 warps)
@@ -361,46 +424,60 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_kernel(const BwdParams p) 
               for (int j = 0; j < 32; ++j) w0[j] = j < EPW ? we[j < EPW ? j : 0] : 0u;
             }
           }
-        } else if (valid) {
+        } else if (valid && !p.plan.g_in) {
           const float* src = p.d_out + prow * p.dim_out;
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             if (j < p.dim_out) go[j] = __ldg(src + j);
         }
+        // spilled gradient g_{hi+1} of this row (this thread's half of the columns), written by the previous launch
+        const size_t spill_row = ((size_t)(t + ti) * 128 + row) * (size_t)(WP / 2) + c0 / 2;
+        uint32_t gin[32];
+        const uint32_t* g_src = p.g_spill + spill_row;
+        const bool chain_top = top > lo || (top == 0 && p.plan.want_denc) || (top == lo && lo >= 1 && p.plan.emit_g);
+        uint8_t* g_buf = acts + p.plan.buf_off[top + 1 <= L ? top + 1 : L];
+        if (p.plan.g_in && fwd_layers == 0) fetch_spill(g_src, gin, CPT);
         // the previous tile's last weight-gradient group reads the buffers this tile is about to overwrite
         if (dw_pending) {
           ptx::mbar_wait_lean(&sm.dw_done, pdw);
           pdw ^= 1;
           dw_pending = false;
         }
+        ptx::tc_fence_after();
         if (h == 0) {
-          ptx::tc_fence_after();
-          ptx::tmem_st16(a_addr, w0);
-          if (p.EP > 32) ptx::tmem_st16(a_addr + 16, w0 + 16);
+          if (fwd_layers > 0) {
+            ptx::tmem_st16(a_addr, w0);
+            if (p.EP > 32) ptx::tmem_st16(a_addr + 16, w0 + 16);
+          }
           if (lo == 0) {
             uint8_t* b0 = acts + p.plan.buf_off[0];
             store_row_words16(b0, row, 0, w0);
             if (p.EP > 32) store_row_words16(b0, row, 32, w0 + 16);
           }
         }
+        if (p.plan.g_in && fwd_layers == 0) place_spill(gin, CPT, chain_top, a_addr + c0 / 2, g_buf, row, c0);
         ptx::tc_wait_st();
         ptx::fence_proxy_async();
         ptx::tc_fence_before();
         ptx::mbar_arrive(&sm.a_ready);
 
         // ---- forward recompute ----
-        uint32_t mk[L][2];
 #pragma unroll
         for (int l = 0; l < L; ++l) {
+          if (l >= fwd_layers) continue;
+          if (p.plan.g_in && l + 1 == fwd_layers) fetch_spill(g_src, gin, CPT);
           ptx::mbar_wait_lean(&sm.d_ready, pd);
           pd ^= 1;
           ptx::tc_fence_after();
           const int j = l + 1;  // this epilogue produces h_j
-          const bool to_tmem = j < L;
-          uint8_t* sbuf = (j >= lo && j <= hi) ? acts + p.plan.buf_off[j] : nullptr;
-          if (CPT == 64) fwd_epilogue<64>(d_addr, a_addr, bias2 + l * (W / 2), c0, W, to_tmem, sbuf, row, mk[l]);
-          else           fwd_epilogue<32>(d_addr, a_addr, bias2 + l * (W / 2), c0, W, to_tmem, sbuf, row, mk[l]);
-          if (j == L && h == 1) {
+          const bool to_tmem = j < fwd_layers;
+          // h_j goes to shared memory when a weight-gradient GEMM reads it (j in [lo, hi]) or the chain needs its
+          // ReLU mask (j <= hi + 1): both are the buffer range [lo, min(hi + 1, L)]
+          uint8_t* sbuf = (j >= lo && j <= hi + 1) ? acts + p.plan.buf_off[j] : nullptr;
+          if (CPT == 64) fwd_epilogue<64>(d_addr, a_addr, bias2 + l * (W / 2), c0, W, to_tmem, sbuf, row);
+          else           fwd_epilogue<32>(d_addr, a_addr, bias2 + l * (W / 2), c0, W, to_tmem, sbuf, row);
+          if (j == fwd_layers && p.plan.g_in) place_spill(gin, CPT, chain_top, a_addr + c0 / 2, g_buf, row, c0);
+          if (j == L && h == 1 && !p.plan.g_in) {
             // g_out of this row: scaled fp16 into the A operand (K = 16) and, transposed, into the 16 x 128 tile
             uint32_t wg[8];
 #pragma unroll
@@ -434,20 +511,35 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_kernel(const BwdParams p) 
         // ---- backward chain ----
 #pragma unroll
         for (int l = L; l >= 0; --l) {
-          if (l >= lo) {
-            const bool chain = l > lo || (l == 0 && p.plan.want_denc);
+          if (l >= lo && l <= top) {
+            const bool emit = l == lo && lo >= 1 && p.plan.emit_g;
+            const bool chain = l > lo || emit || (l == 0 && p.plan.want_denc);
             const bool dw = l <= hi;
             if (chain) {
               ptx::mbar_wait_lean(&sm.d_ready, pd);
               pd ^= 1;
               ptx::tc_fence_after();
             }
-            if (l >= 1 && chain) {
+            if (emit) {
+              // g_lo = D .* mask(h_lo) -> HBM (fp16 rows): the next launch continues the chain from it
+              uint32_t wg[32];
+              const uint8_t* hbuf = acts + p.plan.buf_off[l];
+              if (CPT == 64) chain_epilogue<64>(d_addr, c0, W, hbuf, row, reinterpret_cast<uint32_t(&)[32]>(wg));
+              else           chain_epilogue<32>(d_addr, c0, W, hbuf, row, reinterpret_cast<uint32_t(&)[16]>(wg));
+              uint4* dst = reinterpret_cast<uint4*>(p.g_spill + spill_row);
+#pragma unroll
+              for (int k = 0; k < 8; ++k)
+                if (k < CPT / 8) __stcs(dst + k, make_uint4(wg[4 * k], wg[4 * k + 1], wg[4 * k + 2], wg[4 * k + 3]));
+              ptx::tc_fence_before();
+              if (dw) dw_pending = true;
+            } else if (l >= 1 && chain) {
               // g_l = D .* mask(h_l): A operand of the next chain step, and (in place over h_l) operand of dW_{l-1}
               uint32_t wg[32];
-              if (CPT == 64) chain_epilogue<64>(d_addr, c0, W, mk[l - 1], reinterpret_cast<uint32_t(&)[32]>(wg));
-              else           chain_epilogue<32>(d_addr, c0, W, mk[l - 1], reinterpret_cast<uint32_t(&)[16]>(wg));
-              const bool more = (l - 1 > lo) || (l - 1 == 0 && p.plan.want_denc);  // g_l feeds another chain step
+              const uint8_t* hbuf = acts + p.plan.buf_off[l];
+              if (CPT == 64) chain_epilogue<64>(d_addr, c0, W, hbuf, row, reinterpret_cast<uint32_t(&)[32]>(wg));
+              else           chain_epilogue<32>(d_addr, c0, W, hbuf, row, reinterpret_cast<uint32_t(&)[16]>(wg));
+              const bool more = (l - 1 > lo) || (l - 1 == lo && lo >= 1 && p.plan.emit_g) ||
+                                (l - 1 == 0 && p.plan.want_denc);  // g_l feeds another chain step
               if (more) {
                 ptx::tmem_st16(a_addr + c0 / 2, wg);
                 if (CPT == 64) ptx::tmem_st16(a_addr + c0 / 2 + 16, wg + 16);
@@ -597,6 +689,10 @@ bool plan_launch(const NgmFieldDesc& fd, const TcImage& im, int hi, bool want_de
   plan.ones_off = off; off += 4096;
   plan.acts_bytes = off;
   plan.want_denc = (want_denc && best_lo == 0) ? 1 : 0;
+  // more than one launch: this one hands g_lo to the next (fp16 rows in HBM) instead of the next one recomputing
+  // the whole forward and chain; a launch that starts below the last linear continues from that spill
+  plan.emit_g = best_lo >= 1 ? 1 : 0;
+  plan.g_in = hi < L ? 1 : 0;
   return true;
 }
 
@@ -646,12 +742,33 @@ bool field_bwd_tc_supported(const NgmFieldDesc& fd, const char** why) {
   return w == nullptr;
 }
 
-// workspace: [weight images][fp16 rows of pre-encoded encodings][absmax]
+// fields per launch group: the gradient spill between two launches of a group stays below ~1 GB
+constexpr size_t kSpillBudget = (size_t)1 << 30;
+long long group_fields(const NgmFieldFwdArgs& a) {
+  const long long tiles_per_field = (a.points_per_field + 127) / 128;
+  const size_t per_field = (size_t)tiles_per_field * 128 * (a.field.dim_mlp_out > 64 ? 128 : 64) * 2;
+  long long g = (long long)(kSpillBudget / (per_field ? per_field : 1));
+  if (g < 1) g = 1;
+  return g < a.num_fields ? g : a.num_fields;
+}
+bool needs_spill(const NgmFieldDesc& fd) {
+  BwdPlan plan;
+  return plan_launch(fd, make_image(fd, ep_of(fd)), fd.num_layers, false, plan) && plan.lo >= 1;
+}
+size_t spill_bytes(const NgmFieldFwdArgs& a) {
+  if (!needs_spill(a.field)) return 0;
+  const long long tiles_per_field = (a.points_per_field + 127) / 128;
+  return (size_t)group_fields(a) * (size_t)tiles_per_field * 128 * (a.field.dim_mlp_out > 64 ? 128 : 64) * 2;
+}
+
+// workspace: [weight images][fp16 rows of pre-encoded encodings][gradient spill of one launch group][absmax]
 size_t field_bwd_tc_workspace_bytes(const NgmFieldBwdArgs& b) {
   const NgmFieldFwdArgs& a = b.fwd;
-  size_t n = ((size_t)make_image(a.field, ep_of(a.field)).total_bytes * (size_t)(a.num_fields > 0 ? a.num_fields : 1) + 255) / 256 * 256;
+  size_t n = a.field.packed_weights ? 0 :
+      ((size_t)make_image(a.field, ep_of(a.field)).total_bytes * (size_t)(a.num_fields > 0 ? a.num_fields : 1) + 255) / 256 * 256;
   if (bwd_oct(a.field) == 0 && !a.rows_half)
     n += ((size_t)a.num_fields * (size_t)a.points_per_field * (size_t)ep_of(a.field) * 2 + 255) / 256 * 256;
+  n += (spill_bytes(a) + 255) / 256 * 256;
   return n + 256;
 }
 
@@ -681,11 +798,16 @@ int launch_field_bwd_tc(const NgmFieldBwdArgs& b, cudaStream_t stream) {
   p.total_tiles = p.tiles_per_field * a.num_fields;
   char* ws = static_cast<char*>(a.workspace);
   size_t off = 0;
-  p.images = reinterpret_cast<const uint8_t*>(ws);
-  off = ((size_t)p.im.total_bytes * (size_t)a.num_fields + 255) / 256 * 256;
-  PackParams pk{fd, p.im, p.field_slots, reinterpret_cast<uint8_t*>(ws), fd.dim_encoding};
-  pack_weights_kernel<<<a.num_fields, 256, 0, stream>>>(pk);
-  if (int rc = check_launch("pack_weights_kernel")) return rc;
+  if (fd.packed_weights) {
+    p.images = static_cast<const uint8_t*>(fd.packed_weights);
+    p.images_by_slot = 1;
+  } else {
+    p.images = reinterpret_cast<const uint8_t*>(ws);
+    off = ((size_t)p.im.total_bytes * (size_t)a.num_fields + 255) / 256 * 256;
+    PackParams pk{fd, p.im, p.field_slots, reinterpret_cast<uint8_t*>(ws), fd.dim_encoding, 0};
+    pack_weights_kernel<<<a.num_fields, 256, 0, stream>>>(pk);
+    if (int rc = check_launch("pack_weights_kernel")) return rc;
+  }
   const int oct = bwd_oct(fd);
   if (oct == 0) {
     if (a.rows_half) {
@@ -707,6 +829,8 @@ int launch_field_bwd_tc(const NgmFieldBwdArgs& b, cudaStream_t stream) {
       off += ((size_t)e.num_points * (size_t)p.EP * 2 + 255) / 256 * 256;
     }
   }
+  p.g_spill = reinterpret_cast<uint32_t*>(ws + off);
+  off += (spill_bytes(a) + 255) / 256 * 256;
   unsigned* absmax = reinterpret_cast<unsigned*>(ws + off);
   NGM_CUDA(cudaMemsetAsync(absmax, 0, sizeof(unsigned), stream));
   const long long n_out = (long long)a.num_fields * a.points_per_field * fd.dim_out;
@@ -724,23 +848,44 @@ int launch_field_bwd_tc(const NgmFieldBwdArgs& b, cudaStream_t stream) {
   }
   const char* e = getenv("NGM_TC_MAX_CTAS");
   const int cap = e ? atoi(e) : 0;
-  long long g = num_sms();
-  if (cap > 0 && cap < g) g = cap;
-  const int grid = (int)(p.total_tiles < g ? p.total_tiles : g);
-  for (int hi = L; hi >= 0;) {
-    if (!plan_launch(fd, p.im, hi, b.d_encoding != nullptr, p.plan)) {
-      set_error("tcgen05 backward: field too large for shared memory / TMEM");
-      return NGM_ERR_UNSUPPORTED;
+  long long sms = num_sms();
+  if (cap > 0 && cap < sms) sms = cap;
+  // launch groups of fields (bounded gradient spill); inside a group the launches go from the last linear down
+  const long long gf = needs_spill(fd) ? group_fields(a) : a.num_fields;
+  const BwdParams base = p;
+  for (long long f0 = 0; f0 < a.num_fields; f0 += gf) {
+    const long long nf = a.num_fields - f0 < gf ? a.num_fields - f0 : gf;
+    p = base;
+    p.field_base = f0;
+    p.num_fields = (int)nf;
+    if (!base.images_by_slot) p.images = base.images + (size_t)f0 * p.im.total_bytes;
+    const size_t pt0 = (size_t)f0 * (size_t)a.points_per_field;
+    if (base.points) p.points = base.points + pt0 * 3;
+    if (base.raw_a) p.raw_a = base.raw_a + pt0 * (size_t)p.EP;
+    p.d_out = base.d_out + pt0 * (size_t)fd.dim_out;
+    if (base.d_enc) p.d_enc = base.d_enc + pt0 * (size_t)fd.dim_encoding;
+    for (int l = 0; l <= L; ++l) {
+      const size_t out_l = l == L ? fd.dim_out : W, in_l = l == 0 ? fd.dim_encoding : W;
+      p.d_w[l] = base.d_w[l] + (size_t)f0 * out_l * in_l;
+      p.d_b[l] = base.d_b[l] + (size_t)f0 * out_l;
     }
-    const size_t smem = bwd_smem_bytes(p.im, p.plan);
-    int rc;
-    switch (oct) {
-      case 4: rc = launch_bwd_l<4>(p, smem, grid, stream); break;
-      case 8: rc = launch_bwd_l<8>(p, smem, grid, stream); break;
-      default: rc = launch_bwd_l<0>(p, smem, grid, stream); break;
+    p.total_tiles = p.tiles_per_field * nf;
+    const int grid = (int)(p.total_tiles < sms ? p.total_tiles : sms);
+    for (int hi = L; hi >= 0;) {
+      if (!plan_launch(fd, p.im, hi, b.d_encoding != nullptr, p.plan)) {
+        set_error("tcgen05 backward: field too large for shared memory / TMEM");
+        return NGM_ERR_UNSUPPORTED;
+      }
+      const size_t smem = bwd_smem_bytes(p.im, p.plan);
+      int rc;
+      switch (oct) {
+        case 4: rc = launch_bwd_l<4>(p, smem, grid, stream); break;
+        case 8: rc = launch_bwd_l<8>(p, smem, grid, stream); break;
+        default: rc = launch_bwd_l<0>(p, smem, grid, stream); break;
+      }
+      if (rc) return rc;
+      hi = p.plan.lo - 1;
     }
-    if (rc) return rc;
-    hi = p.plan.lo - 1;
   }
   return NGM_OK;
 }

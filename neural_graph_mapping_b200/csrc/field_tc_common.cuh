@@ -53,12 +53,13 @@ struct PackParams {
   const long long* field_slots;
   uint8_t* images;
   int E;
+  int dst_by_slot;  // persistent images: row r of the tables -> image r (instead of the call's field index)
 };
 
 __global__ void __launch_bounds__(256) pack_weights_kernel(PackParams p) {
   const int f = blockIdx.x;
   const long long slot = p.field_slots ? p.field_slots[f] : f;
-  uint8_t* img = p.images + (size_t)f * p.im.total_bytes;
+  uint8_t* img = p.images + (size_t)(p.dst_by_slot ? slot : f) * p.im.total_bytes;
   const int L = p.fd.num_layers, W = p.fd.dim_mlp_out;
   for (int l = 0; l <= L; ++l) {
     const TcLayer y = p.im.layer[l];

@@ -31,7 +31,8 @@ def fieldset_forward_knn(model, query_points, field_positions, field_orientation
         out = torch.empty(n, 4, device=dev)
         a = _lib.NgmKnnFwdArgs()
         with torch.cuda.device(dev):
-            a.field, keep = model._prototype_field.field_desc(params, True)
+            a.field, keep = model._prototype_field.field_desc(
+                params, True, model.packed_images(params) if precision == "fp16" else None)
             a.num_points, a.num_fields = n, F
             a.points, a.positions, a.orientations = pts.data_ptr(), pos.data_ptr(), ori.data_ptr()
             if field_ids is not None:

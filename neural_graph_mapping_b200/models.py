@@ -103,12 +103,16 @@ class NeuralField(torch.nn.Module):
         return sum(p.numel() for p in self.parameters())
 
     # ---- descriptor ---------------------------------------------------------------------
-    def field_desc(self, params: Dict[str, torch.Tensor], stacked: bool):
+    def field_desc(self, params: Dict[str, torch.Tensor], stacked: bool, packed: Optional[torch.Tensor] = None):
         """Fill an ``NgmFieldDesc`` from a parameter dict with the reference's state_dict names.
-        ``stacked``: tensors carry a leading field dimension (all_fields_params layout).
+        ``stacked``: tensors carry a leading field dimension (all_fields_params layout).  ``packed``: persistent
+        pre-swizzled fp16 images of the same tables (``NeuralFieldSet.packed_images``).
         Returns (desc, keepalive) -- keepalive holds the contiguous tensors the desc points to."""
         d = _lib.NgmFieldDesc()
         keep = []
+        if packed is not None:
+            keep.append(packed)
+            d.packed_weights = packed.data_ptr()
         enc = self._encoding
         d.encoding = _lib.ENC[enc.KIND]
         d.dim_encoding = self._dim_encoding
@@ -240,6 +244,58 @@ class NeuralFieldSet(torch.nn.Module):
         self._prototype_field = ft(**field_kwargs)
         self.all_fields_params = None
         self.vmap_fields_params = None
+
+    # ---- persistent kernel-friendly weight layout ------------------------------------------------
+    def _linear_names(self):
+        n = self._prototype_field._num_layers + 1
+        return [f"_linears.{i}.{w}" for i in range(n) for w in ("weight", "bias")]
+
+    def _packed_key(self, params):
+        return tuple((k, params[k].data_ptr(), params[k]._version, tuple(params[k].shape)) for k in self._linear_names())
+
+    def packed_images(self, params: Dict[str, torch.Tensor]) -> Optional[torch.Tensor]:
+        """Pre-swizzled fp16 weight images (one per table row) of ``params`` for the tensor-core kernels, cached
+        while the tables are unchanged: the cache key is every linear's storage pointer, torch version counter and
+        shape, so in-place updates by torch ops (the reference driver's scatter-back, run_mapping.py:1204) and new
+        tables (``add_fields``, ``load_model``) invalidate it; ``ngm_adam_step`` writes through raw pointers, so
+        ``repack_rows`` re-packs exactly the rows it touched and keeps the cache valid.  None when the field has no
+        tensor-core path or ``params`` is not this set's ``all_fields_params``."""
+        if params is not self.all_fields_params or params is None:
+            return None
+        key = self._packed_key(params)
+        cache = getattr(self, "_packed_cache", None)
+        if cache is not None and cache[0] == key:
+            return cache[1]
+        dev = params[self._linear_names()[0]].device
+        if dev.type != "cuda":
+            return None
+        with torch.cuda.device(dev):
+            desc, keep = self._prototype_field.field_desc(params, True)
+            per = C.c_size_t(0)
+            rc = _lib.lib.ngm_packed_weights_bytes(C.byref(desc), C.byref(per))
+            if rc == -2:  # field outside the tensor-core path: nothing to cache
+                self._packed_cache = (key, None)
+                return None
+            _lib.check(rc)
+            rows = params[self._linear_names()[0]].shape[0]
+            buf = torch.empty(max(rows * per.value, 16), dtype=torch.uint8, device=dev)
+            _lib.check(_lib.lib.ngm_pack_weights(C.byref(desc), None, rows, buf.data_ptr(), _lib.stream_ptr(dev)))
+        self._packed_cache = (key, buf)
+        return buf
+
+    def repack_rows(self, field_ids: torch.Tensor) -> None:
+        """Re-pack the images of rows ``field_ids`` after an in-place update that torch's version counters cannot
+        see (``ngm_adam_step``); no-op without a cache."""
+        cache = getattr(self, "_packed_cache", None)
+        params = self.all_fields_params
+        if cache is None or cache[1] is None or params is None or cache[0] != self._packed_key(params):
+            return
+        dev = cache[1].device
+        ids = field_ids.to(device=dev, dtype=torch.int64).contiguous()
+        with torch.cuda.device(dev):
+            desc, keep = self._prototype_field.field_desc(params, True)
+            _lib.check(_lib.lib.ngm_pack_weights(C.byref(desc), ids.data_ptr(), ids.numel(), cache[1].data_ptr(),
+                                                 _lib.stream_ptr(dev)))
 
     def add_fields(self, num_fields: int) -> None:
         """Append ``num_fields`` copies of the prototype's state (ngm/models.py:245-264)."""

@@ -137,3 +137,5 @@ def update_step(driver, loss_dict: dict, field_ids: torch.Tensor) -> None:
     if driver._optim_state is None:
         driver._optim_state = new_optim_state(model.all_fields_params)
     adam_step(model.all_fields_params, model.vmap_fields_params, driver._optim_state, field_ids, **adam_hyper(driver))
+    if hasattr(model, "repack_rows"):  # keep the persistent fp16 weight images in step with the rows just updated
+        model.repack_rows(field_ids)

@@ -144,7 +144,8 @@ def render_rays(
             0 if jitter is not None else (_next_seed() if seed is None else int(seed)), _precision(driver),
             sample_offset=int(sample_offset)))
     with torch.no_grad(), torch.cuda.device(dev):
-        a.field, k2 = proto.field_desc(params, True)
+        packed = model.packed_images(params) if (slots is not None and _precision(driver) == "fp16") else None
+        a.field, k2 = proto.field_desc(params, True, packed)
         keep += k2
         a.cam = camera_struct(camera)
         a.num_fields, a.rays_per_field = F, R

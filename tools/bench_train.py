@@ -25,14 +25,11 @@ def run(F, R, S, G, prec, reps=5):
     cfg["num_samples_coarse"], cfg["num_samples_depth_guided"] = S, G
     st = ngm.RenderState(cfg)
     st.set_fields(sc["params"], sc["positions"], sc["orientations"])
-    for v in st._model.all_fields_params.values():
-        v.requires_grad_(True)
+    st._reference_flow = True  # the driver's flow: _render_ijs first gathers the active fields into leaves (:500)
     dz = {k: sc[k].to(dev) for k in ("ijs", "c2w", "near", "far", "field_ids")}
     gt = (dz["near"] + dz["far"]) * 0.5 if G else None
     ts = []
     for i in range(reps + 2):
-        for v in st._model.all_fields_params.values():
-            v.grad = None
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         p = st._render_ijs(dz["ijs"], dz["c2w"], cam, dz["field_ids"], True, dz["near"], dz["far"], gt)
@@ -68,8 +65,14 @@ def run_cpu(F, R, S, G):
     return (time.perf_counter() - t0) * 1e3
 
 
-for name, (F, R, S, G) in {"default training batch (32 x 512 x 8+16)": (32, 512, 8, 16),
-                           "config-4 shard (32 x 4096 x 64)": (32, 4096, 64, 0)}.items():
+SHAPES = {"default training batch (32 x 512 x 8+16)": (32, 512, 8, 16),
+          "config-4 shard (32 x 4096 x 64)": (32, 4096, 64, 0)}
+if "--profile" in sys.argv:  # under ncu: python tools/bench_train.py --profile {default|c4}: one fp16 step, no CPU column
+    which = sys.argv[sys.argv.index("--profile") + 1]
+    F, R, S, G = SHAPES[[k for k in SHAPES if (which == "c4") == k.startswith("config-4")][0]]
+    print(json.dumps({"profiled": which, "ms": run(F, R, S, G, "fp16", reps=1)}))
+    sys.exit(0)
+for name, (F, R, S, G) in SHAPES.items():
     row = {"shape": name, "rays": F * R, "points": F * R * (S + G)}
     for prec in ("fp16", "fp32"):  # fp16: tcgen05 forward + tcgen05 backward; fp32: reference arithmetic
         ms = run(F, R, S, G, prec)
