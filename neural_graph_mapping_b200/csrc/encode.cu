@@ -98,8 +98,8 @@ __global__ void __launch_bounds__(256) permuto_rows_f32_kernel(PermutoRowsArgs a
   float* out = reinterpret_cast<float*>(a.out);
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(idx % groups);
-    const long long pt = idx / groups;
+    const int g = (int)(idx / a.num_points);  // lanes = consecutive points of one level group (see the fp16 kernel)
+    const long long pt = idx - (long long)g * a.num_points;
     long long f = pt / a.points_per_field, src_pt = pt;
     if (a.pair_field) {
       f = __ldg(a.pair_field + pt);
@@ -139,10 +139,14 @@ __global__ void __launch_bounds__(256) permuto_rows_half_kernel(PermutoRowsArgs 
   const int L = fd.permuto_levels, groups = (L + 3) / 4, words = a.EP / 2;
   const size_t level_elems = ((size_t)1 << fd.permuto_log2_capacity) * 2;
   const long long total = a.num_points * groups;
+  // Lane mapping: consecutive lanes = consecutive points (neighbouring samples of a ray) of ONE group of 4 levels.
+  // On the coarse levels neighbouring samples fall into the same or adjacent simplices, so the lanes of a gather
+  // instruction hit the same 32-byte sectors and the request count drops; with (point, group) interleaved across
+  // lanes every lane of an instruction reads a different level's table (ncu: 2.1 L2 sectors per vertex).
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(idx % groups);
-    const long long pt = idx / groups;
+    const int g = (int)(idx / a.num_points);
+    const long long pt = idx - (long long)g * a.num_points;
     long long f = pt / a.points_per_field, src_pt = pt;
     if (a.pair_field) {
       f = __ldg(a.pair_field + pt);
@@ -213,10 +217,14 @@ __global__ void __launch_bounds__(256) feature_rows_half_kernel(PermutoRowsArgs 
   const NgmFieldDesc& fd = a.field;
   const int E = fd.dim_encoding, groups = a.EP / 8;
   const long long total = a.num_points * groups;
+  // Lane mapping: consecutive lanes = consecutive points (neighbouring samples of a ray) of ONE group of 4 levels.
+  // On the coarse levels neighbouring samples fall into the same or adjacent simplices, so the lanes of a gather
+  // instruction hit the same 32-byte sectors and the request count drops; with (point, group) interleaved across
+  // lanes every lane of an instruction reads a different level's table (ncu: 2.1 L2 sectors per vertex).
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(idx % groups);
-    const long long pt = idx / groups;
+    const int g = (int)(idx / a.num_points);
+    const long long pt = idx - (long long)g * a.num_points;
     long long f = pt / a.points_per_field, src_pt = pt;
     if (a.pair_field) {
       f = __ldg(a.pair_field + pt);

@@ -147,12 +147,23 @@ __device__ __forceinline__ void permuto_level(const float* x, const float* __res
   float acc[MAXF];
 #pragma unroll
   for (int f = 0; f < MAXF; ++f) acc[f] = 0.0f;
+  if (feats == 2 && MAXF >= 2 && (reinterpret_cast<uintptr_t>(table) & 7) == 0) {
+    // nr_feat_per_level = 2 (the reference's default, neural_graph_map.yaml:11): one 8-byte gather per vertex instead
+    // of two 4-byte ones -- the row encoder is bound by L2 sector requests (ncu: 2.1 sectors per vertex before)
 #pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const float* fv = table + (size_t)row[r] * feats;
+    for (int r = 0; r < 4; ++r) {
+      const float2 v = __ldg(reinterpret_cast<const float2*>(table) + row[r]);
+      acc[0] = __fadd_rn(acc[0], __fmul_rn(weight[r], v.x));
+      acc[1] = __fadd_rn(acc[1], __fmul_rn(weight[r], v.y));
+    }
+  } else {
 #pragma unroll
-    for (int f = 0; f < MAXF; ++f)
-      if (f < feats) acc[f] = __fadd_rn(acc[f], __fmul_rn(weight[r], __ldg(fv + f)));
+    for (int r = 0; r < 4; ++r) {
+      const float* fv = table + (size_t)row[r] * feats;
+#pragma unroll
+      for (int f = 0; f < MAXF; ++f)
+        if (f < feats) acc[f] = __fadd_rn(acc[f], __fmul_rn(weight[r], __ldg(fv + f)));
+    }
   }
 #pragma unroll
   for (int f = 0; f < MAXF; ++f)

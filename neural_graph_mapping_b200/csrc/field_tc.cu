@@ -102,6 +102,7 @@ struct TcParams {
   float* tsdf;
   uint8_t* tsdf_mask;
   int trace;
+  int acc16;  // hidden layers accumulate in fp16 inside the tensor core (NGM_TC_ACC16=1): packed accumulator loads
 };
 
 constexpr int kMaxRaysPerTile = 16;  // Sp >= 8
@@ -196,6 +197,36 @@ __device__ __forceinline__ void hidden_epilogue(uint32_t d_addr, uint32_t a_addr
     ptx::tc_wait_ld();
     uint32_t w[8];
     cvt16(v, bias2 + c / 2, w);
+    ptx::tmem_st8(a_addr + c / 2, w);
+  }
+}
+
+// the same with 16-bit accumulators: packed loads deliver two columns per register, no fp32 -> fp16 convert
+__device__ __forceinline__ void hidden_epilogue_acc16(uint32_t d_addr, uint32_t a_addr, const uint32_t* bias2, int c0, int n) {
+  int c = c0;
+  const int end = c0 + n;
+  for (; c + 32 <= end; c += 32) {  // 32 columns -> 16 packed registers (small register footprint: 96-register cap)
+    uint32_t v[16];
+    ptx::tmem_ld16_pack16(d_addr + c, v);
+    ptx::tc_wait_ld();
+    uint32_t w[16];
+#pragma unroll
+    for (int q4 = 0; q4 < 4; ++q4) {
+      const uint4 bb = *reinterpret_cast<const uint4*>(bias2 + c / 2 + 4 * q4);
+      w[4 * q4] = ptx::bias_relu_half2(v[4 * q4], bb.x);
+      w[4 * q4 + 1] = ptx::bias_relu_half2(v[4 * q4 + 1], bb.y);
+      w[4 * q4 + 2] = ptx::bias_relu_half2(v[4 * q4 + 2], bb.z);
+      w[4 * q4 + 3] = ptx::bias_relu_half2(v[4 * q4 + 3], bb.w);
+    }
+    ptx::tmem_st16(a_addr + c / 2, w);
+  }
+  if (c + 16 <= end) {
+    uint32_t v[8];
+    ptx::tmem_ld8_pack16(d_addr + c, v);
+    ptx::tc_wait_ld();
+    uint32_t w[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) w[i] = ptx::bias_relu_half2(v[i], bias2[c / 2 + i]);
     ptx::tmem_st8(a_addr + c / 2, w);
   }
 }
@@ -438,7 +469,7 @@ __device__ __forceinline__ void issue_layer(uint32_t d_addr, uint32_t a_addr, ui
 // slotted into the waits for the current tile's MMAs), h = 0 threads the COMPOSITOR of the current tile.
 // (A lockstep variant in which all 16 warps share every epilogue job of both slots was measured slower --
 // 3.85 ms vs 2.83 ms per frame -- because each duty then stalls all 512 threads; profiles/README.md.)
-template <int MODE, int OCT, bool TRACE>
+template <int MODE, int OCT, bool TRACE, bool ACC16>
 __global__ void __launch_bounds__(threads_of(MODE), 1) tc_kernel(const TcParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   // weights image first (1024-B aligned for SWIZZLE_128B), bookkeeping after it; plain pointer
@@ -566,7 +597,7 @@ __global__ void __launch_bounds__(threads_of(MODE), 1) tc_kernel(const TcParams 
           tev(ev_id(0, s, 0, l));
           const TcLayer y = p.im.layer[l];
           const uint64_t desc0 = ptx::make_smem_desc_sw128(wsm_u + y.off);
-          const uint32_t idesc = ptx::make_idesc_f16(y.n_pad);
+          const uint32_t idesc = (ACC16 && l < L) ? ptx::make_idesc_f16_acc16(y.n_pad) : ptx::make_idesc_f16(y.n_pad);
           if (ptx::elect_one()) {
             issue_layer(d_addr, l == 0 ? d_addr + kStageCol : a_addr, desc0, (uint32_t)y.n_pad * 8u, idesc, y.k_pad / 16);
             ptx::mma_commit(&sm.d_ready[s]);
@@ -751,7 +782,10 @@ __global__ void __launch_bounds__(threads_of(MODE), 1) tc_kernel(const TcParams 
             if (l < L) {
               // ---------- hidden layer l (both halves) ----------
               tev(ev_id(1 + (h == 0), s, 3, l));
-              if (my_n > 0) hidden_epilogue(d_addr, a_addr, bias2 + l * (W / 2), my_c0, my_n);
+              if (my_n > 0) {
+                if constexpr (ACC16) hidden_epilogue_acc16(d_addr, a_addr, bias2 + l * (W / 2), my_c0, my_n);
+                else                 hidden_epilogue(d_addr, a_addr, bias2 + l * (W / 2), my_c0, my_n);
+              }
               ptx::tc_wait_st();
               ptx::tc_fence_before();
               ptx::mbar_arrive(&sm.a_ready[s]);
@@ -875,6 +909,10 @@ template <int MODE>
 int launch_tc(const TcParams& p_in, int octaves, size_t smem, int grid, cudaStream_t stream) {
   TcParams p = p_in;
   p.trace = tc_trace_enabled();
+  {
+    const char* e = getenv("NGM_TC_ACC16");  // read per call: tests / A-B runs switch it
+    p.acc16 = (e && e[0] == '1') ? 1 : 0;
+  }
   if (p.trace) {
     unsigned zero = 0;
     cudaMemcpyToSymbolAsync(g_trace_n, &zero, sizeof(zero), 0, cudaMemcpyHostToDevice, stream);
@@ -884,14 +922,22 @@ int launch_tc(const TcParams& p_in, int octaves, size_t smem, int grid, cudaStre
     kernel<<<grid, threads_of(MODE), smem, stream>>>(p);
     return check_launch("tc_kernel");
   };
+  if (p.acc16 && !p.trace) {  // 16-bit accumulation of the hidden layers (NGM_TC_ACC16=1)
+    switch (octaves) {
+      case 0: return go(tc_kernel<MODE, 0, false, true>);
+      case 4: return go(tc_kernel<MODE, 4, false, true>);
+      case 8: return go(tc_kernel<MODE, 8, false, true>);
+      default: break;
+    }
+  }
   switch (octaves * 2 + (p.trace ? 1 : 0)) {  // octaves == 0: permutohedral
-    case 0: return go(tc_kernel<MODE, 0, false>);
-    case 8: return go(tc_kernel<MODE, 4, false>);
-    case 16: return go(tc_kernel<MODE, 8, false>);
+    case 0: return go(tc_kernel<MODE, 0, false, false>);
+    case 8: return go(tc_kernel<MODE, 4, false, false>);
+    case 16: return go(tc_kernel<MODE, 8, false, false>);
 #ifdef NGM_DEBUG_EXPORTS
-    case 1: return go(tc_kernel<MODE, 0, true>);
-    case 9: return go(tc_kernel<MODE, 4, true>);
-    case 17: return go(tc_kernel<MODE, 8, true>);
+    case 1: return go(tc_kernel<MODE, 0, true, false>);
+    case 9: return go(tc_kernel<MODE, 4, true, false>);
+    case 17: return go(tc_kernel<MODE, 8, true, false>);
 #endif
     default: set_error("tcgen05 path: unsupported num_octaves %d", octaves); return NGM_ERR_UNSUPPORTED;
   }
