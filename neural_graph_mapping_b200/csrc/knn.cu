@@ -82,19 +82,24 @@ __device__ __forceinline__ int warp_aggregated_inc(int* counters, int f, bool ac
   return slot;
 }
 
+// KT = compile-time K (0: runtime K <= kMaxK): the sorted insertion is K predicated compare-swaps per centre; with
+// the reference's K = 2 (neural_graph_map.yaml:21) the runtime-K form spent 4x the instructions on dead slots
+template <int KT>
 __global__ void __launch_bounds__(256) knn_assign_kernel(const float* __restrict__ points, long long N,
-                                                         const float* __restrict__ centres, int F, int K, float radius,
+                                                         const float* __restrict__ centres, int F, int K_rt, float radius,
                                                          float distance_factor, int* __restrict__ pair_field,
                                                          float* __restrict__ pair_w, int* __restrict__ counts) {
   __shared__ float sc[kCentreChunk * 3];
+  constexpr int KM = KT > 0 ? KT : kMaxK;
+  const int K = KT > 0 ? KT : K_rt;
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const bool live = i < N;
   float px = 0.f, py = 0.f, pz = 0.f;
   if (live) { px = __ldg(points + i * 3); py = __ldg(points + i * 3 + 1); pz = __ldg(points + i * 3 + 2); }
-  float bd[kMaxK];
-  int bi[kMaxK];
+  float bd[KM];
+  int bi[KM];
 #pragma unroll
-  for (int j = 0; j < kMaxK; ++j) { bd[j] = INFINITY; bi[j] = -1; }
+  for (int j = 0; j < KM; ++j) { bd[j] = INFINITY; bi[j] = -1; }
   for (int c0 = 0; c0 < F; c0 += kCentreChunk) {
     const int cn = min(kCentreChunk, F - c0);
     __syncthreads();
@@ -108,7 +113,7 @@ __global__ void __launch_bounds__(256) knn_assign_kernel(const float* __restrict
         float cd = d2;
         int ci = c0 + c;
 #pragma unroll
-        for (int j = 0; j < kMaxK; ++j) {
+        for (int j = 0; j < KM; ++j) {
           if (j < K && cd < bd[j]) {
             const float td = bd[j]; const int ti = bi[j];
             bd[j] = cd; bi[j] = ci;
@@ -121,16 +126,16 @@ __global__ void __launch_bounds__(256) knn_assign_kernel(const float* __restrict
   const float d0 = sqrtf(bd[0]);
   const bool inside = live && d0 < radius;  // models.py:369: only the nearest centre is tested
   // softmax(-distance_factor * d) over the K neighbours (models.py:384)
-  float logit[kMaxK], m = -INFINITY;
+  float logit[KM], m = -INFINITY;
 #pragma unroll
-  for (int j = 0; j < kMaxK; ++j)
+  for (int j = 0; j < KM; ++j)
     if (j < K) { logit[j] = -distance_factor * sqrtf(bd[j]); m = fmaxf(m, logit[j]); }
   float sum = 0.f;
 #pragma unroll
-  for (int j = 0; j < kMaxK; ++j)
+  for (int j = 0; j < KM; ++j)
     if (j < K) { logit[j] = expf(logit[j] - m); sum += logit[j]; }
 #pragma unroll
-  for (int j = 0; j < kMaxK; ++j) {
+  for (int j = 0; j < KM; ++j) {
     if (j < K) {  // K is warp-uniform: every lane reaches the warp collective
       if (live) {
         pair_field[i * K + j] = inside ? bi[j] : -1;
@@ -232,7 +237,9 @@ int launch_fieldset_knn(const NgmKnnFwdArgs& a, cudaStream_t stream) {
   const KnnWs w = carve(a.workspace, N, K, F, tc_bytes_of(a), row_bytes);
   NGM_CUDA(cudaMemsetAsync(w.counts, 0, (size_t)(F + 1) * sizeof(int), stream));
   const unsigned pb = (unsigned)((N + 255) / 256);
-  knn_assign_kernel<<<pb, 256, 0, stream>>>(a.points, N, a.positions, F, K, a.field_radius, a.distance_factor,
+  auto assign = K == 1 ? knn_assign_kernel<1> : K == 2 ? knn_assign_kernel<2> : K == 3 ? knn_assign_kernel<3>
+                                                                          : K == 4 ? knn_assign_kernel<4> : knn_assign_kernel<0>;
+  assign<<<pb, 256, 0, stream>>>(a.points, N, a.positions, F, K, a.field_radius, a.distance_factor,
                                             w.pair_field, w.pair_w, w.counts);
   if (int rc = check_launch("knn_assign_kernel")) return rc;
   knn_scan_kernel<<<1, 1024, 0, stream>>>(w.counts, F, w.entry_offsets, w.tile_offsets, w.cursors);

@@ -201,3 +201,30 @@ def render_rays_split(driver, ijs, c2ws, camera, field_ids, near=None, far=None,
     parts = [packed_views(res[r], F * Rs) for r in range(res.shape[0])]
     cat = lambda i, tail: torch.cat([p[i].view(F, Rs, *tail) for p in parts], 1)  # noqa: E731
     return Prediction(cat(0, (4,)), cat(1, (3,)), cat(2, ()), cat(3, ()), None, None)
+
+
+def render_image_sharded(driver, c2w: torch.Tensor, camera, group=None, seed: Optional[int] = None):
+    """``render_image`` (ngm/run_mapping.py:402-437: full frame through the kNN path over ALL fields) with the pixel
+    rows split over the ranks and one all-gather of the (rgbd, depth variance) tiles -- the re-render of BASELINE
+    config 5 (after a pose-graph update only two small tensors, the field positions / orientations, have changed; every
+    rank holds all field parameters).  All ranks use one jitter seed and global sample indices, so the frame equals
+    the single-GPU frame rendered with that seed.  Returns (rgbds (H, W, 4), depth_vars (H, W)) on every rank."""
+    world, rank = world_info(group)
+    h, w = camera.height, camera.width
+    if h % world != 0:
+        raise ValueError(f"image height {h} must be divisible by the world size {world}")
+    dev = driver._device
+    r0, r1 = shard_range(h, world, rank)
+    if seed is None:
+        seed = shared_seed(torch.device(dev), group)
+    ijs = torch.cartesian_prod(torch.arange(r0, r1, device=dev), torch.arange(w, device=dev))
+    with torch.no_grad():
+        p = render_rays(driver, ijs, c2w, camera, seed=seed, sample_offset=r0 * w * int(driver._num_samples))
+    n = (r1 - r0) * w
+    local = torch.empty(5 * n, device=ijs.device, dtype=torch.float32)
+    local[:4 * n].view(n, 4).copy_(p.rgbds)
+    local[4 * n:].copy_(p.depth_vars)
+    buf = gather_tiles(local, group)
+    rgbd = torch.cat([buf[r, :4 * n].view(r1 - r0, w, 4) for r in range(buf.shape[0])])
+    dvar = torch.cat([buf[r, 4 * n:].view(r1 - r0, w) for r in range(buf.shape[0])])
+    return rgbd, dvar

@@ -11,6 +11,10 @@ from . import _lib, models
 from .camera import sample_rays
 
 
+POINT_BLOCK_BYTES = 6 << 30
+POINT_BYTES = 160  # pair tables, bucketed entries, per-pair outputs (K = 2) + fp16 rows of the widest row encoding
+
+
 def fieldset_forward_knn(model, query_points, field_positions, field_orientations, field_ids, field_radius,
                          precision=None):
     """``ngm_fieldset_knn_fwd``: (..., 3) world points -> (..., 4).  ``precision`` "fp16" evaluates the
@@ -55,7 +59,7 @@ def fieldset_forward_knn(model, query_points, field_positions, field_orientation
     return out.reshape(*leading, 4)
 
 
-def render_rays_knn(driver, ijs, c2ws, camera, field_ids, near, far, gt, overwrite, jitter):
+def render_rays_knn(driver, ijs, c2ws, camera, field_ids, near, far, gt, overwrite, jitter, seed=None, sample_offset=0):
     """``_render_ijs`` with use_vmap=False (ngm/run_mapping.py:586-595): sampler stage -> kNN
     field set (in blocks of ``_block_size`` points, like utils.batched_evaluation) -> compositor."""
     from .renderer import Prediction, _next_seed, _overwrite_gate, _precision, composite
@@ -77,14 +81,21 @@ def render_rays_knn(driver, ijs, c2ws, camera, field_ids, near, far, gt, overwri
             camera, ijs, S, driver._near_distance if near is None else near,
             driver._far_distance if far is None else far, gt=gt, num_samples_guided=G,
             range_guided=float(driver._range_depth_guided or 0.0), c2ws=c2ws, jitter=jitter,
-            seed=0 if jitter is not None else _next_seed(), want_world=True, want_depth=True, want_cam=False)
+            seed=0 if jitter is not None else (_next_seed() if seed is None else int(seed)), offset=int(sample_offset),
+            want_world=True, want_depth=True, want_cam=False)
         St = dist.shape[-1]
         pts = world.reshape(-1, 3)
-        outs = []
-        for s0 in range(0, pts.shape[0], int(driver._block_size)):
-            outs.append(fieldset_forward_knn(model, pts[s0:s0 + int(driver._block_size)], positions, orientations,
-                                             field_ids, None, _precision(driver)))
-        o = torch.cat(outs) if len(outs) > 1 else outs[0]
+        # The reference evaluates the field set in blocks of `block_size` (3 M) points to bound the memory of its
+        # PyTorch intermediates (run_mapping.py:588).  Points are independent; the CUDA path holds ~150 B per point in
+        # flight, so its blocks are as large as POINT_BLOCK_BYTES allows and never smaller than the configured size.
+        block = max(int(driver._block_size), POINT_BLOCK_BYTES // POINT_BYTES)
+        if pts.shape[0] <= block:
+            o = fieldset_forward_knn(model, pts, positions, orientations, field_ids, None, _precision(driver))
+        else:
+            o = torch.empty(pts.shape[0], 4, device=pts.device)
+            for s0 in range(0, pts.shape[0], block):
+                o[s0:s0 + block] = fieldset_forward_knn(model, pts[s0:s0 + block], positions, orientations, field_ids,
+                                                        None, _precision(driver))
         n = dist.numel() // St
         gt_t = None if gt is None else _lib.dev_f32(gt, "gt").expand(leading).reshape(-1).contiguous()
         want_fs = driver._freespace_weight != 0.0 and gt is not None

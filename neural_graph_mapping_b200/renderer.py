@@ -104,7 +104,7 @@ def render_rays(
         from .knn import render_rays_knn
 
         return render_rays_knn(driver, ijs, c2ws, camera, field_ids, near_distances, far_distances,
-                               gt_distances, overwrite, jitter)
+                               gt_distances, overwrite, jitter, seed, sample_offset)
 
     model = driver._model
     dev = ijs.device

@@ -75,6 +75,16 @@ def _worker(rank, world, port, tmpdir):
         buf = pend.wait()
         torch.cuda.synchronize()
         assert buf.shape[0] == world and torch.equal(buf[rank], pend.local)
+        # config-5 re-render: full frame through the kNN path, pixel rows split over the ranks, one shared seed
+        small = ngm.Camera(width=64, height=48, fx=55.4, fy=55.4, cx=31.5, cy=23.5)
+        st.eval()
+        with torch.no_grad():
+            seed = D.shared_seed(torch.device(dev))
+            rgbd_s, dvar_s = D.render_image_sharded(st, c2w, small, seed=seed)
+            ij = torch.cartesian_prod(torch.arange(48, device=dev), torch.arange(64, device=dev))
+            whole = st._render_ijs(ij, c2w, small, seed=seed)
+        st.train()
+        assert torch.equal(rgbd_s.view(-1, 4), whole.rgbds) and torch.equal(dvar_s.view(-1), whole.depth_vars), prec
     dist.barrier()
     dist.destroy_process_group()
 
