@@ -227,36 +227,46 @@ class MappingLoop(RenderState):
 
     # ---- losses (run_mapping.py:1769-1871; ngm/losses.py:10-78) ----
     def _compute_losses(self, target, prediction) -> dict:
-        depth_mask = target.depth_mask * (prediction.term_probs > 0.8)
-        rgb_mask = depth_mask
+        """The reference's loss terms.  The reference compacts every masked operand first (`x[mask]`, a nonzero +
+        gather + a sorting index_put in the backward: ~60 small launches per iteration) and then takes means; the
+        same means are computed here as masked sums over the dense tensors divided by the mask count -- equal up to
+        the order of the floating-point sums, NaN for an empty mask exactly like `mean()` of an empty tensor."""
+        depth_mask = target.depth_mask * (prediction.term_probs > 0.8)  # :1787
+        rgb_mask = depth_mask                                           # :1788
         out = {}
-        term = ((prediction.term_probs[target.term_mask] - target.term_probs[target.term_mask]) ** 2).mean()
+
+        def masked_mean(x, m, per_element=1):
+            return (x * m).sum() / (m.sum() * per_element)
+
+        tm = target.term_mask.float()
+        term = masked_mean((prediction.term_probs - target.term_probs) ** 2, tm)  # :1803-1806
         combined = 0 + self._termination_weight * term
         out["termination"] = term
-        p_rgb, t_rgb = prediction.rgbds[rgb_mask][:, :3], target.rgbds[rgb_mask][:, :3]
-        if self._photometric_loss == "l1":
-            photo = torch.mean(torch.abs(p_rgb - t_rgb))
-        elif self._photometric_loss == "l2":
-            photo = torch.mean((p_rgb - t_rgb) ** 2)
+        m = rgb_mask.float()
+        p_rgb, t_rgb = prediction.rgbds[..., :3], target.rgbds[..., :3]
+        if self._photometric_loss == "l1":      # losses.py:22-23
+            photo = masked_mean(torch.abs(p_rgb - t_rgb), m[..., None], 3)
+        elif self._photometric_loss == "l2":    # losses.py:24-25
+            photo = masked_mean((p_rgb - t_rgb) ** 2, m[..., None], 3)
         else:
             raise NotImplementedError(f"photometric_loss={self._photometric_loss}")
         combined = combined + self._photometric_weight * photo
         out[f"photometric_{self._photometric_loss}"] = photo
-        t_d, p_d = target.rgbds[depth_mask][:, 3], prediction.rgbds[depth_mask][:, 3]
-        if self._depth_loss == "huber":
-            dl = torch.nn.functional.huber_loss(p_d, t_d, delta=0.05)
-        elif self._depth_loss == "gaussian_nll":
-            v = prediction.depth_vars[depth_mask] + 1e-15
-            dl = (0.5 * (p_d - t_d) ** 2 / v + torch.log(torch.sqrt(v))).mean()
+        t_d, p_d = target.rgbds[..., 3], prediction.rgbds[..., 3]
+        if self._depth_loss == "huber":         # losses.py:60-61: F.huber_loss(rendered, measured, delta=0.05)
+            dl = masked_mean(torch.nn.functional.huber_loss(p_d, t_d, delta=0.05, reduction="none"), m)
+        elif self._depth_loss == "gaussian_nll":  # losses.py:62-67
+            v = prediction.depth_vars + 1e-15
+            dl = masked_mean(0.5 * (p_d - t_d) ** 2 / v + torch.log(torch.sqrt(v)), m)
         else:
             raise NotImplementedError(f"depth_loss={self._depth_loss}")
         combined = combined + self._depth_weight * dl
         out[f"depth_{self._depth_loss}"] = dl
-        if prediction.freespace_geometry is not None:
+        if prediction.freespace_geometry is not None:  # :1842-1846
             fs = ((prediction.freespace_geometry - self._truncation_distance) ** 2).mean()
             combined = combined + self._freespace_weight * fs
             out["freespace"] = fs
-        if prediction.tsdf_residuals is not None:
+        if prediction.tsdf_residuals is not None:      # :1848-1851
             ts = (prediction.tsdf_residuals ** 2).mean()
             combined = combined + self._tsdf_weight * ts
             out["tsdf"] = ts

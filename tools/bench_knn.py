@@ -21,6 +21,9 @@ dev = "cuda:0"
 cam = ngm.Camera(**bench.CAMERA)
 runs = [("nerf8_4x128", "fp16", 5), ("nerf8_4x128", "fp32", 1),
         ("permuto_1x32 (reference default field)", "fp16", 3), ("permuto_1x32 (reference default field)", "fp32", 3)]
+if "--only" in sys.argv:  # e.g. --only nerf8_4x128:fp16 (profiling one configuration under ncu)
+    v_, p_ = sys.argv[sys.argv.index("--only") + 1].split(":")
+    runs = [r for r in runs if r[0].startswith(v_) and r[1] == p_]
 for variant, prec, reps in runs:
     enc, ekw, E, L, W = bv.VARIANTS[variant]
     sc = bv.scene(E, L, W, enc)
@@ -49,6 +52,8 @@ for variant, prec, reps in runs:
                       "inside_fraction": round(float((p.term_probs > 0).float().mean()), 3)}), flush=True)
 
 
+if "--only" in sys.argv:
+    sys.exit(0)
 # render_image (the driver's call, run_mapping.py:402-437): whole 640x480 frame, reference block size vs ours
 from neural_graph_mapping_b200 import renderer  # noqa: E402
 
