@@ -24,6 +24,11 @@ int ngm_debug_tc_trace(uint64_t* host_out, int max_events);
 /* same without synchronising the device (reads the trace of a still-running kernel; deadlock diagnosis) */
 int ngm_debug_tc_trace_peek(uint64_t* host_out, int max_events);
 
+/* diagnostics: cycles CTA 0 of the tcgen05 backward launches spent per phase since the last call (16 counters:
+ * row thread 0 front end, 1 wait previous dW, 2 wait forward MMA, 3 forward epilogue, 4 wait chain MMA, 5 chain epilogue,
+ * 6 wait dW, 7 store + arrive, 8 flush; issuer 10 wait for operands, 11 issue); synchronises the device. */
+int ngm_debug_bwd_phases(uint64_t* host_out16);
+
 #ifdef __cplusplus
 }
 #endif

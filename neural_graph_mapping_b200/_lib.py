@@ -228,6 +228,8 @@ def load_debug_lib():
     dbg.ngm_debug_tc_trace_peek.argtypes = [C.c_void_p, C.c_int]
     dbg.ngm_debug_tc_trace.restype = C.c_int
     dbg.ngm_debug_tc_trace.argtypes = [C.c_void_p, C.c_int]
+    dbg.ngm_debug_bwd_phases.restype = C.c_int
+    dbg.ngm_debug_bwd_phases.argtypes = [C.c_void_p]
     dbg.ngm_debug_tc_gemm.restype = C.c_int
     dbg.ngm_debug_tc_gemm.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p,
                                       C.c_void_p, C.c_size_t, C.c_void_p]

@@ -58,6 +58,7 @@ int launch_tc_gemm_debug(const NgmFieldDesc& fd, const void* a_half, long long r
                          cudaStream_t stream);
 int tc_trace_read(unsigned long long* out, int max_events);
 int tc_trace_peek(unsigned long long* out, int max_events);
+int bwd_phases_read(unsigned long long* out16);
 #endif
 
 size_t knn_workspace_bytes(const NgmKnnFwdArgs& a);
@@ -436,6 +437,11 @@ int ngm_fieldset_knn_fwd(const NgmKnnFwdArgs* a, void* stream) {
 int ngm_debug_tc_trace_peek(uint64_t* host_out, int max_events) {
   NGM_CHECK_ARG(host_out && max_events > 0, "null args");
   return tc_trace_peek(reinterpret_cast<unsigned long long*>(host_out), max_events);
+}
+
+int ngm_debug_bwd_phases(uint64_t* host_out16) {
+  NGM_CHECK_ARG(host_out16 != nullptr, "null args");
+  return bwd_phases_read(reinterpret_cast<unsigned long long*>(host_out16));
 }
 
 int ngm_debug_tc_trace(uint64_t* host_out, int max_events) {

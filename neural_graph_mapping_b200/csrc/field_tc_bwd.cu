@@ -92,6 +92,24 @@ struct BwdSmem {
 
 __device__ __forceinline__ int in_dim(const BwdParams& p, int l) { return l == 0 ? p.EP : p.W; }
 
+// Phase accounting (diagnostics build only): CTA 0's issuer lane and one row thread add the cycles they spend in each
+// phase to a global table, read back with ngm_debug_bwd_phases.
+//   row thread: 0 front end, 1 wait prev dW, 2 wait forward MMA, 3 forward epilogue, 4 wait chain MMA, 5 chain epilogue,
+//               6 wait dW of this step, 7 store + arrive, 8 flush;   issuer: 10 wait for operands, 11 issue
+#ifdef NGM_DEBUG_EXPORTS
+__device__ unsigned long long g_bwd_phase[16];
+#define BWD_PHASE_INIT const bool ph_on = blockIdx.x == 0 && (threadIdx.x == 0 || threadIdx.x == 32); long long ph_t = clock64();
+#define BWD_PHASE(i)                                                                      \
+  if (ph_on) {                                                                            \
+    const long long now_ = clock64();                                                     \
+    atomicAdd(&g_bwd_phase[i], (unsigned long long)(now_ - ph_t));                        \
+    ph_t = now_;                                                                          \
+  }
+#else
+#define BWD_PHASE_INIT
+#define BWD_PHASE(i)
+#endif
+
 // K-major SWIZZLE_128B operand (weights forward, g_out^T, ones): k-step ks of 16 halves
 __device__ __forceinline__ uint64_t kmajor_step(uint64_t desc0, int ks, uint32_t atom_stride16) {
   return desc0 + (uint64_t)((ks & 3) * 2u + (ks >> 2) * atom_stride16);
@@ -293,6 +311,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_kernel(const BwdParams p) 
     }
   }
 
+  BWD_PHASE_INIT
   const long long total_tiles = p.total_tiles;
   const long long t_begin = total_tiles * blockIdx.x / gridDim.x;
   const long long t_end = total_tiles * (blockIdx.x + 1) / gridDim.x;
@@ -332,7 +351,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_kernel(const BwdParams p) 
 #pragma unroll
         for (int l = 0; l < L; ++l) {  // forward recompute (only up to h_hi when the chain starts from a spilled gradient)
           if (l < fwd_layers) {
+            BWD_PHASE(11)
             ptx::mbar_wait_spin(&sm.a_ready, pa);
+            BWD_PHASE(10)
             pa ^= 1;
             ptx::tc_fence_after();
             if (ptx::elect_one()) {
@@ -345,7 +366,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_kernel(const BwdParams p) 
 #pragma unroll
         for (int l = L; l >= 0; --l) {  // backward step l: chain to g_l, weight gradient of linear l
           if (l >= lo && l <= top) {
+            BWD_PHASE(11)
             ptx::mbar_wait_spin(&sm.a_ready, pa);
+            BWD_PHASE(10)
             pa ^= 1;
             ptx::tc_fence_after();
             const bool chain = l > lo || (l == lo && lo >= 1 && p.plan.emit_g) || (l == 0 && p.plan.want_denc);
@@ -438,11 +461,13 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_kernel(const BwdParams p) 
         uint8_t* g_buf = acts + p.plan.buf_off[top + 1 <= L ? top + 1 : L];
         if (p.plan.g_in && fwd_layers == 0) fetch_spill(g_src, gin, CPT);
         // the previous tile's last weight-gradient group reads the buffers this tile is about to overwrite
+        BWD_PHASE(0)
         if (dw_pending) {
           ptx::mbar_wait_lean(&sm.dw_done, pdw);
           pdw ^= 1;
           dw_pending = false;
         }
+        BWD_PHASE(1)
         ptx::tc_fence_after();
         if (h == 0) {
           if (fwd_layers > 0) {
@@ -460,6 +485,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_kernel(const BwdParams p) 
         ptx::fence_proxy_async();
         ptx::tc_fence_before();
         ptx::mbar_arrive(&sm.a_ready);
+        BWD_PHASE(0)
 
         // ---- forward recompute ----
 #pragma unroll
@@ -467,6 +493,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_kernel(const BwdParams p) 
           if (l >= fwd_layers) continue;
           if (p.plan.g_in && l + 1 == fwd_layers) fetch_spill(g_src, gin, CPT);
           ptx::mbar_wait_lean(&sm.d_ready, pd);
+          BWD_PHASE(2)
           pd ^= 1;
           ptx::tc_fence_after();
           const int j = l + 1;  // this epilogue produces h_j
@@ -506,6 +533,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_kernel(const BwdParams p) 
           ptx::fence_proxy_async();
           ptx::tc_fence_before();
           ptx::mbar_arrive(&sm.a_ready);
+          BWD_PHASE(3)
         }
 
         // ---- backward chain ----
@@ -517,6 +545,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_kernel(const BwdParams p) 
             const bool dw = l <= hi;
             if (chain) {
               ptx::mbar_wait_lean(&sm.d_ready, pd);
+              BWD_PHASE(4)
               pd ^= 1;
               ptx::tc_fence_after();
             }
@@ -544,10 +573,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_kernel(const BwdParams p) 
                 ptx::tmem_st16(a_addr + c0 / 2, wg);
                 if (CPT == 64) ptx::tmem_st16(a_addr + c0 / 2 + 16, wg + 16);
               }
+              BWD_PHASE(5)
               if (dw) {  // dW_l of this step reads h_l: wait before overwriting it
                 ptx::mbar_wait_lean(&sm.dw_done, pdw);
                 pdw ^= 1;
               }
+              BWD_PHASE(6)
               if (l - 1 <= hi) {  // dW_{l-1} is accumulated by this launch: it needs g_l in shared memory
                 uint8_t* sbuf = acts + p.plan.buf_off[l];
                 store_row_words16(sbuf, row, c0, wg);
@@ -557,6 +588,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_kernel(const BwdParams p) 
               ptx::fence_proxy_async();
               ptx::tc_fence_before();
               ptx::mbar_arrive(&sm.a_ready);
+              BWD_PHASE(7)
             } else {
               // l == lo: nothing feeds a further step
               if (l == 0 && chain) {  // dLoss/d h_0 rows -> HBM (gradient of the encoding's parameters)
@@ -580,6 +612,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_kernel(const BwdParams p) 
       }
 
       // ---- flush the accumulators of this field segment ----
+      BWD_PHASE(5)
       if (dw_pending) {
         ptx::mbar_wait_lean(&sm.dw_done, pdw);
         pdw ^= 1;
@@ -632,6 +665,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_kernel(const BwdParams p) 
         }
       }
       ptx::tc_fence_before();
+      BWD_PHASE(8)
     }
     w_phase ^= 1;
     t = seg_end;
@@ -723,6 +757,17 @@ int launch_bwd_l(const BwdParams& p, size_t smem, int grid, cudaStream_t stream)
 }
 
 }  // namespace
+
+#ifdef NGM_DEBUG_EXPORTS
+// diagnostics: read (and clear) the phase table of CTA 0 (synchronises the device)
+int bwd_phases_read(unsigned long long* out16) {
+  if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+  if (cudaMemcpyFromSymbol(out16, g_bwd_phase, sizeof(unsigned long long) * 16) != cudaSuccess) return -1;
+  unsigned long long zero[16] = {0};
+  if (cudaMemcpyToSymbol(g_bwd_phase, zero, sizeof(zero)) != cudaSuccess) return -1;
+  return 16;
+}
+#endif
 
 bool field_bwd_tc_supported(const NgmFieldDesc& fd, const char** why) {
   const char* w = nullptr;
