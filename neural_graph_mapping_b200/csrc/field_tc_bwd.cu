@@ -25,6 +25,10 @@
 // to fp16 -- mean-reduced losses give |g_out| ~ 1e-7, far below the fp16 range -- and the accumulators are unscaled
 // by 1/s when they are flushed.  The ReLU mask of a layer is re-derived from its stored activation (h > 0).
 //
+// Measured dead ends (tools/bwd_phases.py, config-4 shard): two accumulator loads in flight (spills at the 168-register
+// cap of a 9-warp CTA), spinning row threads (they starve the issuer warp's MMA issue: +4 %), loading the next tile's
+// point / upstream gradient one tile ahead (+5 %: the extra live registers cost more than the hidden latency).
+//
 // TMEM (512 columns): [0,128) chain/forward accumulator, [128,192) fp16 A operand, the rest weight / bias gradient
 // accumulators.  Three 128x128 fp32 accumulators do not fit next to those, so a 4-layer x 128 field is processed in
 // two launches (linears {4,3,2}, then {1,0}); each launch recomputes the forward and as much of the chain as it needs.
@@ -95,7 +99,7 @@ __device__ __forceinline__ int in_dim(const BwdParams& p, int l) { return l == 0
 // Phase accounting (diagnostics build only): CTA 0's issuer lane and one row thread add the cycles they spend in each
 // phase to a global table, read back with ngm_debug_bwd_phases.
 //   row thread: 0 front end, 1 wait prev dW, 2 wait forward MMA, 3 forward epilogue, 4 wait chain MMA, 5 chain epilogue,
-//               6 wait dW of this step, 7 store + arrive, 8 flush;   issuer: 10 wait for operands, 11 issue
+//               6 wait dW of this step, 7 store + arrive, 8 flush, 9 spill epilogue;   issuer: 10 wait for operands, 11 issue
 #ifdef NGM_DEBUG_EXPORTS
 __device__ unsigned long long g_bwd_phase[16];
 #define BWD_PHASE_INIT const bool ph_on = blockIdx.x == 0 && (threadIdx.x == 0 || threadIdx.x == 32); long long ph_t = clock64();
@@ -561,6 +565,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_kernel(const BwdParams p) 
                 if (k < CPT / 8) __stcs(dst + k, make_uint4(wg[4 * k], wg[4 * k + 1], wg[4 * k + 2], wg[4 * k + 3]));
               ptx::tc_fence_before();
               if (dw) dw_pending = true;
+              BWD_PHASE(9)
             } else if (l >= 1 && chain) {
               // g_l = D .* mask(h_l): A operand of the next chain step, and (in place over h_l) operand of dW_{l-1}
               uint32_t wg[32];

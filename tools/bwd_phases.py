@@ -26,13 +26,13 @@ dz = {k: sc[k].to(dev) for k in ("ijs", "c2w", "near", "far", "field_ids")}
 dbg = _lib.load_debug_lib()
 buf = (C.c_uint64 * 16)()
 NAMES = {0: "front end", 1: "wait previous tile's dW", 2: "wait forward MMA", 3: "forward epilogue (+arrive)", 4: "wait chain MMA",
-         5: "chain epilogue", 6: "wait this step's dW", 7: "store g + arrive", 8: "flush", 10: "issuer: wait for operands",
+         5: "chain epilogue", 6: "wait this step's dW", 7: "store g + arrive", 8: "flush", 9: "spill epilogue (g_lo -> HBM)", 10: "issuer: wait for operands",
          11: "issuer: issue"}
 for it in range(3):
     p = st._render_ijs(dz["ijs"], dz["c2w"], cam, dz["field_ids"], True, dz["near"], dz["far"])
     (p.rgbds.square().mean() + p.depth_vars.mean()).backward()
     dbg.ngm_debug_bwd_phases(buf)
-tot_row = sum(buf[i] for i in range(9))
+tot_row = sum(buf[i] for i in range(10))
 tiles = F * R * S // 128 // 148
 print(f"CTA 0, {tiles} tiles per launch pass (2 groups x 2 launches); row-thread cycles {tot_row}, per tile {tot_row / tiles:.0f}")
 for i, n in NAMES.items():
