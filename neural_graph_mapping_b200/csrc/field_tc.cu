@@ -105,6 +105,22 @@ struct TcParams {
   int acc16;  // hidden layers accumulate in fp16 inside the tensor core (NGM_TC_ACC16=1): packed accumulator loads
 };
 
+// Arrivals on the slot barriers: one per warp (lane 0 after a __syncwarp; each lane has ordered its own tcgen05 / shared
+// memory accesses before the warp barrier) instead of one per thread -- 8 arrivals per phase instead of 256.
+#ifdef NGM_WARP_ARRIVE
+constexpr int kArrivalsPerWarp = 1;
+#else
+constexpr int kArrivalsPerWarp = 32;
+#endif
+__device__ __forceinline__ void slot_arrive(uint64_t* bar) {
+  if (kArrivalsPerWarp == 1) {
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) ptx::mbar_arrive(bar);
+  } else {
+    ptx::mbar_arrive(bar);
+  }
+}
+
 constexpr int kMaxRaysPerTile = 16;  // Sp >= 8
 constexpr int kRayFloats = 12;       // o_local[3], dir_local[3], zscale, near, far, gt, valid, pad
 
@@ -491,14 +507,14 @@ __global__ void __launch_bounds__(threads_of(MODE), 1) tc_kernel(const TcParams 
       // 128 front-end stores + 128 compositor threads that drained the accumulator.  No parity aliasing on d_ready:
       // the compositor threads arrive only after the slot-wide named barrier that follows the last-layer wait, so
       // the next tile's layer 0 cannot complete before all 256 slot threads have observed the last-layer phase.
-      ptx::mbar_init(&sm.a0_ready[s], 256);
-      ptx::mbar_init(&sm.a_ready[s], 256);
+      ptx::mbar_init(&sm.a0_ready[s], 8 * kArrivalsPerWarp);
+      ptx::mbar_init(&sm.a_ready[s], 8 * kArrivalsPerWarp);
       ptx::mbar_init(&sm.d_ready[s], 1);
     }
     ptx::mbar_init(&sm.w_ready, 1);
     for (int i = 0; i < 8; ++i) {
       ptx::mbar_init(&sm.ray_full[i >> 2][i & 3], 32);
-      ptx::mbar_init(&sm.ray_empty[i >> 2][i & 3], 128);
+      ptx::mbar_init(&sm.ray_empty[i >> 2][i & 3], 4 * kArrivalsPerWarp);
     }
     ptx::fence_mbar_init();
   }
@@ -735,7 +751,7 @@ __global__ void __launch_bounds__(threads_of(MODE), 1) tc_kernel(const TcParams 
         }
         ptx::tc_wait_st();
         ptx::tc_fence_before();
-        ptx::mbar_arrive(&sm.a0_ready[s]);
+        slot_arrive(&sm.a0_ready[s]);
         tev(ev_id(1, s, 2, 0));
       };
       // permutohedral front end: the 16 x 4 table gathers of a row are spread over the waits of up to four
@@ -749,7 +765,7 @@ __global__ void __launch_bounds__(threads_of(MODE), 1) tc_kernel(const TcParams 
           encode_permuto_tail(p, a0_addr, fx);
           ptx::tc_wait_st();
           ptx::tc_fence_before();
-          ptx::mbar_arrive(&sm.a0_ready[s]);
+          slot_arrive(&sm.a0_ready[s]);
           tev(ev_id(1, s, 2, 0));
         }
       };
@@ -788,7 +804,7 @@ __global__ void __launch_bounds__(threads_of(MODE), 1) tc_kernel(const TcParams 
               }
               ptx::tc_wait_st();
               ptx::tc_fence_before();
-              ptx::mbar_arrive(&sm.a_ready[s]);
+              slot_arrive(&sm.a_ready[s]);
               tev(ev_id(1 + (h == 0), s, 4, l));
             } else {
               // ---------- last layer ----------
@@ -816,7 +832,7 @@ __global__ void __launch_bounds__(threads_of(MODE), 1) tc_kernel(const TcParams 
                     }
                   }
                   ptx::tc_fence_before();
-                  if (has_next) ptx::mbar_arrive(&sm.a0_ready[s]);
+                  if (has_next) slot_arrive(&sm.a0_ready[s]);
                 } else {
                   uint32_t v[4];
                   ptx::tmem_ld4(d_addr, v);
@@ -828,10 +844,10 @@ __global__ void __launch_bounds__(threads_of(MODE), 1) tc_kernel(const TcParams 
                   sm.comp[s][5][row] = dz.y;
                   sm.comp[s][6][row] = rp[9];
                   sm.comp[s][7][row] = rp[10];
-                  ptx::mbar_arrive(&sm.ray_empty[s][ring]);  // the producer may refill this ring entry
+                  slot_arrive(&sm.ray_empty[s][ring]);  // the producer may refill this ring entry
                   ptx::tc_wait_ld();
                   ptx::tc_fence_before();
-                  if (has_next) ptx::mbar_arrive(&sm.a0_ready[s]);  // the next layer-0 MMA may overwrite the accumulator
+                  if (has_next) slot_arrive(&sm.a0_ready[s]);  // the next layer-0 MMA may overwrite the accumulator
                   sm.comp[s][0][row] = p.color_factor * (__uint_as_float(v[0]) + bias_last[0]);
                   sm.comp[s][1][row] = p.color_factor * (__uint_as_float(v[1]) + bias_last[1]);
                   sm.comp[s][2][row] = p.color_factor * (__uint_as_float(v[2]) + bias_last[2]);
@@ -843,7 +859,7 @@ __global__ void __launch_bounds__(threads_of(MODE), 1) tc_kernel(const TcParams 
               }
             }
           } else if (h == 0) {
-            if (has_next) ptx::mbar_arrive(&sm.a0_ready[s]);  // first tile: no accumulator to drain
+            if (has_next) slot_arrive(&sm.a0_ready[s]);  // first tile: no accumulator to drain
           }
           if (h == 1 && has_next) {
             if (l == 0) fe_a(ti + 2, ray_n + 1, npar);
