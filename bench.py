@@ -385,6 +385,20 @@ def main():
     pending = [None, None]
     counter = [0]
 
+    # The exchange fused into the render kernel (distributed.TileExchange: mirrored stores over NVSwitch multicast /
+    # NVLink peer memory + a signal-pad barrier) replaces the NCCL all-gather when symmetric memory is available AND
+    # one step through it equals the NCCL all-gather of the same step bit for bit on every rank.
+    ex_dev = ex_e2e = None
+    exchange_info = None
+    if world > 1:
+        exchange_info = {"mode": "nccl all-gather"}
+        if os.environ.get("NGM_BENCH_EXCHANGE", "fused") == "fused":
+            try:
+                ex_dev, ex_e2e, exchange_info = fused_exchange(distributed, st, dz, cam, dev, rays_per_step, bufs[0])
+            except Exception as e:
+                ex_dev = ex_e2e = None
+                exchange_info = {"mode": "nccl all-gather", "fused_unavailable": f"{type(e).__name__}: {e}"[:300]}
+
     def step_resident():
         i = counter[0] & 1
         counter[0] += 1
@@ -392,7 +406,7 @@ def main():
             pending[i].wait()
         with torch.no_grad():
             pending[i] = distributed.render_rays_gathered(st, dz["ijs"], dz["c2w"], cam, dz["field_ids"], dz["near"],
-                                                          dz["far"], async_gather=True, buffers=bufs[i])
+                                                          dz["far"], async_gather=True, buffers=bufs[i], exchange=ex_dev)
 
     def drain():
         for i in range(2):
@@ -461,7 +475,7 @@ def main():
                 d = {k: hz[k].to(dev, non_blocking=True) for k in hz}
                 flush.fill_(1)
                 pend[b] = distributed.render_rays_gathered(st, d["ijs"], d["c2w"], cam, dz["field_ids"], d["near"], d["far"],
-                                                           async_gather=True, buffers=e_bufs[b])
+                                                           async_gather=True, buffers=e_bufs[b], exchange=ex_e2e)
                 h_outs[b].copy_(pend[b].local, non_blocking=True)
 
         def finish():
@@ -493,8 +507,8 @@ def main():
     e2e_seq_ms = timed_e2e(max(args.steps // 4, 3), args.warmup, 1) / max(args.steps // 4, 3)
     e2e_ms = timed_e2e(args.steps, args.warmup, 2) / args.steps
     e2e_mode = ("2 CUDA streams, steps alternate: step i+1's H2D and step i-1's D2H overlap step i's render; every rank "
-                "copies its rays H2D and ITS OWN rendered tile D2H each step; the NCCL all-gather of the tiles stays in "
-                "flight behind the next step; one device-timed bracket around all steps (L2 flushes included), max over ranks")
+                "copies its rays H2D and ITS OWN rendered tile D2H each step; the exchange of the tiles (config.parallelism) stays "
+                "in flight behind the next step; one device-timed bracket around all steps (L2 flushes included), max over ranks")
     e2e_value = world * rays_per_step / (e2e_ms / 1e3)
 
     # ---- roofline of the dominant kernel (field MLP; tensor-bound), measured live with events ----
@@ -539,8 +553,12 @@ def main():
                             "encoding (E=48), 75 fields x 4096 rays per keyframe, nrgbd compositing; one keyframe per GPU",
                 "rays_per_step_per_gpu": rays_per_step, "samples_per_ray": S, "precision": precision,
                 "l2": "flushed between timed iterations (256 MiB write)",
-                "parallelism": (f"rays sharded by keyframe x{world}; one NCCL all-gather of rendered tiles per step, left in "
-                                "flight behind the next step's render") if world > 1 else "single GPU",
+                "parallelism": (f"rays sharded by keyframe x{world}; "
+                                + ("the rendered tiles reach every rank as mirrored stores of the render kernel itself "
+                                   "(symmetric memory over NVSwitch) + one signal-pad barrier per step on a side stream"
+                                   if ex_dev is not None else
+                                   "one NCCL all-gather of rendered tiles per step, left in flight behind the next "
+                                   "step's render")) if world > 1 else "single GPU",
             },
             "clocks": clock_info,
             "e2e": {"value": e2e_value, "unit": "rays/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d_bytes,
@@ -555,12 +573,44 @@ def main():
         }
         if parity is not None:
             line["parity"] = parity
+        if exchange_info is not None:
+            line["exchange"] = exchange_info
         line.update(extras)
         print(json.dumps(line), flush=True)
     if world > 1:
         import torch.distributed as dist
 
         dist.destroy_process_group()
+
+
+def fused_exchange(distributed, st, dz, cam, dev, rays_per_step, nccl_bufs):
+    """Set up the fused tile exchange and check it against the NCCL all-gather of the same step (same seed) on every
+    rank; returns (exchange of the device-timed loop, exchange of the e2e loop, info) or raises."""
+    import torch
+    import torch.distributed as dist
+
+    # 3 slots: one step of slack (single-stream loop); 4 slots: a slot is reused on the stream that last read it
+    ex_dev = distributed.TileExchange(rays_per_step, dev, slots=3)
+    ex_e2e = distributed.TileExchange(rays_per_step, dev, slots=4)
+    ok = torch.ones(1, device=dev, dtype=torch.int32)
+    with torch.no_grad():
+        for ex in (ex_dev, ex_e2e):
+            for _ in range(ex.slots + 1):  # every slot, and one reuse
+                want = distributed.render_rays_gathered(st, dz["ijs"], dz["c2w"], cam, dz["field_ids"], dz["near"], dz["far"],
+                                                        return_packed=True, buffers=nccl_bufs, seed=99)
+                got = distributed.render_rays_gathered(st, dz["ijs"], dz["c2w"], cam, dz["field_ids"], dz["near"], dz["far"],
+                                                       return_packed=True, exchange=ex, seed=99)
+                if not torch.equal(got, want):
+                    ok.zero_()
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if int(ok.item()) != 1:
+        raise RuntimeError("the fused exchange did not reproduce the NCCL all-gather bit for bit")
+    info = {"mode": "fused into the render kernel: mirrored Prediction stores over "
+                    + ("the NVSwitch multicast mapping" if ex_dev.multicast else "NVLink peer mappings")
+                    + " of a symmetric tile buffer + signal-pad barrier",
+            "multicast": bool(ex_dev.multicast), "mirrors_per_store": len(ex_dev.mirrors),
+            "equals_nccl_all_gather": True}
+    return ex_dev, ex_e2e, info
 
 
 def multi_gpu_parity(st, cam, dev, world, rank, precision):

@@ -345,6 +345,7 @@ typedef struct NgmObservedArgs {
  * Replaces NeuralGraphMap._render_ijs with use_vmap=True (ngm/run_mapping.py:440-666):
  * sampler -> world->local -> encoding -> per-field MLP -> compositor for
  * (num_fields x rays_per_field) rays, ray (f, r) being evaluated by field f only. */
+#define NGM_MAX_MIRRORS 8
 typedef struct NgmRenderArgs {
   NgmFieldDesc field;
   NgmCamera cam;
@@ -380,6 +381,15 @@ typedef struct NgmRenderArgs {
   float* tsdf;       uint8_t* tsdf_mask;
   void* workspace;
   size_t workspace_bytes;
+  /* multi-GPU tile exchange fused into the render (the reference is single-GPU): every store of the
+   * Prediction (rgbd, color_var, depth_var, term_prob) is repeated at `ptr + mirror_delta[i]` BYTES for
+   * i < num_mirrors.  The deltas lead from this rank's tile inside a symmetric buffer to the same tile inside the
+   * peers' copies of that buffer mapped into this process (NVLink peer memory: num_mirrors = world - 1), or to ONE
+   * NVSwitch multicast mapping of it (num_mirrors = 1: the switch replicates the store to every rank).  The caller
+   * orders the readers (a barrier over the buffer's signal pads after the kernel).  Fused tcgen05 render only. */
+  int64_t mirror_delta[NGM_MAX_MIRRORS];
+  int32_t num_mirrors;
+  int32_t _pad2;
 } NgmRenderArgs;
 
 /* ---- field set, kNN blend ----------------------------------------------------------------

@@ -154,6 +154,7 @@ class NgmRenderArgs(C.Structure):
         ("rgbd", _fp), ("color_var", _fp), ("depth_var", _fp), ("term_prob", _fp),
         ("freespace", _fp), ("freespace_mask", _fp), ("tsdf", _fp), ("tsdf_mask", _fp),
         ("workspace", _fp), ("workspace_bytes", C.c_size_t),
+        ("mirror_delta", C.c_int64 * 8), ("num_mirrors", C.c_int32), ("_pad2", C.c_int32),
     ]
 
 

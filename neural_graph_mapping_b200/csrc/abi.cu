@@ -500,6 +500,12 @@ int ngm_render_rays_fwd(const NgmRenderArgs* a, void* stream_) {
   char* ws = static_cast<char*>(a->workspace);
   const bool fused = render_fused_tc_ok(*a);
   const bool precoded = fused && render_tc_precoded(*a);
+  NGM_CHECK_ARG(a->num_mirrors >= 0 && a->num_mirrors <= NGM_MAX_MIRRORS, "num_mirrors=%d outside [0, %d]",
+                a->num_mirrors, NGM_MAX_MIRRORS);
+  for (int i = 0; i < a->num_mirrors; ++i)
+    NGM_CHECK_ARG((a->mirror_delta[i] & 15) == 0, "mirror_delta[%d] must be a multiple of 16 bytes", i);
+  NGM_UNSUPPORTED(a->num_mirrors > 0 && !fused,
+                  "mirrored Prediction stores exist in the fused tcgen05 render only (precision fp16, <= 128 samples)");
   if (fused && !precoded)  // one fused tcgen05 kernel per render batch
     return launch_render_fused_tc(*a, ws + w.tc, reinterpret_cast<float*>(ws + w.isd), nullptr, nullptr, nullptr, stream);
 

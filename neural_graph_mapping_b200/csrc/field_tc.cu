@@ -101,6 +101,9 @@ struct TcParams {
   uint8_t* freespace_mask;
   float* tsdf;
   uint8_t* tsdf_mask;
+  int num_mirrors;  // fused multi-GPU tile exchange (NgmRenderArgs.mirror_delta)
+  int mirror_per_ray;
+  long long mirror_delta[NGM_MAX_MIRRORS];
   int trace;
   int acc16;  // hidden layers accumulate in fp16 inside the tensor core (NGM_TC_ACC16=1): packed accumulator loads
 };
@@ -140,6 +143,7 @@ struct Smem {
   float sm_g[2][128];      // per slot: geometry after the behind-camera overwrite (neus neighbour)
   float sm_part[2][16][12];  // per slot, per segment (128 / wseg <= 16): 9 partial moments + transmittance leaving the segment
   float comp[2][8][128];     // per slot: deferred compositor inputs of the previous tile {c0,c1,c2,g,d,z,gt,ray_ok} per row
+  long long mirror_delta[NGM_MAX_MIRRORS];  // NgmRenderArgs.mirror_delta (fused tile exchange)
 };
 
 __device__ __forceinline__ float fast_sigmoid(float x) { return __frcp_rn(1.0f + __expf(-x)); }
@@ -395,6 +399,52 @@ __device__ __forceinline__ void comp_stage1(const TcParams& p, Smem& sm, int s, 
   if (ls == wseg - 1) part[9] = incl;
 }
 
+// Fused tile exchange (NgmRenderArgs.mirror_delta): the whole CTA repeats rays [r0, r1) of the Prediction arrays --
+// the contiguous range its finished field segment has just stored, still in L2 -- at every mirror offset (the
+// NVSwitch multicast mapping or the peers' mappings of the symmetric tile buffer) as coalesced 16-byte stores:
+// full NVLink packets instead of one 4..16-byte packet per value.  Call after a __syncthreads().
+__device__ __forceinline__ void mirror_floats(float* q0, float* q1, const long long* deltas, int nm) {
+  const int tid = threadIdx.x, nthreads = blockDim.x;
+  float* a0 = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(q0) + 15) & ~uintptr_t(15));
+  if (a0 > q1) a0 = q1;
+  float* a1 = a0 + ((q1 - a0) & ~3LL);
+  for (float* q = q0 + tid; q < a0; q += nthreads) {  // unaligned head
+    const float v = __ldcg(q);
+    for (int m = 0; m < nm; ++m) *reinterpret_cast<float*>(reinterpret_cast<char*>(q) + deltas[m]) = v;
+  }
+  for (float4* q = reinterpret_cast<float4*>(a0) + tid; q < reinterpret_cast<float4*>(a1); q += nthreads) {
+    const float4 v = __ldcg(q);
+    for (int m = 0; m < nm; ++m) *reinterpret_cast<float4*>(reinterpret_cast<char*>(q) + deltas[m]) = v;
+  }
+  for (float* q = a1 + tid; q < q1; q += nthreads) {  // tail
+    const float v = __ldcg(q);
+    for (int m = 0; m < nm; ++m) *reinterpret_cast<float*>(reinterpret_cast<char*>(q) + deltas[m]) = v;
+  }
+}
+
+// (not inlined, arguments by value, the deltas in shared memory: the fused kernel's register allocation and its
+// constant-bank parameters stay exactly what they are without the exchange)
+__device__ __noinline__ void mirror_range(float* rgbd, float* cvar, float* dvar, float* term, long long r0, long long r1,
+                                          const long long* deltas, int nm) {
+  mirror_floats(rgbd + r0 * 4, rgbd + r1 * 4, deltas, nm);
+  if (cvar) mirror_floats(cvar + r0 * 3, cvar + r1 * 3, deltas, nm);
+  if (dvar) mirror_floats(dvar + r0, dvar + r1, deltas, nm);
+  if (term) mirror_floats(term + r0, term + r1, deltas, nm);
+}
+
+__device__ __forceinline__ void store_prediction(const TcParams& p, long long delta, long long ray, float4 rgbd,
+                                                 float cv0, float cv1, float cv2, float dv, float tp) {
+#define NGM_AT(q) reinterpret_cast<float*>(reinterpret_cast<char*>(q) + delta)
+  reinterpret_cast<float4*>(NGM_AT(p.rgbd))[ray] = rgbd;
+  if (p.color_var) {
+    float* cv = NGM_AT(p.color_var) + ray * 3;
+    cv[0] = cv0; cv[1] = cv1; cv[2] = cv2;
+  }
+  if (p.depth_var) NGM_AT(p.depth_var)[ray] = dv;
+  if (p.term_prob) NGM_AT(p.term_prob)[ray] = tp;
+#undef NGM_AT
+}
+
 __device__ __forceinline__ void comp_stage2(const TcParams& p, Smem& sm, int s, int row, int barrier_id, long long f,
                                             long long tile_in_field) {
   ptx::named_bar_sync(barrier_id, 128);
@@ -413,14 +463,18 @@ __device__ __forceinline__ void comp_stage2(const TcParams& p, Smem& sm, int s, 
     const float P = m[0], D = m[1], C0 = m[2], C1 = m[3], C2 = m[4];
     const float t2 = 2.0f - P;
     const long long ray_global = f * p.rays_per_field + tile_in_field * p.rpt + (row >> p.sp_shift);
-    reinterpret_cast<float4*>(p.rgbd)[ray_global] = make_float4(C0, C1, C2, D);
-    if (p.color_var) {
-      p.color_var[ray_global * 3 + 0] = fmaxf(fmaf(-C0 * C0, t2, m[6]), 0.0f);
-      p.color_var[ray_global * 3 + 1] = fmaxf(fmaf(-C1 * C1, t2, m[7]), 0.0f);
-      p.color_var[ray_global * 3 + 2] = fmaxf(fmaf(-C2 * C2, t2, m[8]), 0.0f);
-    }
-    if (p.depth_var) p.depth_var[ray_global] = fmaxf(fmaf(-D * D, t2, m[5]), 0.0f);
-    if (p.term_prob) p.term_prob[ray_global] = 1.0f - (1.0f - P);
+    const float4 rgbd = make_float4(C0, C1, C2, D);
+    const float cv0 = fmaxf(fmaf(-C0 * C0, t2, m[6]), 0.0f);
+    const float cv1 = fmaxf(fmaf(-C1 * C1, t2, m[7]), 0.0f);
+    const float cv2 = fmaxf(fmaf(-C2 * C2, t2, m[8]), 0.0f);
+    const float dv = fmaxf(fmaf(-D * D, t2, m[5]), 0.0f);
+    const float tp = 1.0f - (1.0f - P);
+    store_prediction(p, 0, ray_global, rgbd, cv0, cv1, cv2, dv, tp);
+    // fused tile exchange (NgmRenderArgs.mirror_delta), diagnostic variant NGM_MIRROR_PER_RAY=1: the same small stores
+    // straight into the peer / multicast mappings (1.8 M NVLink packets of 4-16 B per keyframe; measured slower than
+    // the per-segment bulk repeat below)
+    if (p.mirror_per_ray)
+      for (int i = 0; i < p.num_mirrors; ++i) store_prediction(p, sm.mirror_delta[i], ray_global, rgbd, cv0, cv1, cv2, dv, tp);
   }
 }
 
@@ -486,7 +540,7 @@ __device__ __forceinline__ void issue_layer(uint32_t d_addr, uint32_t a_addr, ui
 // (A lockstep variant in which all 16 warps share every epilogue job of both slots was measured slower --
 // 3.85 ms vs 2.83 ms per frame -- because each duty then stalls all 512 threads; profiles/README.md.)
 template <int MODE, int OCT, bool TRACE, bool ACC16>
-__global__ void __launch_bounds__(threads_of(MODE), 1) tc_kernel(const TcParams p) {
+__global__ void __launch_bounds__(threads_of(MODE), 1) tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   // weights image first (1024-B aligned for SWIZZLE_128B), bookkeeping after it; plain pointer
   // arithmetic on smem_raw keeps the shared address space (LDS/STS, not generic LD/ST)
@@ -502,6 +556,7 @@ __global__ void __launch_bounds__(threads_of(MODE), 1) tc_kernel(const TcParams 
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
 
   if (warp == 0) ptx::tmem_alloc(&sm.tmem_base, kTmemCols);
+  if (MODE == 0 && tid >= 96 && tid < 96 + NGM_MAX_MIRRORS) sm.mirror_delta[tid - 96] = p.mirror_delta[tid - 96];
   if (tid == 64) {
     for (int s = 0; s < 2; ++s) {
       // 128 front-end stores + 128 compositor threads that drained the accumulator.  No parity aliasing on d_ready:
@@ -892,6 +947,12 @@ __global__ void __launch_bounds__(threads_of(MODE), 1) tc_kernel(const TcParams 
     t = seg_end;
     ptx::fence_proxy_async();  // generic-proxy reads of the image before the next bulk copy overwrites it
     __syncthreads();
+    if (MODE == 0 && p.num_mirrors > 0 && !p.mirror_per_ray) {
+      const long long r0 = f * p.rays_per_field + tile0_in_field * p.rpt;
+      long long r1 = r0 + (long long)ntiles * p.rpt;
+      if (r1 > (f + 1) * p.rays_per_field) r1 = (f + 1) * p.rays_per_field;
+      mirror_range(p.rgbd, p.color_var, p.depth_var, p.term_prob, r0, r1, sm.mirror_delta, p.num_mirrors);
+    }
   }
 
   ptx::tc_fence_before();
@@ -1230,6 +1291,9 @@ int launch_render_fused_tc(const NgmRenderArgs& a, void* tc_ws, float* isd_ws, c
     p.neus_isd = isd_ws;
   }
   p.rgbd = a.rgbd; p.color_var = a.color_var; p.depth_var = a.depth_var; p.term_prob = a.term_prob;
+  p.num_mirrors = a.num_mirrors;
+  { const char* e = getenv("NGM_MIRROR_PER_RAY"); p.mirror_per_ray = (e && e[0] == '1') ? 1 : 0; }  // diagnostics, read per call
+  for (int i = 0; i < a.num_mirrors; ++i) p.mirror_delta[i] = a.mirror_delta[i];
   p.freespace = a.freespace; p.freespace_mask = a.freespace_mask; p.tsdf = a.tsdf; p.tsdf_mask = a.tsdf_mask;
   p.tiles_per_field = (a.rays_per_field + p.rpt - 1) / p.rpt;
   p.total_tiles = p.tiles_per_field * a.num_fields;

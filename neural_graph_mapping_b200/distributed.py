@@ -92,15 +92,126 @@ def gather_tiles(local_flat: torch.Tensor, group=None, out: Optional[torch.Tenso
     return PendingTiles(out, local_flat, work) if async_op else out
 
 
+class _EventWork:
+    """``wait()`` orders the current stream after an event recorded on another stream (no host block)."""
+
+    def __init__(self, event) -> None:
+        self._event = event
+
+    def wait(self) -> None:
+        torch.cuda.current_stream().wait_event(self._event)
+
+
+class TileExchange:
+    """The tile exchange FUSED into the render kernel (replaces the NCCL all-gather).
+
+    A symmetric buffer of ``slots x world`` tiles (``torch.distributed._symmetric_memory``: the same allocation on
+    every rank, each mapped into every process over NVLink, plus ONE NVSwitch multicast mapping where the fabric has
+    it).  Rank r renders straight into tile r of a slot and the fused kernel repeats each 36-byte Prediction store at
+    the byte offsets ``mirrors`` -- the multicast mapping (the switch replicates the store to all ranks) or, without
+    multicast, the world-1 peer mappings -- so the transfer rides along with the math, ray by ray, and the exchange
+    ends with a barrier over the buffer's signal pads instead of a collective.
+
+    Slots form a ring over the steps of a loop (``acquire`` hands out slot ``step % slots``).  A rank reads a step's
+    tiles after that step's barrier and BEFORE it issues its next render (stream order); ``acquire`` orders the
+    render of step i after the barrier of step ``i - slots + 1``: every rank has then finished the render that FOLLOWS the
+    step being overwritten, hence its reads of it.  With 3 slots a rank may run one step
+    ahead of the slowest peer (the slack the in-flight NCCL all-gather had); with 2 every step waits for all ranks.
+    """
+
+    def __init__(self, n_rays: int, device, group=None, slots: int = 3, multicast: bool = True) -> None:
+        import torch.distributed._symmetric_memory as symm
+
+        d = _dist()
+        if d is None:
+            raise RuntimeError("TileExchange needs an initialised process group")
+        self.world, self.rank = world_info(group)
+        if self.world - 1 > 8 and not multicast:
+            raise ValueError("at most 8 peer mirrors")
+        self.n_rays, self.slots = int(n_rays), int(slots)
+        self.tile_floats = FLOATS_PER_RAY * self.n_rays
+        self.stride = (self.tile_floats + 3) // 4 * 4  # tiles start 16-byte aligned (the rgbd vector store)
+        self.device = torch.device(device)
+        with torch.cuda.device(self.device):
+            self.buffer = symm.empty(self.slots * self.world * self.stride, dtype=torch.float32, device=self.device)
+            self.handle = symm.rendezvous(self.buffer, group if group is not None else d.group.WORLD)
+            self.buffer.zero_()
+        ptrs = [int(x) for x in self.handle.buffer_ptrs]
+        mc = int(getattr(self.handle, "multicast_ptr", 0) or 0) if multicast else 0
+        self.multicast = mc != 0
+        if self.multicast:
+            self.mirrors = [mc - ptrs[self.rank]]
+        else:
+            self.mirrors = [ptrs[r] - ptrs[self.rank] for r in range(self.world) if r != self.rank]
+        self._side = torch.cuda.Stream(device=self.device)
+        self._step = 0
+        self._done = {}  # step -> event recorded after that step's barrier
+        torch.cuda.synchronize(self.device)
+        self.handle.barrier(channel=0)  # every rank's zero fill has landed before anyone's first mirrored store
+
+    def acquire(self) -> int:
+        """Slot of the next step; orders the current stream after the barrier that frees it (no host block)."""
+        ev = self._done.pop(self._step - self.slots + 1, None)
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
+        return self._step % self.slots
+
+    def tile(self, slot: int, rank: Optional[int] = None) -> torch.Tensor:
+        r = self.rank if rank is None else rank
+        o = (slot * self.world + r) * self.stride
+        return self.buffer[o:o + self.tile_floats]
+
+    def gathered(self, slot: int) -> torch.Tensor:
+        """(world, 9 n) view of a slot: every rank's tile, valid after ``finish``."""
+        return self.buffer[slot * self.world * self.stride:(slot + 1) * self.world * self.stride].view(
+            self.world, self.stride)[:, :self.tile_floats]
+
+    def finish(self, slot: int, async_op: bool = False):
+        """Barrier over the signal pads: afterwards every rank's tile of ``slot`` is complete on every rank.  With
+        ``async_op`` the barrier runs on a side stream (the next render does not wait for the slowest peer) and a
+        PendingTiles is returned."""
+        ev = torch.cuda.Event()
+        ev.record()
+        with torch.cuda.stream(self._side):  # all barriers of an exchange run on ONE stream, in step order
+            self._side.wait_event(ev)
+            self.handle.barrier(channel=0)
+            done = torch.cuda.Event()
+            done.record()
+        self._done[self._step] = done
+        self._step += 1
+        if not async_op:
+            torch.cuda.current_stream().wait_event(done)
+            return self.gathered(slot)
+        return PendingTiles(self.gathered(slot), self.tile(slot), _EventWork(done))
+
+
 def render_rays_gathered(driver, ijs, c2ws, camera, field_ids, near=None, far=None, gt=None,
                          return_packed: bool = False, group=None, async_gather: bool = False,
-                         buffers: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, **kw):
+                         buffers: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
+                         exchange: Optional["TileExchange"] = None, **kw):
     """Each rank renders ITS OWN (F, R) ray batch (e.g. its keyframe / its pixel tiles); the packed
     tiles of all ranks are all-gathered.  Returns the packed (world, 9*F*R) buffer, a PendingTiles
     (``async_gather``), or a list of per-rank ``Prediction`` views.  ``buffers`` = (local 9n, gathered world x 9n)
-    preallocated tensors to reuse (a step loop double-buffers them)."""
+    preallocated tensors to reuse (a step loop double-buffers them).  ``exchange`` = a TileExchange: the
+    tiles travel as mirrored stores of the render kernel itself instead of an NCCL all-gather."""
     F, R = ijs.shape[0], ijs.shape[1]
     n = F * R
+    if exchange is not None:
+        ex, slot = exchange, exchange.acquire()
+        if n != ex.n_rays:
+            raise ValueError(f"the exchange was sized for {ex.n_rays} rays per rank, got {n}")
+        rgbd, cvar, dvar, term = packed_views(ex.tile(slot), n)
+        render_rays(driver, ijs, c2ws, camera, field_ids, True, near, far, gt,
+                    out=(rgbd.view(F, R, 4), cvar.view(F, R, 3), dvar.view(F, R), term.view(F, R)),
+                    mirrors=ex.mirrors, **kw)
+        res = ex.finish(slot, async_op=async_gather)
+        if async_gather or return_packed:
+            return res
+        preds = []
+        for r in range(ex.world):
+            a, b, c, d = packed_views(res[r], n)
+            preds.append(Prediction(a.view(F, R, 4), b.view(F, R, 3), c.view(F, R), d.view(F, R), None, None))
+        return preds
     if buffers is not None:
         local, out = buffers
     else:

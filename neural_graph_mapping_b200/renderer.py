@@ -13,7 +13,7 @@ from __future__ import annotations
 
 import ctypes as C
 from collections import namedtuple
-from typing import Optional, Tuple
+from typing import Optional, Sequence, Tuple
 
 import torch
 
@@ -79,6 +79,7 @@ def render_rays(
     out: Optional[tuple] = None,
     seed: Optional[int] = None,
     sample_offset: int = 0,
+    mirrors: Optional[Sequence[int]] = None,
 ) -> Prediction:
     """Drop-in for ``NeuralGraphMap._render_ijs`` (ngm/run_mapping.py:440-666).
 
@@ -88,7 +89,9 @@ def render_rays(
     multi-GPU all-gather so the tiles land directly in the send buffer).  ``seed`` / ``sample_offset`` pin the
     in-kernel jitter stream: sample k of ray r draws element ``sample_offset + r * St + k`` of stream ``seed``, so
     a shard of a batch rendered with the batch's seed and its first sample's global index as offset draws
-    exactly what the whole batch would (multi-GPU field sharding).
+    exactly what the whole batch would (multi-GPU field sharding).  ``mirrors`` = byte offsets from the ``out``
+    tensors to peer / multicast mappings of the same tile (``distributed.TileExchange``): the fused kernel repeats
+    every Prediction store there, which replaces the all-gather.
     """
     if use_vmap and field_ids is None:
         raise ValueError("field_ids=None only supported for use_vmap=False")  # run_mapping.py:497-498
@@ -102,6 +105,9 @@ def render_rays(
     overwrite = bool(overwrite_samples_behind_camera) and near_distances is not None
     if not use_vmap:
         from .knn import render_rays_knn
+
+        if mirrors:
+            raise NotImplementedError("mirrors= exists on the use_vmap=True path only")
 
         return render_rays_knn(driver, ijs, c2ws, camera, field_ids, near_distances, far_distances,
                                gt_distances, overwrite, jitter, seed, sample_offset)
@@ -136,8 +142,8 @@ def render_rays(
         if slots is not None:  # gather the active fields (differentiable; what set_vmap_fields does, models.py:274-276)
             params = {k: v[slots] for k, v in params.items()}
             positions, orientations = positions[slots], orientations[slots]
-        if out is not None:
-            raise ValueError("out= is not supported on the differentiable path")
+        if out is not None or mirrors:
+            raise ValueError("out= / mirrors= are not supported on the differentiable path")
         return Prediction(*ag.render_rays_vmap(
             driver, camera, ijs, c2ws, params, positions, orientations, near_distances, far_distances, gt_distances,
             overwrite, jitter, jitter_guided,
@@ -208,6 +214,14 @@ def render_rays(
             dvar = torch.empty(F, R, device=dev)
             term = torch.empty(F, R, device=dev)
         a.rgbd, a.color_var, a.depth_var, a.term_prob = rgbd.data_ptr(), cvar.data_ptr(), dvar.data_ptr(), term.data_ptr()
+        if mirrors:
+            if out is None:
+                raise ValueError("mirrors= needs out= (views of the symmetric tile buffer)")
+            if len(mirrors) > len(a.mirror_delta):
+                raise ValueError(f"at most {len(a.mirror_delta)} mirrors")
+            a.num_mirrors = len(mirrors)
+            for i, d in enumerate(mirrors):
+                a.mirror_delta[i] = int(d)
         fs = fs_m = ts = ts_m = None
         if driver._freespace_weight != 0.0 and gt_t is not None:  # :624
             fs = torch.empty(F, R, St, device=dev)
