@@ -531,7 +531,7 @@ def main():
     if not args.no_extras:
         try:
             extras = run_extras(ngm, distributed, make_state, cam, dev, world, rank, precision, flush, timed, barrier,
-                                steps=max(5, min(args.steps, 20)), warmup=3)
+                                steps=max(5, min(args.steps, 20)), warmup=3, fused=ex_dev is not None)
         except Exception as e:  # never lose the headline line to an extra
             extras = {"extras_error": f"{type(e).__name__}: {e}"[:300]}
 
@@ -654,7 +654,8 @@ def multi_gpu_parity(st, cam, dev, world, rank, precision):
     return res
 
 
-def run_extras(ngm, distributed, make_state, cam, dev, world, rank, precision, flush, timed, barrier, steps, warmup):
+def run_extras(ngm, distributed, make_state, cam, dev, world, rank, precision, flush, timed, barrier, steps, warmup,
+               fused=False):
     """Workloads BASELINE.json names beside the headline one, as extra keys of the same JSON line:
     `c4` -- configs[3]: 256 fields x 4096 rays x 64 samples with per-ray poses, the batch sharded by FIELD over the N
             GPUs (strong scaling: the total work is fixed), one all-gather of the rendered tiles;
@@ -667,18 +668,21 @@ def run_extras(ngm, distributed, make_state, cam, dev, world, rank, precision, f
     st4 = make_state(precision, c4)
     d4 = {k: c4[k].to(dev) for k in ("ijs", "c2ws", "near", "far", "field_ids")}
     n4 = C4_FIELDS * C4_RAYS
+    how = ("tiles exchanged by the render kernel itself (distributed.TileExchange)" if fused
+           else "NCCL all-gather of the tiles")
     if C4_FIELDS % world == 0:
         seed_box = [0]
+        ex4 = distributed.TileExchange(n4 // world, dev, slots=3) if fused else None
 
         def step_c4():
             seed_box[0] += 1
             with torch.no_grad():
                 distributed.render_rays_sharded(st4, d4["ijs"], d4["c2ws"], cam, d4["field_ids"], d4["near"], d4["far"],
-                                                seed=seed_box[0])
+                                                seed=seed_box[0], exchange=ex4)
 
         ms = timed(step_c4, steps, warmup) / steps
         out["c4"] = {"workload": "configs[3]: 256 anchored fields x 4096 rays (1,048,576 rays) x 64 samples, per-ray c2ws, "
-                                 "4-layer x 128 MLP NeRF-8; fields sharded over the GPUs, NCCL all-gather of the tiles; the "
+                                 "4-layer x 128 MLP NeRF-8; fields sharded over the GPUs, " + how + "; the "
                                  "forward render of the batch (the training step's fwd+bwd is `train`)",
                      "value": n4 / (ms / 1e3), "unit": "rays/s", "ms_per_step": ms, "n_gpus": world, "scaling": "strong",
                      "rays_per_step": n4, "steps": steps}
@@ -754,6 +758,7 @@ def run_extras(ngm, distributed, make_state, cam, dev, world, rank, precision, f
         bufs = [(torch.empty(tf, device=dev), torch.empty(world, tf, device=dev)) for _ in range(2)]
         pend = [None, None]
         cnt = [0]
+        exs = distributed.TileExchange(n_local, dev, slots=3) if fused else None
 
         def step_split():
             i = cnt[0] & 1
@@ -762,7 +767,7 @@ def run_extras(ngm, distributed, make_state, cam, dev, world, rank, precision, f
                 pend[i].wait()
             with torch.no_grad():
                 pend[i] = distributed.render_rays_split(st, dz["ijs"], dz["c2w"], cam, dz["field_ids"], dz["near"], dz["far"],
-                                                        async_gather=True, buffers=bufs[i])
+                                                        async_gather=True, buffers=bufs[i], exchange=exs)
 
         def drain():
             for i in range(2):
@@ -771,7 +776,7 @@ def run_extras(ngm, distributed, make_state, cam, dev, world, rank, precision, f
                     pend[i] = None
 
         ms = timed(step_split, steps, warmup, after=drain) / steps
-        out["strong_c2"] = {"workload": "configs[1] keyframe (307,200 rays x 64) split by ray over the GPUs, all-gather of tiles",
+        out["strong_c2"] = {"workload": "configs[1] keyframe (307,200 rays x 64) split by ray over the GPUs, " + how,
                             "value": F_FIELDS * R_RAYS / (ms / 1e3), "unit": "rays/s", "ms_per_step": ms, "n_gpus": world,
                             "scaling": "strong", "steps": steps}
     return out

@@ -127,6 +127,22 @@ def _worker(rank, world, port):
             assert len(preds) == world and preds[rank].rgbds.shape == (ijs.shape[0], ijs.shape[1], 4)
         torch.cuda.synchronize()
         dist.barrier()
+    # the other partitions ride on the same exchange: one batch split by ray, one batch sharded by field
+    F, R = ijs.shape[0], ijs.shape[1]
+    ex_split = D.TileExchange(F * R // world, dev)
+    ex_shard = D.TileExchange(F // world * R, dev)
+    g = torch.Generator().manual_seed(3)
+    jit = torch.rand(F, R, 16, generator=g).to(dev)
+    ijs0 = (ijs - rank) % 480  # the SAME batch on every rank
+    with torch.no_grad():
+        for _ in range(4):
+            a_ = D.render_rays_split(st, ijs0, c2w, cam, fid, near, far, jitter=jit)
+            b_ = D.render_rays_split(st, ijs0, c2w, cam, fid, near, far, jitter=jit, exchange=ex_split)
+            c_ = D.render_rays_sharded(st, ijs0, c2w, cam, fid, near, far, seed=17)
+            d_ = D.render_rays_sharded(st, ijs0, c2w, cam, fid, near, far, seed=17, exchange=ex_shard)
+            for x, y in zip(a_[:4] + c_[:4], b_[:4] + d_[:4]):
+                assert torch.equal(x, y)
+    torch.cuda.synchronize()
     if rank == 0:
         print("multicast used:", modes)
     dist.barrier()
