@@ -270,9 +270,55 @@ def test_render_knn_golden(name):
     _close(p.term_probs, a["out_term_probs"], 3e-5, 3e-5, "term")
 
 
-@pytest.mark.parametrize("F,K,n", [(1, 2, 300), (3, 1, 1000), (40, 2, 5000), (1500, 3, 4000)])
+@pytest.mark.parametrize("side,K", [(12, 2), (45, 2), (45, 3)])
+def test_fieldset_knn_large_map_rays(side, K):
+    """A map of side x side fields on a grid and points along rays (neighbouring samples are spatially coherent, the
+    renderer's access pattern): the candidate pruning of the assign kernel -- per warp, and per block on maps of more
+    than a few hundred fields -- must select exactly the K nearest fields of the full scan."""
+    import neural_graph_mapping_b200 as ngm
+
+    F = side * side
+    g = torch.Generator().manual_seed(side + K)
+    spec = R.FieldSpec("nerf", {"dim_in": 3, "num_octaves": 4}, 1, 4, 16, "no")
+    n_tab = 8
+    params = R.stack_params([R.init_field_params(spec, g) for _ in range(n_tab)])
+    idx = torch.arange(F)
+    pos = torch.stack([(idx % side).float() * 1.1547, torch.zeros(F), -(idx // side).float() * 1.1547], -1)
+    pos = pos + 0.05 * torch.randn(F, 3, generator=g)
+    q = torch.randn(F, 4, generator=g)
+    ori = q / q.norm(dim=-1, keepdim=True)
+    fid = torch.randint(0, n_tab, (F,), generator=g)
+    rays, S = 70, 64  # 4,480 points: the last block of the kernel is partial
+    origin = torch.stack([torch.rand(rays, generator=g) * side * 1.1547, torch.rand(rays, generator=g) * 0.6 - 0.3,
+                          -torch.rand(rays, generator=g) * side * 1.1547], -1)
+    d = torch.randn(rays, 3, generator=g) * torch.tensor([1.0, 0.15, 1.0])
+    d = d / d.norm(dim=-1, keepdim=True)
+    t = torch.linspace(0.0, 4.0, S)
+    pts = (origin[:, None] + t[None, :, None] * d[:, None]).reshape(-1, 3)
+    rs = R.RenderSpec(field_radius=1.0, scale_mode="unit_cube", num_knn=K, distance_factor=10.0, outside_value=1.0)
+    ref = R.fieldset_forward_knn(pts, pos, ori, fid, spec, params, rs)
+    model = ngm.NeuralFieldSet(3, "neural_graph_mapping_b200.models.NeuralField",
+                               {"encoding_type": "neural_graph_mapping_b200.positional_encodings.PositionalEncodingNeRF",
+                                "encoding_kwargs": {"dim_in": 3, "num_octaves": 4}, "num_layers": 1, "dim_out": 4,
+                                "dim_mlp_out": 16}, K, 10.0, 1.0, field_radius=1.0, scale_mode="unit_cube").to(DEV)
+    model.all_fields_params = {k: v.to(DEV) for k, v in params.items()}
+    with torch.no_grad():
+        y = model(pts.to(DEV), pos.to(DEV), ori.to(DEV), fid.to(DEV), False)
+    dd = torch.cdist(pts, pos)
+    srt = torch.sort(dd, dim=-1)[0]
+    margin = (srt[:, 0] - 1.0).abs() > 1e-5
+    for j in range(K):
+        margin &= (srt[:, j + 1] - srt[:, j]).abs() > 1e-5
+    assert margin.float().mean() > 0.95
+    _close(y.cpu()[margin], ref[margin], 3e-5, 3e-5, "kNN fieldset, large map")
+    inside = (ref != 1.0).any(-1).float().mean().item()
+    assert 0.3 < inside <= 1.0
+
+
+@pytest.mark.parametrize("F,K,n", [(1, 2, 300), (3, 1, 1000), (40, 2, 5000), (1500, 3, 4000), (9000, 2, 3000)])
 def test_fieldset_knn_vs_oracle(F, K, n):
-    """Field counts below K, K=1/3, more centres than one shared-memory chunk, field_ids remap."""
+    """Field counts below K, K=1/3, more centres than one shared-memory chunk, more fields than the per-block
+    histogram of the bucketing kernels holds (global counters then), field_ids remap."""
     import neural_graph_mapping_b200 as ngm
 
     g = torch.Generator().manual_seed(F * 10 + K)
