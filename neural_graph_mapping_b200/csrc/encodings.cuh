@@ -67,71 +67,74 @@ __device__ __forceinline__ float triplane_feature(const float* x, int c, const f
 
 // Enclosing simplex of a 3-D point on one level of the permutohedral lattice: the hashed table rows of
 // its four vertices and their barycentric weights.  shift/scale = 3 floats of this level.
+//
+// Register-only and branch-free.  The textbook form indexes bary[] and the key offsets by the run-time ranks; the
+// compiler turned that into local-memory arrays and jump tables (172 LDL + 172 STL + 32 BRX in the row encoder, ~650
+// instructions per level).  Here the ranks -- a permutation of 0..3 -- are inverted with selects instead:
+// bary[s] = delta[rank == 3-s] - delta[rank == 4-s], which is what the accumulation loop computes (each slot receives
+// exactly one +delta and one -delta, and 0 + a - b = 0 - b + a in floating point), so rows and weights are bit-identical.
 __device__ __forceinline__ void permuto_simplex(const float* x, const float* __restrict__ shift,
                                                 const float* __restrict__ scale, int log2_capacity, uint32_t (&row)[4],
                                                 float (&weight)[4]) {
-  constexpr int D = 3, D1 = 4;
-  float cf[D];
-#pragma unroll
-  for (int i = 0; i < D; ++i) cf[i] = __fmul_rn(__fadd_rn(x[i], __ldg(shift + i)), __ldg(scale + i));
-  float E[D1];
-  float sm = 0.0f;
-#pragma unroll
-  for (int i = D; i > 0; --i) {
-    E[i] = __fsub_rn(sm, __fmul_rn((float)i, cf[i - 1]));
-    sm = __fadd_rn(sm, cf[i - 1]);
-  }
-  E[0] = sm;
-  int rem0[D1], rank[D1] = {0, 0, 0, 0};
-  int sum = 0;
-#pragma unroll
-  for (int i = 0; i < D1; ++i) {
-    const float v = __fmul_rn(E[i], 1.0f / D1);
-    const float up = ceilf(v) * D1, down = floorf(v) * D1;
-    rem0[i] = (__fsub_rn(up, E[i]) < __fsub_rn(E[i], down)) ? (int)up : (int)down;
-    sum += rem0[i];
-  }
-  sum /= D1;  // C truncation
-  float resid[D1];
-#pragma unroll
-  for (int i = 0; i < D1; ++i) resid[i] = __fsub_rn(E[i], (float)rem0[i]);
-#pragma unroll
-  for (int i = 0; i < D; ++i)
-#pragma unroll
-    for (int j = i + 1; j < D1; ++j) {
-      if (resid[i] < resid[j]) rank[i]++;
-      else rank[j]++;
-    }
-#pragma unroll
-  for (int i = 0; i < D1; ++i) {
-    rank[i] += sum;
-    if (rank[i] < 0) { rank[i] += D1; rem0[i] += D1; }
-    else if (rank[i] > D) { rank[i] -= D1; rem0[i] -= D1; }
-  }
-  float bary[D + 2] = {0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-  for (int i = 0; i < D1; ++i) {
-    const float delta = __fmul_rn(__fsub_rn(E[i], (float)rem0[i]), 1.0f / D1);
-    // bary[D - rank] += delta; bary[D + 1 - rank] -= delta  (rank in 0..3; unrolled select keeps registers)
-#pragma unroll
-    for (int r = 0; r <= D + 1; ++r) {
-      if (r == D - rank[i]) bary[r] = __fadd_rn(bary[r], delta);
-      if (r == D + 1 - rank[i]) bary[r] = __fsub_rn(bary[r], delta);
-    }
-  }
-  bary[0] = __fadd_rn(bary[0], __fadd_rn(1.0f, bary[D + 1]));
+  const float cf0 = __fmul_rn(__fadd_rn(x[0], __ldg(shift + 0)), __ldg(scale + 0));
+  const float cf1 = __fmul_rn(__fadd_rn(x[1], __ldg(shift + 1)), __ldg(scale + 1));
+  const float cf2 = __fmul_rn(__fadd_rn(x[2], __ldg(shift + 2)), __ldg(scale + 2));
+  // elevate: E[i] = sm - i * cf[i-1], sm += cf[i-1], for i = 3, 2, 1; E[0] = sm
+  const float E3 = __fsub_rn(0.0f, __fmul_rn(3.0f, cf2));
+  const float s2 = __fadd_rn(0.0f, cf2);
+  const float E2 = __fsub_rn(s2, __fmul_rn(2.0f, cf1));
+  const float s1 = __fadd_rn(s2, cf1);
+  const float E1 = __fsub_rn(s1, __fmul_rn(1.0f, cf0));
+  const float E0 = __fadd_rn(s1, cf0);
+  // nearest lattice point with remainder 0
+  auto nearest = [](float e) {
+    const float v = __fmul_rn(e, 0.25f);
+    const float up = ceilf(v) * 4.0f, down = floorf(v) * 4.0f;
+    return (__fsub_rn(up, e) < __fsub_rn(e, down)) ? (int)up : (int)down;
+  };
+  int m0 = nearest(E0), m1 = nearest(E1), m2 = nearest(E2), m3 = nearest(E3);
+  const int sum = (m0 + m1 + m2 + m3) / 4;  // C truncation
+  const float r0 = __fsub_rn(E0, (float)m0), r1 = __fsub_rn(E1, (float)m1), r2 = __fsub_rn(E2, (float)m2),
+              r3 = __fsub_rn(E3, (float)m3);
+  // rank[i] = number of j with resid[i] < resid[j] (j > i) or not resid[j] < resid[i] (j < i)
+  const int c01 = r0 < r1, c02 = r0 < r2, c03 = r0 < r3, c12 = r1 < r2, c13 = r1 < r3, c23 = r2 < r3;
+  int k0 = c01 + c02 + c03 + sum;
+  int k1 = (1 - c01) + c12 + c13 + sum;
+  int k2 = (1 - c02) + (1 - c12) + c23 + sum;
+  int k3 = (1 - c03) + (1 - c13) + (1 - c23) + sum;
+  auto wrap = [](int& k, int& m) {
+    const int lo = k < 0, hi = k > 3;
+    k += 4 * (lo - hi);
+    m += 4 * (lo - hi);
+  };
+  wrap(k0, m0); wrap(k1, m1); wrap(k2, m2); wrap(k3, m3);
+  const float d0 = __fmul_rn(__fsub_rn(E0, (float)m0), 0.25f), d1 = __fmul_rn(__fsub_rn(E1, (float)m1), 0.25f),
+              d2 = __fmul_rn(__fsub_rn(E2, (float)m2), 0.25f), d3 = __fmul_rn(__fsub_rn(E3, (float)m3), 0.25f);
+  // delta of the coordinate whose rank is r (0 if the ranks are not a permutation, as the indexed form would skip it)
+  auto by_rank = [&](int r) {  // a chain of selects (the nested conditional compiled to branches)
+    float q = k3 == r ? d3 : 0.0f;
+    q = k2 == r ? d2 : q;
+    q = k1 == r ? d1 : q;
+    q = k0 == r ? d0 : q;
+    return q;
+  };
+  const float q0 = by_rank(0), q1 = by_rank(1), q2 = by_rank(2), q3 = by_rank(3);
+  // bary[s] += delta where rank == 3 - s, -= delta where rank == 4 - s;  bary[0] += 1 + bary[4]
+  const float b4 = __fsub_rn(0.0f, q0);
+  weight[0] = __fadd_rn(q3, __fadd_rn(1.0f, b4));
+  weight[1] = __fsub_rn(q2, q3);
+  weight[2] = __fsub_rn(q1, q2);
+  weight[3] = __fsub_rn(q0, q1);
   const uint32_t mask = (1u << log2_capacity) - 1u;
 #pragma unroll
-  for (int r = 0; r < D1; ++r) {
-    uint32_t h = 0;
-#pragma unroll
-    for (int i = 0; i < D; ++i) {
-      int key = rem0[i] + r;
-      if (rank[i] > D - r) key -= D1;
-      h = (h + (uint32_t)key) * 2531011u;
-    }
+  for (int r = 0; r < 4; ++r) {  // vertex r: key_i = rem0_i + r, minus 4 where rank_i > 3 - r (first three coordinates)
+    const int key0 = m0 + r - ((k0 > 3 - r) ? 4 : 0);
+    const int key1 = m1 + r - ((k1 > 3 - r) ? 4 : 0);
+    const int key2 = m2 + r - ((k2 > 3 - r) ? 4 : 0);
+    uint32_t h = (uint32_t)key0 * 2531011u;
+    h = (h + (uint32_t)key1) * 2531011u;
+    h = (h + (uint32_t)key2) * 2531011u;
     row[r] = h & mask;
-    weight[r] = bary[r];
   }
 }
 
