@@ -104,6 +104,7 @@ struct TcParams {
   int num_mirrors;  // fused multi-GPU tile exchange (NgmRenderArgs.mirror_delta)
   int mirror_per_ray;
   long long mirror_delta[NGM_MAX_MIRRORS];
+  int skip;  // 0 no, 1 "add", 2 "concat" (NgmFieldDesc.skip_mode; rezero stays on the fp32 path)
   int trace;
   int acc16;  // hidden layers accumulate in fp16 inside the tensor core (NGM_TC_ACC16=1): packed accumulator loads
 };
@@ -217,6 +218,37 @@ __device__ __forceinline__ void hidden_epilogue(uint32_t d_addr, uint32_t a_addr
     ptx::tc_wait_ld();
     uint32_t w[8];
     cvt16(v, bias2 + c / 2, w);
+    ptx::tmem_st8(a_addr + c / 2, w);
+  }
+}
+
+// skip mode "add" (ngm/models.py:162-169): relu(x + b) + encoding on the first E columns.  `enc` = the row's
+// pre-encoded fp16 features as half2 words (zero-padded to enc_words), nullptr for a padding row.
+__device__ __forceinline__ void add_words(uint32_t* w, const uint32_t* enc, int w0, int n, int enc_words) {
+  if (!enc) return;
+  for (int i = 0; i < n; i += 4) {
+    if (w0 + i >= enc_words) break;  // enc_words is a multiple of 8
+    const uint4 e = __ldg(reinterpret_cast<const uint4*>(enc + w0 + i));
+    const uint32_t ev[4] = {e.x, e.y, e.z, e.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __half2 r = __hadd2(*reinterpret_cast<const __half2*>(&w[i + j]), *reinterpret_cast<const __half2*>(&ev[j]));
+      w[i + j] = *reinterpret_cast<const uint32_t*>(&r);
+    }
+  }
+}
+
+__device__ __forceinline__ void hidden_epilogue_add(uint32_t d_addr, uint32_t a_addr, const uint32_t* bias2, int c0, int n,
+                                                    const uint32_t* enc, int enc_words) {
+  int c = c0;
+  const int end = c0 + n;
+  for (; c + 16 <= end; c += 16) {
+    uint32_t v[16];
+    ptx::tmem_ld16(d_addr + c, v);
+    ptx::tc_wait_ld();
+    uint32_t w[8];
+    cvt16(v, bias2 + c / 2, w);
+    add_words(w, enc, c / 2, 8, enc_words);
     ptx::tmem_st8(a_addr + c / 2, w);
   }
 }
@@ -522,7 +554,7 @@ __device__ __forceinline__ unsigned ev_id(int role, int slot, int phase, int lay
 __device__ __forceinline__ void issue_layer(uint32_t d_addr, uint32_t a_addr, uint64_t desc0, uint32_t atom_stride16,
                                             uint32_t idesc, int ksteps) {
 #pragma unroll
-  for (int ks = 0; ks < 8; ++ks) {
+  for (int ks = 0; ks < 12; ++ks) {  // K <= 192: 128 activations + 64 encoding features of skip mode "concat"
     if (ks < ksteps) {
       const uint64_t desc = desc0 + (uint64_t)((ks & 3) * 2u + (ks >> 2) * atom_stride16);
       ptx::mma_f16_ts(d_addr, a_addr + ks * 8, desc, idesc, ks > 0 ? 1u : 0u);
@@ -539,7 +571,9 @@ __device__ __forceinline__ void issue_layer(uint32_t d_addr, uint32_t a_addr, ui
 // slotted into the waits for the current tile's MMAs), h = 0 threads the COMPOSITOR of the current tile.
 // (A lockstep variant in which all 16 warps share every epilogue job of both slots was measured slower --
 // 3.85 ms vs 2.83 ms per frame -- because each duty then stalls all 512 threads; profiles/README.md.)
-template <int MODE, int OCT, bool TRACE, bool ACC16>
+// SKIP: 0 = no skip connection; 1 = "add", 2 = "concat" (ngm/models.py:160-170) -- only with pre-encoded rows
+// (p.raw_a): the encoding of a row is read back from them in the hidden epilogues
+template <int MODE, int OCT, bool TRACE, bool ACC16, int SKIP = 0>
 __global__ void __launch_bounds__(threads_of(MODE), 1) tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   // weights image first (1024-B aligned for SWIZZLE_128B), bookkeeping after it; plain pointer
@@ -578,6 +612,9 @@ __global__ void __launch_bounds__(threads_of(MODE), 1) tc_kernel(const __grid_co
   ptx::tc_fence_after();
   const uint32_t tmem_base = sm.tmem_base;
 
+  // "concat" keeps a tile's encoding right behind its activations (columns kACol + W/2 ..., up to kStageCol + 32) for
+  // all of its layers, so the next tile's layer-0 operand is staged in the spare columns behind that
+  constexpr uint32_t stage_col = SKIP == 2 ? kStageCol + 32 : kStageCol;
   // contiguous, balanced tile range of this CTA
   const bool gather = MODE == 1 && p.entries != nullptr;
   const long long total_tiles = gather ? (long long)__ldg(p.tile_offsets + p.num_fields) : p.total_tiles;
@@ -670,7 +707,7 @@ __global__ void __launch_bounds__(threads_of(MODE), 1) tc_kernel(const __grid_co
           const uint64_t desc0 = ptx::make_smem_desc_sw128(wsm_u + y.off);
           const uint32_t idesc = (ACC16 && l < L) ? ptx::make_idesc_f16_acc16(y.n_pad) : ptx::make_idesc_f16(y.n_pad);
           if (ptx::elect_one()) {
-            issue_layer(d_addr, l == 0 ? d_addr + kStageCol : a_addr, desc0, (uint32_t)y.n_pad * 8u, idesc, y.k_pad / 16);
+            issue_layer(d_addr, l == 0 ? d_addr + stage_col : a_addr, desc0, (uint32_t)y.n_pad * 8u, idesc, y.k_pad / 16);
             ptx::mma_commit(&sm.d_ready[s]);
           }
           __syncwarp();
@@ -695,10 +732,31 @@ __global__ void __launch_bounds__(threads_of(MODE), 1) tc_kernel(const __grid_co
       const int my_c0 = h ? w0 : 0, my_n = h ? W - w0 : w0;
       tev_role(2 + 2 * s + h, lane == 0 && qwarp == 2);  // one leader thread per half
 
-      const uint32_t a0_addr = d_addr + kStageCol;  // staging columns: layer-0 A operand of the NEXT tile
+      const uint32_t a0_addr = d_addr + stage_col;  // staging columns: layer-0 A operand of the NEXT tile
       // layer-0 A operand read from HBM (pre-encoded rows): compiled out of the fused NeRF renderer
       const bool raw = (MODE == 1 || OCT == 0) && p.raw_a != nullptr;
       float3 fx = make_float3(0.f, 0.f, 0.f);        // sample point of this row for the next tile (fe_a -> fe_b)
+      // skip connections: the pre-encoded row that fed this thread's row of tile `ti` (nullptr: padding row)
+      auto skip_row = [&](int ti) -> const uint32_t* {
+        long long rr;
+        bool valid;
+        if (MODE == 1) {
+          const long long gp = (tile0_in_field + ti) * 128 + row;
+          valid = gp < p.points_per_field;
+          rr = f * p.points_per_field + gp;
+          if (gather) {
+            const int e = __ldg(p.entry_offsets + f) + (int)gp;
+            valid = e < __ldg(p.entry_offsets + f + 1);
+            rr = valid ? __ldg(p.entries + e) : 0;
+          }
+        } else {
+          const long long r = (tile0_in_field + ti) * p.rpt + (row >> p.sp_shift);
+          const int k = row & (p.Sp - 1);
+          valid = r < p.rays_per_field && k < p.St;
+          rr = (f * p.rays_per_field + r) * p.St + k;
+        }
+        return valid ? reinterpret_cast<const uint32_t*>(p.raw_a + rr * p.EP) : nullptr;
+      };
 
       // Front end of tile `ti` (h == 1 threads), in two parts that are slotted into the waits for
       // the CURRENT tile's MMAs:  fe_a = sample point + row data,  fe_b = encoding -> staging -> arrive.
@@ -853,7 +911,27 @@ __global__ void __launch_bounds__(threads_of(MODE), 1) tc_kernel(const __grid_co
             if (l < L) {
               // ---------- hidden layer l (both halves) ----------
               tev(ev_id(1 + (h == 0), s, 3, l));
-              if (my_n > 0) {
+              if constexpr (SKIP != 0) {
+                const uint32_t* enc = skip_row(ti);
+                if (SKIP == 1) {
+                  if (my_n > 0) hidden_epilogue_add(d_addr, a_addr, bias2 + l * (W / 2), my_c0, my_n, enc, p.EP / 2);
+                } else {
+                  if (my_n > 0) hidden_epilogue(d_addr, a_addr, bias2 + l * (W / 2), my_c0, my_n);
+                  if (l == 0) {  // this tile's encoding behind its activations: words [W/2, W/2 + EP/2), 8 per step
+                    const int steps = p.EP / 16, s0 = h ? (steps + 1) / 2 : 0, s1 = h ? steps : (steps + 1) / 2;
+                    for (int q = s0; q < s1; ++q) {
+                      uint32_t wv[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+                      if (enc) {
+                        const uint4 e0 = __ldg(reinterpret_cast<const uint4*>(enc + q * 8));
+                        const uint4 e1 = __ldg(reinterpret_cast<const uint4*>(enc + q * 8 + 4));
+                        wv[0] = e0.x; wv[1] = e0.y; wv[2] = e0.z; wv[3] = e0.w;
+                        wv[4] = e1.x; wv[5] = e1.y; wv[6] = e1.z; wv[7] = e1.w;
+                      }
+                      ptx::tmem_st8(a_addr + W / 2 + q * 8, wv);
+                    }
+                  }
+                }
+              } else if (my_n > 0) {
                 if constexpr (ACC16) hidden_epilogue_acc16(d_addr, a_addr, bias2 + l * (W / 2), my_c0, my_n);
                 else                 hidden_epilogue(d_addr, a_addr, bias2 + l * (W / 2), my_c0, my_n);
               }
@@ -999,6 +1077,10 @@ int launch_tc(const TcParams& p_in, int octaves, size_t smem, int grid, cudaStre
     kernel<<<grid, threads_of(MODE), smem, stream>>>(p);
     return check_launch("tc_kernel");
   };
+  if (p.skip) {  // skip connections: pre-encoded rows only (field_tc_supported / tc_rows_required)
+    if (!p.raw_a) { set_error("tcgen05 path: skip connections need pre-encoded rows"); return NGM_ERR_UNSUPPORTED; }
+    return p.skip == 1 ? go(tc_kernel<MODE, 0, false, false, 1>) : go(tc_kernel<MODE, 0, false, false, 2>);
+  }
   if (p.acc16 && !p.trace) {  // 16-bit accumulation of the hidden layers (NGM_TC_ACC16=1)
     switch (octaves) {
       case 0: return go(tc_kernel<MODE, 0, false, true>);
@@ -1033,6 +1115,7 @@ int fill_common(TcParams& p, const NgmFieldDesc& fd, int num_fields, const float
   p.L = fd.num_layers;
   p.dim_out = fd.dim_out;
   p.nerf_start = fd.nerf_start_octave;
+  p.skip = fd.skip_mode == NGM_SKIP_ADD ? 1 : (fd.skip_mode == NGM_SKIP_CONCAT ? 2 : 0);
   if (fd.encoding == NGM_ENC_PERMUTO) {
     p.pm_table = fd.enc_param0; p.pm_table_stride = fd.enc_param0_stride;
     p.pm_shift = fd.enc_param1; p.pm_shift_stride = fd.enc_param1_stride;
@@ -1068,7 +1151,8 @@ size_t tc_smem_bytes(const TcImage& im) {
 // reach the kernel as pre-encoded fp16 rows.
 bool tc_rows_required(const NgmFieldDesc& fd) {
   return fd.encoding == NGM_ENC_FOURIER || fd.encoding == NGM_ENC_TRIPLANE ||
-         (fd.encoding == NGM_ENC_NERF && !nerf_octaves_supported(fd.nerf_num_octaves));
+         (fd.encoding == NGM_ENC_NERF && !nerf_octaves_supported(fd.nerf_num_octaves)) ||
+         fd.skip_mode == NGM_SKIP_ADD || fd.skip_mode == NGM_SKIP_CONCAT;  // the hidden epilogues re-read the encoding
 }
 
 bool field_tc_supported(const NgmFieldDesc& fd, const char** why) {
@@ -1081,7 +1165,8 @@ bool field_tc_supported(const NgmFieldDesc& fd, const char** why) {
     w = "pre-encoded rows: encoding wider than 64 features";  // (these encodings reach the kernel as fp16 rows)
   else if (fd.encoding == NGM_ENC_PERMUTO && fd.permuto_feats != 2) w = "permutohedral: nr_feat_per_level must be 2 on the tcgen05 path";
   else if (fd.encoding == NGM_ENC_PERMUTO && ep_of(fd) > 64) w = "permutohedral: encoding wider than 64 features";
-  else if (fd.skip_mode != NGM_SKIP_NO) w = "skip connections are only on the fp32 path";
+  else if (fd.skip_mode == NGM_SKIP_REZERO) w = "skip mode rezero is only on the fp32 path";
+  else if (fd.skip_mode != NGM_SKIP_NO && ep_of(fd) > 64) w = "skip connections: encoding wider than 64 features";
   else if (fd.dim_mlp_out % 16 != 0 || fd.dim_mlp_out < 16 || fd.dim_mlp_out > 128) w = "dim_mlp_out must be a multiple of 16 in [16,128]";
   else if (fd.dim_out > 128) w = "dim_out > 128";
   else if (make_image(fd, ep_of(fd)).total_bytes > kMaxImageBytes) w = "weight image exceeds shared memory (too many layers)";

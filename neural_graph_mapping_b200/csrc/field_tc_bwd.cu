@@ -777,7 +777,8 @@ int bwd_phases_read(unsigned long long* out16) {
 bool field_bwd_tc_supported(const NgmFieldDesc& fd, const char** why) {
   const char* w = nullptr;
   if (!field_tc_supported(fd, &w)) { if (why) *why = w; return false; }
-  if (fd.num_layers < 1 || fd.num_layers > 4) w = "tcgen05 backward: num_layers must be in [1, 4]";
+  if (fd.skip_mode != NGM_SKIP_NO) w = "tcgen05 backward: skip connections are differentiated on the fp32 path";
+  else if (fd.num_layers < 1 || fd.num_layers > 4) w = "tcgen05 backward: num_layers must be in [1, 4]";
   else if (fd.dim_out > 8) w = "tcgen05 backward: dim_out must be <= 8";
   else if (fd.dim_mlp_out % 32 != 0) w = "tcgen05 backward: dim_mlp_out must be a multiple of 32";
   else {

@@ -32,7 +32,8 @@ inline TcImage make_image(const NgmFieldDesc& fd, int EP) {
   for (int l = 0; l <= L; ++l) {
     TcLayer& y = im.layer[l];
     y.n_pad = l == L ? (fd.dim_out + 15) / 16 * 16 : W;
-    y.k_pad = l == 0 ? EP : W;
+    // skip mode "concat" (ngm/models.py:160-161): every linear after the first reads [activations | encoding]
+    y.k_pad = l == 0 ? EP : (fd.skip_mode == NGM_SKIP_CONCAT ? W + EP : W);
     y.atoms = (y.k_pad + 63) / 64;
     y.off = off;
     off += (uint32_t)y.atoms * y.n_pad * 128;
@@ -64,7 +65,7 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(PackParams p) {
   for (int l = 0; l <= L; ++l) {
     const TcLayer y = p.im.layer[l];
     const int N = l == L ? p.fd.dim_out : W;
-    const int K = l == 0 ? p.E : W;
+    const int K = l == 0 ? p.E : (p.fd.skip_mode == NGM_SKIP_CONCAT ? W + p.E : W);
     const float* Wg = p.fd.weights[l] + slot * p.fd.weight_stride[l];
     const int chunks = y.atoms * y.n_pad * 8;  // 16-byte chunks (8 halves)
     for (int c = threadIdx.x; c < chunks; c += blockDim.x) {

@@ -426,3 +426,112 @@ def test_row_encoded_fields_fp16(kind, enc_cls, ekw):
     assert (p16.rgbds[..., :3] - p32.rgbds[..., :3]).abs().mean().item() < 2e-3
     assert (p16.rgbds[..., 3] - p32.rgbds[..., 3]).abs().mean().item() < 5e-3
     assert (p16.term_probs - p32.term_probs).abs().mean().item() < 3e-3
+
+
+# ---- skip connections "add" / "concat" on the tcgen05 path (ngm/models.py:160-170) ----
+
+def test_field_fwd_fp16_skip_add_golden():
+    """The reference's own output of a NeRF-4 field with skip_mode "add" (2 x 48), through the tcgen05 kernel; and the
+    concat golden (width 40, not a multiple of 16) must be refused loudly rather than silently run elsewhere."""
+    meta, a = G.load("fields_forward")
+    name = "nerf4_add"
+    fk = meta["variants"][name]["field_kwargs"]
+    assert fk["skip_mode"] == "add"
+    f16 = _field(fk, "fp16")
+    f16.load_state_dict({k: v.to(DEV) for k, v in G.params(a, prefix=f"{name}:param:").items()}, strict=False)
+    with torch.no_grad():
+        y16 = f16(a[f"{name}:x"].to(DEV))
+    ref = a[f"{name}:y"]
+    scale = ref.abs().max().item()
+    e = (y16.cpu() - ref).abs()
+    assert e.max().item() < 2e-2 * scale and e.mean().item() < 3e-3 * scale, (e.max().item(), e.mean().item(), scale)
+    fk = meta["variants"]["nerf4_concat"]["field_kwargs"]
+    bad = _field(fk, "fp16")
+    bad.load_state_dict({k: v.to(DEV) for k, v in G.params(a, prefix="nerf4_concat:param:").items()}, strict=False)
+    with pytest.raises(NotImplementedError), torch.no_grad():
+        bad(a["nerf4_concat:x"].to(DEV))
+
+
+@pytest.mark.parametrize("skip", ["add", "concat"])
+@pytest.mark.parametrize("W,L,O,n", [(32, 2, 4, 1000), (128, 3, 8, 700), (64, 1, 8, 129), (128, 4, 4, 2500)])
+def test_fieldset_fp16_skip_vs_oracle(skip, W, L, O, n):
+    """Stacked fields with skip connections on the tcgen05 kernel (pre-encoded rows; "concat" widens K of every linear
+    after the first to W + E) against the oracle: tile tails, several fields, widths 32..128."""
+    import neural_graph_mapping_b200 as ngm
+
+    g = torch.Generator().manual_seed(W * 7 + L + (1 if skip == "add" else 2))
+    F = 4
+    spec = R.FieldSpec("nerf", {"dim_in": 3, "num_octaves": O}, L, 4, W, skip)
+    params = R.stack_params([R.init_field_params(spec, g) for _ in range(F)])
+    pos = torch.randn(F, 3, generator=g)
+    q = torch.randn(F, 4, generator=g)
+    ori = q / q.norm(dim=-1, keepdim=True)
+    pts = pos[:, None] + torch.rand(F, n, 3, generator=g) * 1.6 - 0.8
+    rs = R.RenderSpec(field_radius=1.0, scale_mode="unit_cube")
+    ref = R.fieldset_forward_vmap(pts, pos, ori, spec, params, rs)
+    model = ngm.NeuralFieldSet(3, "neural_graph_mapping_b200.models.NeuralField",
+                               {"encoding_type": "neural_graph_mapping_b200.positional_encodings.PositionalEncodingNeRF",
+                                "encoding_kwargs": {"dim_in": 3, "num_octaves": O}, "num_layers": L, "dim_out": 4,
+                                "dim_mlp_out": W, "skip_mode": skip}, 2, 10.0, 1.0, field_radius=1.0,
+                               scale_mode="unit_cube", precision="fp16").to(DEV)
+    model.all_fields_params = {k: v.to(DEV) for k, v in params.items()}
+    model.set_vmap_fields(None)
+    with torch.no_grad():
+        y = model(pts.to(DEV), pos.to(DEV), ori.to(DEV), None, True)
+    scale = ref.abs().max().item()
+    e = (y.cpu() - ref).abs()
+    assert e.max().item() < 2e-2 * scale and e.mean().item() < 3e-3 * scale, (skip, e.max().item(), e.mean().item(), scale)
+    # the kNN blend path runs the same kernel in gather mode
+    rs2 = R.RenderSpec(field_radius=1.0, scale_mode="unit_cube", num_knn=2, distance_factor=10.0, outside_value=1.0)
+    q_pts = pts.reshape(-1, 3)[:: max(1, (F * n) // 1500)]
+    fid = torch.arange(F)
+    ref_k = R.fieldset_forward_knn(q_pts, pos, ori, fid, spec, params, rs2)
+    with torch.no_grad():
+        y_k = model(q_pts.to(DEV), pos.to(DEV), ori.to(DEV), fid.to(DEV), False)
+    d = torch.sort(torch.cdist(q_pts, pos), dim=-1)[0]
+    margin = ((d[:, 1] - d[:, 0]).abs() > 1e-5) & ((d[:, 0] - 1.0).abs() > 1e-5)
+    if F > 2:
+        margin &= (d[:, 2] - d[:, 1]).abs() > 1e-5
+    e = (y_k.cpu()[margin] - ref_k[margin]).abs()
+    assert e.max().item() < 2e-2 * scale and e.mean().item() < 3e-3 * scale, (skip, "knn", e.max().item(), e.mean().item())
+
+
+@pytest.mark.parametrize("skip", ["add", "concat"])
+def test_render_fused_fp16_skip_vs_fp32(skip):
+    """The fused tcgen05 renderer with skip connections (sampler -> row encoder -> fused kernel, like the
+    permutohedral path) against the fp32 kernels on identical rays and jitter."""
+    import neural_graph_mapping_b200 as ngm
+
+    L, W, S = 3, 64, 24
+    meta, a = G.load("vmap_guided_nrgbd")
+    g = torch.Generator().manual_seed(77)
+    F, Rr = 3, 300
+    ekw = {"dim_in": 3, "num_octaves": 8}
+    spec = R.FieldSpec("nerf", dict(ekw), L, 4, W, skip)
+    params = R.stack_params([R.init_field_params(spec, g) for _ in range(F)])
+    params[f"_linears.{L}.weight"][:, 3] *= 3.0
+    params[f"_linears.{L}.bias"][:, 3] += 0.3
+    fk = {"encoding_type": "neural_graph_mapping.positional_encodings.PositionalEncodingNeRF", "encoding_kwargs": dict(ekw),
+          "num_layers": L, "dim_out": 4, "dim_mlp_out": W, "skip_mode": skip, "initial_geometry_bias": 0.0,
+          "neus_initial_sd": 1.0}
+    meta = dict(meta, num_samples=S, num_samples_depth_guided=0, field_kwargs=fk)
+    arrays = {f"param:{k}": v for k, v in params.items()}
+    arrays["positions"], arrays["orientations"] = a["positions"][:F], a["orientations"][:F]
+    ijs = torch.stack([torch.randint(0, 480, (F, Rr), generator=g), torch.randint(0, 640, (F, Rr), generator=g)], -1)
+    near = torch.rand(F, Rr, generator=g) * 0.5 + 0.3
+    far = near + 1.5
+    jit = torch.rand(F, Rr, S, generator=g)
+    cam = ngm.Camera(**meta["camera"])
+    outs = {}
+    for prec in ("fp32", "fp16"):
+        st = make_state(meta, arrays, DEV, prec)
+        with torch.no_grad():
+            outs[prec] = st._render_ijs(ijs.to(DEV), a["c2ws"][:F, :1].expand(F, Rr, 4, 4).to(DEV), cam,
+                                        torch.arange(F, device=DEV), True, near.to(DEV), far.to(DEV), None,
+                                        jitter=jit.to(DEV))
+    p32, p16 = outs["fp32"], outs["fp16"]
+    assert torch.isfinite(p16.rgbds).all()
+    assert (p16.rgbds[..., :3] - p32.rgbds[..., :3]).abs().mean().item() < 2e-3
+    assert (p16.rgbds[..., 3] - p32.rgbds[..., 3]).abs().mean().item() < 5e-3
+    assert (p16.term_probs - p32.term_probs).abs().mean().item() < 3e-3
+    assert p32.term_probs.std().item() > 1e-3, "degenerate scene: the comparison would be vacuous"

@@ -48,7 +48,8 @@ def test_stream_depth_is_on_the_analytic_surfaces():
 def test_field_growth_covers_the_depth_image_once():
     loop, cam, stream = _setup()
     item = stream.frame(0)
-    n0 = loop._extend_global_map_dict(item["rgbd"][..., 3], 0, item["c2w"])
+    shift = torch.tensor([0.3, 0.7, 0.5])
+    n0 = loop._extend_global_map_dict(item["rgbd"][..., 3], 0, item["c2w"], shift=shift)
     assert n0 > 0 and loop._num_fields == n0
     g = loop._global_map_dict
     pos = g["positions"][:n0]
@@ -58,16 +59,18 @@ def test_field_growth_covers_the_depth_image_once():
     fx, fy, cx, cy, _ = cam.get_pinhole_camera_parameters(0.0)
     pc = torch.stack(((ij[:, 1].float() - cx) / fx * z, -(ij[:, 0].float() - cy) / fy * z, -z), -1)
     pw = pc @ item["c2w"][:3, :3].T + item["c2w"][:3, 3]
-    assert torch.cdist(pw, pos).min(dim=-1)[0].max().item() <= 1.0 + 1e-4
-    # grid cells are distinct, orientations are identity quaternions, bookkeeping and parameter tables grew together
+    # -- up to the reference's own cell-centre formula, (ijk - shift + 0.5) * cell (run_mapping.py:325, mirrored as it
+    # is): it displaces every centre by shift * (cell - 1) from the centre of the cell the points were binned into
     cell = 2 * 1.0 / math.sqrt(3)
+    assert torch.cdist(pw, pos).min(dim=-1)[0].max().item() <= 1.0 + (cell - 1.0) * shift.norm().item() + 1e-4
+    # grid cells are distinct, orientations are identity quaternions, bookkeeping and parameter tables grew together
     assert torch.cdist(pos, pos).fill_diagonal_(9.0).min().item() > 0.99 * cell
     assert torch.equal(g["orientations"][:n0], torch.tensor([1.0, 0, 0, 0]).expand(n0, 4))
     assert (g["kf_ids"][:n0] == 0).all() and g["positions"].shape[0] >= n0
     assert all(v.shape[0] == n0 for v in loop._model.all_fields_params.values())
     assert all(s["exp_avg"].shape[0] == n0 for s in loop._optim_state.values())
     # the same frame again adds nothing; a later keyframe adds only what it newly sees and keeps the old rows
-    assert loop._extend_global_map_dict(item["rgbd"][..., 3], 0, item["c2w"]) == 0
+    assert loop._extend_global_map_dict(item["rgbd"][..., 3], 0, item["c2w"], shift=shift) == 0
     before = pos.clone()
     loop._optim_state["_linears.0.weight"]["exp_avg"][:] = 0.5
     item2 = stream.frame(12)
