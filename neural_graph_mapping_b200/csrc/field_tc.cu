@@ -551,11 +551,20 @@ __device__ __forceinline__ unsigned ev_id(int role, int slot, int phase, int lay
 }
 
 // all operands warp-uniform -> the compiler keeps them in uniform registers and issues UTCHMMA directly
+// KS = most K-steps of 16 a layer can have: 8 (K <= 128), or 12 with skip mode "concat" (128 activations + 64 encoding
+// features).  A template parameter: the four extra predicated-off steps cost the default kernel 3.5 % when the bound
+// was simply raised (the issue loop sits on the kernel's critical path).
+template <int KS, bool EXACT = false>
 __device__ __forceinline__ void issue_layer(uint32_t d_addr, uint32_t a_addr, uint64_t desc0, uint32_t atom_stride16,
                                             uint32_t idesc, int ksteps) {
+  if constexpr (!EXACT) {  // the common depths without the per-step predicate
+    if (ksteps == 8 && KS >= 8) { issue_layer<8, true>(d_addr, a_addr, desc0, atom_stride16, idesc, 8); return; }
+    if (ksteps == 4) { issue_layer<4, true>(d_addr, a_addr, desc0, atom_stride16, idesc, 4); return; }
+    if (ksteps == 3) { issue_layer<3, true>(d_addr, a_addr, desc0, atom_stride16, idesc, 3); return; }
+  }
 #pragma unroll
-  for (int ks = 0; ks < 12; ++ks) {  // K <= 192: 128 activations + 64 encoding features of skip mode "concat"
-    if (ks < ksteps) {
+  for (int ks = 0; ks < KS; ++ks) {
+    if (EXACT || ks < ksteps) {
       const uint64_t desc = desc0 + (uint64_t)((ks & 3) * 2u + (ks >> 2) * atom_stride16);
       ptx::mma_f16_ts(d_addr, a_addr + ks * 8, desc, idesc, ks > 0 ? 1u : 0u);
     }
@@ -707,7 +716,8 @@ __global__ void __launch_bounds__(threads_of(MODE), 1) tc_kernel(const __grid_co
           const uint64_t desc0 = ptx::make_smem_desc_sw128(wsm_u + y.off);
           const uint32_t idesc = (ACC16 && l < L) ? ptx::make_idesc_f16_acc16(y.n_pad) : ptx::make_idesc_f16(y.n_pad);
           if (ptx::elect_one()) {
-            issue_layer(d_addr, l == 0 ? d_addr + stage_col : a_addr, desc0, (uint32_t)y.n_pad * 8u, idesc, y.k_pad / 16);
+            issue_layer<SKIP == 2 ? 12 : 8>(d_addr, l == 0 ? d_addr + stage_col : a_addr, desc0, (uint32_t)y.n_pad * 8u, idesc,
+                                            y.k_pad / 16);
             ptx::mma_commit(&sm.d_ready[s]);
           }
           __syncwarp();
