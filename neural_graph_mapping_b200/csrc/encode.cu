@@ -136,22 +136,22 @@ __global__ void __launch_bounds__(256) permuto_rows_f32_kernel(PermutoRowsArgs a
 
 __global__ void __launch_bounds__(256) permuto_rows_half_kernel(PermutoRowsArgs a) {
   const NgmFieldDesc& fd = a.field;
-  const int L = fd.permuto_levels, groups = (L + 3) / 4, words = a.EP / 2;
+  const int L = fd.permuto_levels, words = a.EP / 2;
   const size_t level_elems = ((size_t)1 << fd.permuto_log2_capacity) * 2;
-  const long long total = a.num_points * groups;
-  // Lane mapping: consecutive lanes = consecutive points (neighbouring samples of a ray) of ONE group of 4 levels.
-  // On the coarse levels neighbouring samples fall into the same or adjacent simplices, so the lanes of a gather
-  // instruction hit the same 32-byte sectors and the request count drops; with (point, group) interleaved across
-  // lanes every lane of an instruction reads a different level's table (ncu: 2.1 L2 sectors per vertex).
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(idx / a.num_points);
-    const long long pt = idx - (long long)g * a.num_points;
-    long long f = pt / a.points_per_field, src_pt = pt;
+  // One thread per point, all levels in turn (4 per step, one 16-byte store each): the lanes of a warp are
+  // neighbouring samples of a ray working on the SAME level, so on the coarse levels they hit the same 32-byte sectors,
+  // and the world -> local transform, the index arithmetic and the row address are paid once per point instead of
+  // once per (point, 4 levels) -- the encoder is bound by instruction issue (ncu: 82 % issue active).  The four
+  // 16-byte stores of a row follow each other closely, so L2 merges them into whole sectors.
+  for (long long pt = blockIdx.x * (long long)blockDim.x + threadIdx.x; pt < a.num_points;
+       pt += (long long)gridDim.x * blockDim.x) {
+    long long f, src_pt = pt;
     if (a.pair_field) {
       f = __ldg(a.pair_field + pt);
       if (f < 0) continue;
       src_pt = pt / a.knn_k;
+    } else {
+      f = a.num_points < (1ll << 31) ? (long long)((unsigned)pt / (unsigned)a.points_per_field) : pt / a.points_per_field;
     }
     const long long slot = a.field_slots ? a.field_slots[f] : f;
     const long long pose = a.pair_field ? f : slot;
@@ -166,31 +166,34 @@ __global__ void __launch_bounds__(256) permuto_rows_half_kernel(PermutoRowsArgs 
     const float* table = fd.enc_param0 + slot * fd.enc_param0_stride;
     const float* shift = fd.enc_param1 + slot * fd.enc_param1_stride;
     uint32_t* row = a.out + pt * words;
-    uint32_t w[4] = {0u, 0u, 0u, 0u};
+    const bool vec_ok = (words & 3) == 0;
+#pragma unroll 1
+    for (int l0 = 0; l0 < L; l0 += 4) {
+      uint32_t w[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int l = 4 * g + i;
-      if (l < L) {
-        float f2[2];
-        permuto_level<2>(xs, table + (size_t)l * level_elems, shift + l * 3, fd.permuto_scale + l * 3,
-                         fd.permuto_log2_capacity, 2, f2);
-        const __half2 h = __floats2half2_rn(f2[0], f2[1]);
-        w[i] = *reinterpret_cast<const uint32_t*>(&h);
+      for (int i = 0; i < 4; ++i) {
+        const int l = l0 + i;
+        if (l < L) {
+          float f2[2];
+          permuto_level<2>(xs, table + (size_t)l * level_elems, shift + l * 3, fd.permuto_scale + l * 3,
+                           fd.permuto_log2_capacity, 2, f2);
+          const __half2 h = __floats2half2_rn(f2[0], f2[1]);
+          w[i] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+      }
+      if (l0 + 4 <= L && vec_ok) {
+        *reinterpret_cast<uint4*>(row + l0) = make_uint4(w[0], w[1], w[2], w[3]);
+      } else {
+        for (int i = 0; i < 4 && l0 + i < L; ++i) row[l0 + i] = w[i];
       }
     }
-    if (4 * g + 4 <= L && (words & 3) == 0) {
-      *reinterpret_cast<uint4*>(row + 4 * g) = make_uint4(w[0], w[1], w[2], w[3]);
-    } else {
-      for (int i = 0; i < 4 && 4 * g + i < L; ++i) row[4 * g + i] = w[i];
-    }
-    if (g == groups - 1) {  // raw points (concat_points) and the zero padding up to the K multiple of 16
-      const float cs = fd.permuto_concat_scaling;
-      for (int k = L; k < words; ++k) {
-        __half2 h = __floats2half2_rn(0.f, 0.f);
-        if (fd.permuto_concat_points && k == L) h = __floats2half2_rn(x.x * cs, x.y * cs);
-        if (fd.permuto_concat_points && k == L + 1) h = __floats2half2_rn(x.z * cs, 0.f);
-        row[k] = *reinterpret_cast<const uint32_t*>(&h);
-      }
+    // raw points (concat_points) and the zero padding up to the K multiple of 16
+    const float cs = fd.permuto_concat_scaling;
+    for (int k = L; k < words; ++k) {
+      __half2 h = __floats2half2_rn(0.f, 0.f);
+      if (fd.permuto_concat_points && k == L) h = __floats2half2_rn(x.x * cs, x.y * cs);
+      if (fd.permuto_concat_points && k == L + 1) h = __floats2half2_rn(x.z * cs, 0.f);
+      row[k] = *reinterpret_cast<const uint32_t*>(&h);
     }
   }
 }
@@ -280,7 +283,7 @@ int launch_permuto_rows_half(const PermutoRowsArgs& a, cudaStream_t stream) {
     feature_rows_half_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, stream>>>(a);
     return check_launch("feature_rows_half_kernel");
   }
-  const long long items = a.num_points * ((a.field.permuto_levels + 3) / 4);
+  const long long items = a.num_points;
   long long blocks = (items + 255) / 256;
   const long long cap = (long long)num_sms() * 64;  // 8 resident CTAs per SM x 8 rounds, then grid-stride
   permuto_rows_half_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, stream>>>(a);
