@@ -37,7 +37,7 @@ def _source_hash(extra: str = "") -> str:
     for f in files:
         path = f if os.path.isabs(f) else os.path.join(CSRC, f)
         if os.path.isfile(path):
-            h.update(path.encode())
+            h.update(os.path.basename(path).encode())  # not the absolute path: the tree is copied to other boxes
             h.update(open(path, "rb").read())
     h.update(" ".join(NVCC_FLAGS).encode())
     return h.hexdigest()
@@ -49,8 +49,27 @@ def build(force: bool = False, verbose: bool = False, debug: bool = False) -> st
     lib_path, stamp = (DEBUG_LIB_PATH, DEBUG_STAMP) if debug else (LIB_PATH, STAMP)
     defines = ["-DNGM_DEBUG_EXPORTS"] if debug else []
     want = _source_hash(" ".join(defines))
-    if not force and os.path.exists(lib_path) and os.path.exists(stamp) and open(stamp).read() == want:
+
+    def fresh() -> bool:
+        return os.path.exists(lib_path) and os.path.exists(stamp) and open(stamp).read() == want
+
+    if not force and fresh():
         return lib_path
+    # One builder at a time per tree: under torch.distributed.run every rank calls build(); the others wait on the
+    # lock and then find the stamp fresh (concurrent nvcc runs into one object directory corrupt each other's files).
+    import fcntl
+
+    with open(lib_path + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and fresh():
+                return lib_path
+            return _build_locked(lib_path, stamp, defines, want, debug, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(lib_path: str, stamp: str, defines, want: str, debug: bool, verbose: bool) -> str:
     nvcc = _nvcc()
     objdir = os.path.join(PKG_DIR, "build_debug" if debug else "build")
     os.makedirs(objdir, exist_ok=True)
@@ -66,10 +85,12 @@ def build(force: bool = False, verbose: bool = False, debug: bool = False) -> st
         if p.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}:\n{out}")
         objs.append(obj)
-    link = [nvcc, "-shared", "-o", lib_path, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+    tmp_lib = lib_path + f".tmp{os.getpid()}"  # link beside the target, then rename: a reader never sees a partial file
+    link = [nvcc, "-shared", "-o", tmp_lib, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}")
+    os.replace(tmp_lib, lib_path)
     open(os.path.join(objdir, "build.log"), "w").write("\n".join(log))
     open(stamp, "w").write(want)
     if verbose:
