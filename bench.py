@@ -5,7 +5,8 @@ Workload (N=1): BASELINE.json configs[1] -- one 640x480 keyframe render, 64 samp
 4-layer x 128 MLP, NeRF-8 encoding (E=48): the 307,200 pixels pre-bucketed to 75 posed fields
 x 4,096 rays (SURVEY.md 8d, C2 primary).  One *step* = one full keyframe (307,200 rays,
 19,660,800 sample points).  N>1 (weak scaling): every rank renders one keyframe of its own and
-the rendered tiles (36 B/ray) are all-gathered over NCCL inside the step.
+the rendered tiles (36 B/ray) reach every rank inside the step (mirrored stores of the compositor kernel over
+NVSwitch, or an NCCL all-gather).  A step is three kernel launches: sample_rays -> tcgen05 field kernel -> compositor.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--precision auto|fp16|fp32]
     python bench.py --impl reference ...      # the CPU arm: oracle port of the reference path
@@ -385,7 +386,7 @@ def main():
     pending = [None, None]
     counter = [0]
 
-    # The exchange fused into the render kernel (distributed.TileExchange: mirrored stores over NVSwitch multicast /
+    # The exchange fused into the compositor kernel (distributed.TileExchange: mirrored stores over NVSwitch multicast /
     # NVLink peer memory + a signal-pad barrier) replaces the NCCL all-gather when symmetric memory is available AND
     # one step through it equals the NCCL all-gather of the same step bit for bit on every rank.
     ex_dev = ex_e2e = None
@@ -554,7 +555,7 @@ def main():
                 "rays_per_step_per_gpu": rays_per_step, "samples_per_ray": S, "precision": precision,
                 "l2": "flushed between timed iterations (256 MiB write)",
                 "parallelism": (f"rays sharded by keyframe x{world}; "
-                                + ("the rendered tiles reach every rank as mirrored stores of the render kernel itself "
+                                + ("the rendered tiles reach every rank as mirrored stores of the compositor kernel itself "
                                    "(symmetric memory over NVSwitch) + one signal-pad barrier per step on a side stream"
                                    if ex_dev is not None else
                                    "one NCCL all-gather of rendered tiles per step, left in flight behind the next "
@@ -605,7 +606,7 @@ def fused_exchange(distributed, st, dz, cam, dev, rays_per_step, nccl_bufs):
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)
     if int(ok.item()) != 1:
         raise RuntimeError("the fused exchange did not reproduce the NCCL all-gather bit for bit")
-    info = {"mode": "fused into the render kernel: mirrored Prediction stores over "
+    info = {"mode": "fused into the kernel that writes the Prediction (compositor stage): mirrored stores over "
                     + ("the NVSwitch multicast mapping" if ex_dev.multicast else "NVLink peer mappings")
                     + " of a symmetric tile buffer + signal-pad barrier",
             "multicast": bool(ex_dev.multicast), "mirrors_per_store": len(ex_dev.mirrors),
@@ -668,7 +669,7 @@ def run_extras(ngm, distributed, make_state, cam, dev, world, rank, precision, f
     st4 = make_state(precision, c4)
     d4 = {k: c4[k].to(dev) for k in ("ijs", "c2ws", "near", "far", "field_ids")}
     n4 = C4_FIELDS * C4_RAYS
-    how = ("tiles exchanged by the render kernel itself (distributed.TileExchange)" if fused
+    how = ("tiles exchanged by the compositor kernel itself (distributed.TileExchange)" if fused
            else "NCCL all-gather of the tiles")
     if C4_FIELDS % world == 0:
         seed_box = [0]
@@ -784,7 +785,8 @@ def run_extras(ngm, distributed, make_state, cam, dev, world, rank, precision, f
 
 def stage_breakdown(st, dz, cam, precision, steps, flush, full=True):
     """Per-kernel device time with CUDA events on the launching stream (torch's current stream).
-    fp32 path: the three stage kernels through the stage entry points; fp16 path: the fused kernel.
+    The three stage kernels through the stage entry points (fp32: FFMA field kernel, fp16: tcgen05 field kernel), the
+    whole step as `_render_ijs` runs it, and the opt-in single fused kernel.
     `full=False` (N > 1): only the dominant kernel."""
     import torch
 
@@ -881,28 +883,52 @@ def stage_breakdown(st, dz, cam, precision, steps, flush, full=True):
             stages["composite"] = {"bound": "hbm", "ms": t, "achieved": b / t / 1e6, "peak": peaks["hbm_gbs"],
                                    "unit": "GB/s", "frac": b / t / 1e6 / peaks["hbm_gbs"], "bytes_per_launch": b,
                                    "timing": how, "ms_single_launch_after_flush": t1}
+        else:
+            # N > 1: only the dominant kernel (the field stage), on the sampler's world points
+            _, _, world_pts, _ = sample_rays(cam, dz["ijs"], S, dz["near"], dz["far"], c2ws=dz["c2w"], seed=1, want_world=True,
+                                             want_depth=True, want_cam=False)
+            model = st._model
+            pos, ori = st._global_map_dict["positions"], st._global_map_dict["orientations"]
+            q = world_pts.view(F_FIELDS, R_RAYS * S, 3)
+            t = ev_time(lambda: models.field_forward(model._prototype_field, model.all_fields_params, True, q, pos, ori,
+                                                     dz["field_ids"], model._scale_mode, model._field_radius, precision))
+            stages["field_mlp"] = {"bound": "tensor", "ms": t, "achieved": fl / t / 1e9, "peak": peak, "unit": "TFLOP/s",
+                                   "frac": (fl / t / 1e9 / peak) if peak else None, "flops_per_launch": fl}
         if precision == "fp16":
-            # the product path: ONE fused tcgen05 kernel per render batch (sampler+encode+MLP+composite)
+            # the whole step as the public call runs it: sample_rays -> tcgen05 field kernel -> compositor
             t = ev_time(lambda: st._render_ijs(dz["ijs"], dz["c2w"], cam, dz["field_ids"], True, dz["near"], dz["far"]))
-            stages["render_fused"] = {"bound": "tensor", "ms": t, "achieved": fl / t / 1e9, "peak": peak,
-                                      "unit": "TFLOP/s", "frac": fl / t / 1e9 / peak, "flops_per_launch": fl,
-                                      "hbm_bytes_per_launch_algorithmic": n_rays * FUSED_BYTES_PER_RAY}
+            stages["render_step"] = {"bound": "tensor", "ms": t, "achieved": fl / t / 1e9, "peak": peak,
+                                     "unit": "TFLOP/s", "frac": fl / t / 1e9 / peak, "flops_per_launch": fl,
+                                     "kernels": "sample_rays_kernel + tc_kernel<1,8> + composite_staged_kernel"}
+            if full:
+                # the opt-in single fused kernel (NGM_RENDER_FUSED=1: sampler + encoding + MLP + compositor in one
+                # persistent tcgen05 kernel), for comparison
+                os.environ["NGM_RENDER_FUSED"] = "1"
+                try:
+                    t = ev_time(lambda: st._render_ijs(dz["ijs"], dz["c2w"], cam, dz["field_ids"], True, dz["near"], dz["far"]))
+                finally:
+                    os.environ.pop("NGM_RENDER_FUSED", None)
+                stages["render_single_fused_kernel_opt_in"] = {
+                    "bound": "tensor", "ms": t, "achieved": fl / t / 1e9, "peak": peak, "unit": "TFLOP/s",
+                    "frac": fl / t / 1e9 / peak, "flops_per_launch": fl,
+                    "hbm_bytes_per_launch_algorithmic": n_rays * FUSED_BYTES_PER_RAY}
     if precision == "fp16":
-        dom = dict(stages["render_fused"])
-        dom["kernel"] = "tc_kernel<0,8> fused render (tcgen05 MLP + sampler + composite)"
+        dom = dict(stages["field_mlp"])
+        dom["kernel"] = "tc_kernel<1,8> field stage (NeRF-8 encoding + 4x128 MLP on tcgen05; 93 % of the step's device time)"
+        dom["hbm_bytes_per_launch_algorithmic"] = points * (12 + 16)  # world point in, rgb + geometry out
     elif "field_mlp" in stages:
         dom = dict(stages["field_mlp"])
         dom["kernel"] = "field_fwd_simt_kernel (encode + MLP, fp32 FFMA)"
     else:
         dom = {"bound": "tensor", "kernel": "field_fwd_simt_kernel", "achieved": None, "peak": None, "unit": "TFLOP/s", "frac": None}
-    dom["traffic"] = ncu_traffic("tc_kernel<0" if precision == "fp16" else "field_fwd_simt_kernel")
+    dom["traffic"] = ncu_traffic("tc_kernel<1, 8" if precision == "fp16" else "field_fwd_simt_kernel")
     dom["traffic_source"] = "profiles/ ncu summary (committed ncu --set full capture of this kernel on this workload; not live)"
     return {"stages": stages, "dominant": dom}
 
 
 def ncu_traffic(kernel_substr):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch from the newest committed ncu summary (or None)."""
-    for name in ("r2_ncu_summary.json", "r1_ncu_summary.json"):
+    for name in ("r2_ncu_summary_final.json", "r2_ncu_summary.json", "r1_ncu_summary.json"):
         path = os.path.join(ROOT, "profiles", name)
         try:
             for k in json.load(open(path))["kernels"]:

@@ -177,6 +177,7 @@ typedef struct NgmFieldBwdArgs {
 /* ---- stage: compositor ---------------------------------------------------------------
  * Replaces the post-MLP split + masks (ngm/run_mapping.py:610-639) and
  * NeuralGraphMap._quadrature (ngm/run_mapping.py:709-799). */
+#define NGM_MAX_MIRRORS 8
 typedef struct NgmCompositeArgs {
   int64_t num_rays;
   const float* colors;      /* sample colours, element (r,s,c) at colors[(r*S+s)*color_stride + c] */
@@ -206,6 +207,13 @@ typedef struct NgmCompositeArgs {
   uint8_t* freespace_mask; /* (num_rays, S) */
   float* tsdf;             /* (num_rays, S): geometry*truncation - (gt - dist) (:633-637) */
   uint8_t* tsdf_mask;      /* (num_rays, S) */
+  /* multi-GPU tile exchange fused into the compositor (see NgmRenderArgs.mirror_delta): every store of rgbd,
+   * color_var, depth_var and term_prob is repeated at `ptr + mirror_delta[i]` bytes, i < num_mirrors, as coalesced
+   * 16-byte stores of a warp's 32 rays.  Needs the packed-input compositor (strides (4,4), S % 4 == 0, no weights /
+   * aux outputs). */
+  int64_t mirror_delta[NGM_MAX_MIRRORS];
+  int32_t num_mirrors;
+  int32_t _pad_m;
 } NgmCompositeArgs;
 
 /* ---- stage: positional encoding on its own ------------------------------------------------
@@ -345,7 +353,6 @@ typedef struct NgmObservedArgs {
  * Replaces NeuralGraphMap._render_ijs with use_vmap=True (ngm/run_mapping.py:440-666):
  * sampler -> world->local -> encoding -> per-field MLP -> compositor for
  * (num_fields x rays_per_field) rays, ray (f, r) being evaluated by field f only. */
-#define NGM_MAX_MIRRORS 8
 typedef struct NgmRenderArgs {
   NgmFieldDesc field;
   NgmCamera cam;
@@ -386,7 +393,8 @@ typedef struct NgmRenderArgs {
    * i < num_mirrors.  The deltas lead from this rank's tile inside a symmetric buffer to the same tile inside the
    * peers' copies of that buffer mapped into this process (NVLink peer memory: num_mirrors = world - 1), or to ONE
    * NVSwitch multicast mapping of it (num_mirrors = 1: the switch replicates the store to every rank).  The caller
-   * orders the readers (a barrier over the buffer's signal pads after the kernel).  Fused tcgen05 render only. */
+   * orders the readers (a barrier over the buffer's signal pads after the kernel).  Performed by the kernel that
+   * writes the Prediction: the compositor stage, or the single fused kernel (NGM_RENDER_FUSED=1). */
   int64_t mirror_delta[NGM_MAX_MIRRORS];
   int32_t num_mirrors;
   int32_t _pad2;

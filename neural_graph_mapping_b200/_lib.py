@@ -87,6 +87,7 @@ class NgmCompositeArgs(C.Structure):
         ("overwrite_behind_camera", C.c_int32), ("overwrite_gate", _fp),
         ("rgbd", _fp), ("color_var", _fp), ("depth_var", _fp), ("term_prob", _fp), ("weights", _fp),
         ("freespace", _fp), ("freespace_mask", _fp), ("tsdf", _fp), ("tsdf_mask", _fp),
+        ("mirror_delta", C.c_int64 * 8), ("num_mirrors", C.c_int32), ("_pad_m", C.c_int32),
     ]
 
 

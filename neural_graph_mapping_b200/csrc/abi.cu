@@ -140,8 +140,10 @@ static RenderWorkspace render_workspace(const NgmRenderArgs& a) {
   w.tc = off;
   if (a.precision == NGM_PREC_FP16) {
     off = align_up(off + field_tc_workspace_bytes(a.field, a.num_fields), 256);
-    if (!fused && tc_rows_required(a.field))  // staged path (> 128 samples per ray): rows of the dense field evaluation
-      off = align_up(off + n * ((size_t)(a.field.dim_encoding + 15) / 16 * 16) * 2, 256);
+    // staged path (> 128 samples per ray): rows of the dense field evaluation, when it encodes them itself
+    // (field_tc.cu: fwd_rows_from_encoder -- always for the permutohedral encoding unless NGM_TC_PERMUTO_INKERNEL=1)
+    if (!fused && (tc_rows_required(a.field) || a.field.encoding == NGM_ENC_PERMUTO))
+      off = align_up(off + n * ((size_t)(a.field.dim_encoding + 15) / 16 * 16) * 2 + 256, 256);
   }
   w.total = off;
   return w;
@@ -286,6 +288,10 @@ int ngm_composite(const NgmCompositeArgs* a, void* stream) {
   NGM_CHECK_ARG((a->freespace == nullptr) == (a->freespace_mask == nullptr), "freespace and its mask go together");
   NGM_CHECK_ARG((a->tsdf == nullptr) == (a->tsdf_mask == nullptr), "tsdf and its mask go together");
   NGM_CHECK_ARG(((uintptr_t)a->rgbd & 15) == 0, "rgbd must be 16-byte aligned");
+  NGM_CHECK_ARG(a->num_mirrors >= 0 && a->num_mirrors <= NGM_MAX_MIRRORS, "num_mirrors=%d outside [0, %d]", a->num_mirrors,
+                NGM_MAX_MIRRORS);
+  for (int i = 0; i < a->num_mirrors; ++i)
+    NGM_CHECK_ARG((a->mirror_delta[i] & 15) == 0, "mirror_delta[%d] must be a multiple of 16 bytes", i);
   return launch_composite(*a, (cudaStream_t)stream);
 }
 
@@ -504,8 +510,6 @@ int ngm_render_rays_fwd(const NgmRenderArgs* a, void* stream_) {
                 a->num_mirrors, NGM_MAX_MIRRORS);
   for (int i = 0; i < a->num_mirrors; ++i)
     NGM_CHECK_ARG((a->mirror_delta[i] & 15) == 0, "mirror_delta[%d] must be a multiple of 16 bytes", i);
-  NGM_UNSUPPORTED(a->num_mirrors > 0 && !fused,
-                  "mirrored Prediction stores exist in the fused tcgen05 render only (precision fp16, <= 128 samples)");
   if (fused && !precoded)  // one fused tcgen05 kernel per render batch
     return launch_render_fused_tc(*a, ws + w.tc, reinterpret_cast<float*>(ws + w.isd), nullptr, nullptr, nullptr, stream);
 
@@ -573,6 +577,8 @@ int ngm_render_rays_fwd(const NgmRenderArgs* a, void* stream_) {
   c.rgbd = a->rgbd; c.color_var = a->color_var; c.depth_var = a->depth_var; c.term_prob = a->term_prob;
   c.freespace = a->freespace; c.freespace_mask = a->freespace_mask;
   c.tsdf = a->tsdf; c.tsdf_mask = a->tsdf_mask;
+  c.num_mirrors = a->num_mirrors;  // the compositor writes the Prediction: it also repeats it for the peers
+  for (int i = 0; i < a->num_mirrors; ++i) c.mirror_delta[i] = a->mirror_delta[i];
   if (a->geometry_mode == NGM_GEOM_NEUS) {
     // neus_isds = 1 / |_neus_sd[field_ids]|  (run_mapping.py:641-644)
     float* isd = reinterpret_cast<float*>(ws + w.isd);

@@ -349,14 +349,50 @@ __global__ void __launch_bounds__(kStagedWarps * 32) composite_staged_kernel(Ngm
     if (chunk == nchunk - 1 && ray < a.num_rays) {
       const float P = acc.m[0], D = acc.m[1], C0 = acc.m[2], C1 = acc.m[3], C2 = acc.m[4];
       const float t2 = 2.0f - P;
-      reinterpret_cast<float4*>(a.rgbd)[ray] = make_float4(C0, C1, C2, D);
+      const float4 out4 = make_float4(C0, C1, C2, D);
+      const float dv = fmaxf(fmaf(-D * D, t2, acc.m[5]), 0.0f), tp = 1.0f - (1.0f - P);
+      reinterpret_cast<float4*>(a.rgbd)[ray] = out4;
       if (a.color_var) {
         a.color_var[ray * 3 + 0] = fmaxf(fmaf(-C0 * C0, t2, acc.m[6]), 0.0f);
         a.color_var[ray * 3 + 1] = fmaxf(fmaf(-C1 * C1, t2, acc.m[7]), 0.0f);
         a.color_var[ray * 3 + 2] = fmaxf(fmaf(-C2 * C2, t2, acc.m[8]), 0.0f);
       }
-      if (a.depth_var) a.depth_var[ray] = fmaxf(fmaf(-D * D, t2, acc.m[5]), 0.0f);
-      if (a.term_prob) a.term_prob[ray] = 1.0f - (1.0f - P);
+      if (a.depth_var) a.depth_var[ray] = dv;
+      if (a.term_prob) a.term_prob[ray] = tp;
+      // fused multi-GPU tile exchange (NgmCompositeArgs.mirror_delta): the warp's 32 rays again, into the peer /
+      // multicast mappings -- 512 B of rgbd and 128 B each of depth variance and termination probability straight from
+      // the registers (coalesced), the 384 B of colour variances re-read below as 16-byte pieces
+#pragma unroll
+      for (int m = 0; m < NGM_MAX_MIRRORS; ++m) {
+        if (m < a.num_mirrors) {
+          const long long dl = a.mirror_delta[m];
+          reinterpret_cast<float4*>(reinterpret_cast<char*>(a.rgbd) + dl)[ray] = out4;
+          if (a.depth_var) reinterpret_cast<float*>(reinterpret_cast<char*>(a.depth_var) + dl)[ray] = dv;
+          if (a.term_prob) reinterpret_cast<float*>(reinterpret_cast<char*>(a.term_prob) + dl)[ray] = tp;
+        }
+      }
+    }
+    if (chunk == nchunk - 1 && a.num_mirrors > 0 && a.color_var) {  // warp-uniform
+      __syncwarp();  // the warp's colour variances above are visible to all its lanes
+      const long long ray0 = ray - lane;
+      const long long n_valid = a.num_rays - ray0 < 32 ? a.num_rays - ray0 : 32;
+      float* cv = a.color_var + ray0 * 3;
+      if (n_valid == 32 && (reinterpret_cast<uintptr_t>(cv) & 15) == 0) {
+        if (lane < 24) {
+          const float4 v = __ldcg(reinterpret_cast<const float4*>(cv) + lane);
+#pragma unroll
+          for (int m = 0; m < NGM_MAX_MIRRORS; ++m)
+            if (m < a.num_mirrors)
+              reinterpret_cast<float4*>(reinterpret_cast<char*>(cv) + a.mirror_delta[m])[lane] = v;
+        }
+      } else {
+        for (int j = lane; j < n_valid * 3; j += 32) {
+          const float v = __ldcg(cv + j);
+#pragma unroll
+          for (int m = 0; m < NGM_MAX_MIRRORS; ++m)
+            if (m < a.num_mirrors) reinterpret_cast<float*>(reinterpret_cast<char*>(cv) + a.mirror_delta[m])[j] = v;
+        }
+      }
     }
   }
   cp_async_wait<0>();
@@ -413,6 +449,11 @@ int launch_composite(const NgmCompositeArgs& a, cudaStream_t stream) {
       case NGM_GEOM_NEUS: return launch_staged<NGM_GEOM_NEUS>(a, stream);
       default: break;
     }
+  }
+  if (a.num_mirrors > 0) {
+    set_error("mirrored Prediction stores need the packed-input compositor (strides (4,4), num_samples %% 4 == 0, 16-byte "
+              "aligned inputs, no weights / aux outputs, NGM_COMPOSITE_STAGED not 0)");
+    return NGM_ERR_UNSUPPORTED;
   }
   if (packed) composite_kernel<true><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, stream>>>(a);
   else composite_kernel<false><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, stream>>>(a);

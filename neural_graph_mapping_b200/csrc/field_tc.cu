@@ -1337,6 +1337,15 @@ int launch_neus_isd(const float* sd, const int64_t* slots, int num_fields, float
 bool render_fused_tc_ok(const NgmRenderArgs& a) {
   const int St = a.num_samples + (a.gt ? a.num_samples_guided : 0);
   const char* why;
+  {
+    // The single fused kernel (sampler + encoding + MLP + compositor in one persistent tcgen05 kernel) is opt-in:
+    // measured against the three stage kernels (sample_rays -> tcgen05 field kernel -> compositor) it is 13-22 %
+    // SLOWER at every MLP size (4 x 128 NeRF-8 keyframe: 2.71 against 2.32 ms) -- the compositor and the sampling front
+    // end lengthen the per-tile dependency chain of the slot threads by more than the ~1 GB of HBM round trips
+    // (0.18 ms) costs.  tools/fused_vs_staged.py, profiles/r2_fused_vs_staged.jsonl.  Read per call.
+    const char* e = getenv("NGM_RENDER_FUSED");
+    if (!(e && e[0] == '1')) return false;
+  }
   // num_layers >= 1: the deferred compositor runs in the waits of the hidden layers
   return a.precision == NGM_PREC_FP16 && St <= 128 && a.field.dim_out == 4 && a.field.num_layers >= 1 &&
          field_tc_supported(a.field, &why);

@@ -103,11 +103,11 @@ class _EventWork:
 
 
 class TileExchange:
-    """The tile exchange FUSED into the render kernel (replaces the NCCL all-gather).
+    """The tile exchange FUSED into the kernel that writes the Prediction (replaces the NCCL all-gather).
 
     A symmetric buffer of ``slots x world`` tiles (``torch.distributed._symmetric_memory``: the same allocation on
     every rank, each mapped into every process over NVLink, plus ONE NVSwitch multicast mapping where the fabric has
-    it).  Rank r renders straight into tile r of a slot and the fused kernel repeats each 36-byte Prediction store at
+    it).  Rank r renders straight into tile r of a slot and the compositor kernel (or the opt-in single fused kernel) repeats its Prediction stores at
     the byte offsets ``mirrors`` -- the multicast mapping (the switch replicates the store to all ranks) or, without
     multicast, the world-1 peer mappings -- so the transfer rides along with the math, ray by ray, and the exchange
     ends with a barrier over the buffer's signal pads instead of a collective.
@@ -193,7 +193,7 @@ def render_rays_gathered(driver, ijs, c2ws, camera, field_ids, near=None, far=No
     tiles of all ranks are all-gathered.  Returns the packed (world, 9*F*R) buffer, a PendingTiles
     (``async_gather``), or a list of per-rank ``Prediction`` views.  ``buffers`` = (local 9n, gathered world x 9n)
     preallocated tensors to reuse (a step loop double-buffers them).  ``exchange`` = a TileExchange: the
-    tiles travel as mirrored stores of the render kernel itself instead of an NCCL all-gather."""
+    tiles travel as mirrored stores of the compositor kernel itself instead of an NCCL all-gather."""
     F, R = ijs.shape[0], ijs.shape[1]
     n = F * R
     if exchange is not None:

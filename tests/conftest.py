@@ -34,3 +34,22 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+# The no-grad fp16 render has two pipelines: the three stage kernels (default) and the opt-in single fused kernel
+# (NGM_RENDER_FUSED=1).  The modules that exercise that render run every test under both.
+_BOTH_RENDER_PIPELINES = {"test_gpu_tc", "test_gpu_exchange", "test_gpu_hardening", "test_gpu_fullsize",
+                          "test_gpu_tc_multiround", "test_gpu_packed_weights", "test_gpu_edge_cases", "test_gpu_multi"}
+
+
+@pytest.fixture(autouse=True)
+def render_pipeline(request, monkeypatch):
+    mode = getattr(request, "param", None)
+    if mode is not None:
+        monkeypatch.setenv("NGM_RENDER_FUSED", "1" if mode == "fused" else "0")
+    yield mode
+
+
+def pytest_generate_tests(metafunc):
+    if metafunc.module.__name__.split(".")[-1] in _BOTH_RENDER_PIPELINES and "render_pipeline" in metafunc.fixturenames:
+        metafunc.parametrize("render_pipeline", ["stages", "fused"], indirect=True)

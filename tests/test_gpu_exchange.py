@@ -1,7 +1,8 @@
 """The multi-GPU tile exchange fused into the render kernel (`NgmRenderArgs.mirror_delta`, `distributed.TileExchange`):
 every Prediction store is repeated at byte offsets that lead to peer / multicast mappings of the same tile.
 
-* one GPU: a mirror that points at a second local buffer must receive exactly the rendered tile (the kernel side);
+* one GPU: a mirror that points at a second local buffer must receive exactly the rendered tile (the kernel side: the
+  compositor of the stage pipeline, and the opt-in single fused kernel -- every test runs under both, conftest.py);
 * two GPUs (skipped otherwise): the exchange equals the NCCL all-gather of the same step bit for bit, through the
   multicast mapping and through plain peer mappings, over more steps than the ring has slots."""
 import os
@@ -64,8 +65,11 @@ def test_mirrors_are_refused_where_they_do_not_exist():
     out = tuple(v.view(F, R, *v.shape[1:]) for v in D.packed_views(both[0], n))
     delta = both[1].data_ptr() - both[0].data_ptr()
     with torch.no_grad():
-        with pytest.raises(NotImplementedError):  # the staged fp32 path has no mirrored stores
-            render_rays(make_state(meta, a, dev, "fp32"), ijs, c2w, cam, fid, True, near, far, out=out, mirrors=[delta])
+        # the fp32 path ends in the same compositor kernel: mirrors work there too
+        render_rays(make_state(meta, a, dev, "fp32"), ijs, c2w, cam, fid, True, near, far, out=out, mirrors=[delta])
+        torch.cuda.synchronize()
+        assert torch.equal(both[1], both[0]) and both[0].abs().sum() > 0
+        both.zero_()
         st = make_state(meta, a, dev, "fp16")
         with pytest.raises(ValueError):  # 16-byte granularity of the rgbd vector store
             render_rays(st, ijs, c2w, cam, fid, True, near, far, out=out, mirrors=[delta + 4])
