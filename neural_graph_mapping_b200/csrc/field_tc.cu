@@ -1,10 +1,13 @@
 // fp16-operand tensor-core path (tcgen05 / TMEM / TMA-engine bulk copies), sm_100a only.
 //
-//   * render_fused: ONE kernel per render batch = sampler -> world->local -> NeRF encoding ->
-//     per-field MLP on tcgen05 -> front-to-back alpha composite (ngm/run_mapping.py:440-666,
-//     use_vmap=True).  HBM traffic is ~60 B/ray in + 36 B/ray out; the kernel is tensor-bound.
-//   * field_fwd: the same MLP pipeline with points read from HBM and raw outputs written back
-//     (ngm/models.py:329-345) -- the stage form, also used for St > 128.
+//   * field_fwd (MODE 1): points read from HBM -> world->local -> NeRF encoding -> per-field MLP on
+//     tcgen05 -> raw outputs written back (ngm/models.py:329-345).  THE PRODUCT PATH of a render:
+//     sample_rays_kernel -> this kernel -> composite_staged_kernel (0.60 of the burst cuBLAS rate on the
+//     headline keyframe); also the dense field evaluation and, in gather mode, the kNN path.
+//   * render_fused (MODE 0, opt-in: NGM_RENDER_FUSED=1): ONE kernel per render batch = sampler ->
+//     world->local -> NeRF encoding -> MLP -> front-to-back alpha composite (ngm/run_mapping.py:440-666,
+//     use_vmap=True), ~60 B/ray in + 36 B/ray out.  Measured 13-22 % slower than the three stage kernels
+//     (DESIGN.md 5): the in-kernel sampler and compositor lengthen the slot threads' dependency chain.
 //
 // Design (one persistent CTA per SM, 576 threads):
 //   warps 0 / 1     : MMA issuers of tile slot 0 / 1 (one elected lane issues tcgen05.mma after a
