@@ -467,6 +467,7 @@ def main():
     def timed_e2e(steps, warmup, n_streams):
         streams = [torch.cuda.Stream(device=dev) for _ in range(n_streams)]
         pend = [None, None]
+        rendered = [None]  # event after the previous step's last render kernel
 
         def one(i):
             b = i % 2
@@ -475,8 +476,18 @@ def main():
                     pend[b].wait()
                 d = {k: hz[k].to(dev, non_blocking=True) for k in hz}
                 flush.fill_(1)
+                # A step is three kernels.  With two streams the block scheduler may start step i+1's 2.2 ms field
+                # kernel before step i's compositor; on one or two GPUs that interleaving is harmless (measured: e2e
+                # 2.33 ms/step against 2.40 with the renders kept in step order), but it holds back step i's tile and
+                # with it every rank that waits for it in the exchange barrier -- at N = 8 the unordered loop ran at
+                # 2.91 ms/step against 2.40 device-timed.  So from N = 4 on the renders are kept in step order and only
+                # the copies overlap them.
+                if world > 2 and rendered[0] is not None:
+                    torch.cuda.current_stream().wait_event(rendered[0])
                 pend[b] = distributed.render_rays_gathered(st, d["ijs"], d["c2w"], cam, dz["field_ids"], d["near"], d["far"],
                                                            async_gather=True, buffers=e_bufs[b], exchange=ex_e2e)
+                rendered[0] = torch.cuda.Event()
+                rendered[0].record()
                 h_outs[b].copy_(pend[b].local, non_blocking=True)
 
         def finish():
