@@ -122,3 +122,21 @@ def test_product_does_not_import_oracle():
                 txt = open(os.path.join(dirpath, fn)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", txt, flags=re.M), fn
                 assert "/root/reference" not in txt or fn.endswith((".cu", ".cuh", ".h")), fn
+
+
+def test_build_stamp_does_not_depend_on_where_the_tree_lives(tmp_path, monkeypatch):
+    """The snapshot that travels to a GPU box lives under another path: the staleness hash of `_build.py` must be the
+    same there (otherwise every process on the box rebuilds the library -- and, under torch.distributed.run, all
+    ranks at once)."""
+    import shutil
+
+    from neural_graph_mapping_b200 import _build
+
+    here = _build._source_hash("x")
+    shutil.copytree(_build.CSRC, tmp_path / "elsewhere" / "csrc")
+    shutil.copytree(_build.INCLUDE, tmp_path / "elsewhere" / "include")
+    monkeypatch.setattr(_build, "CSRC", str(tmp_path / "elsewhere" / "csrc"))
+    monkeypatch.setattr(_build, "INCLUDE", str(tmp_path / "elsewhere" / "include"))
+    assert _build._source_hash("x") == here
+    (tmp_path / "elsewhere" / "csrc" / "knn.cu").write_text("// changed\n")
+    assert _build._source_hash("x") != here
