@@ -925,7 +925,7 @@ def stage_breakdown(st, dz, cam, precision, steps, flush, full=True):
                     "hbm_bytes_per_launch_algorithmic": n_rays * FUSED_BYTES_PER_RAY}
     if precision == "fp16":
         dom = dict(stages["field_mlp"])
-        dom["kernel"] = "tc_kernel<1,8> field stage (NeRF-8 encoding + 4x128 MLP on tcgen05; 93 % of the step's device time)"
+        dom["kernel"] = "tc_kernel<1,8> field stage (NeRF-8 encoding + 4x128 MLP on tcgen05; 92 % of the step's device time)"
         dom["hbm_bytes_per_launch_algorithmic"] = points * (12 + 16)  # world point in, rgb + geometry out
     elif "field_mlp" in stages:
         dom = dict(stages["field_mlp"])
