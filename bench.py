@@ -520,7 +520,8 @@ def main():
     e2e_ms = timed_e2e(args.steps, args.warmup, 2) / args.steps
     e2e_mode = ("2 CUDA streams, steps alternate: step i+1's H2D and step i-1's D2H overlap step i's render; every rank "
                 "copies its rays H2D and ITS OWN rendered tile D2H each step; the exchange of the tiles (config.parallelism) stays "
-                "in flight behind the next step; one device-timed bracket around all steps (L2 flushes included), max over ranks")
+                "in flight behind the next step; one device-timed bracket around all steps (L2 flushes included), max over ranks"
+                + ("; the renders of the two streams are kept in step order (only the copies overlap them)" if world > 2 else ""))
     e2e_value = world * rays_per_step / (e2e_ms / 1e3)
 
     # ---- roofline of the dominant kernel (field MLP; tensor-bound), measured live with events ----
